@@ -1,0 +1,690 @@
+// liblvc_b200.so -- C-ABI (include/lvc.h) over the sm_100a kernels.  No torch types, no CPU fallback.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/lvc.h"
+#include "lvc_common.cuh"
+#include "deposit_general.cuh"
+#include "deposit_tile.cuh"
+#include "genotype.cuh"
+
+using namespace lvc;
+
+static thread_local std::string g_create_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct lvc_handle {
+    int device = 0;
+    int64_t G = 0;
+    int min_bq = 0, min_mq = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    int impl = 0;
+    int sm_count = 148;
+    uint64_t launches = 0;
+    uint64_t ordinal = 0;
+    int qprim = 255;                         // primary quality of the current batch (tiled kernel)
+    uint8_t* h_sample = nullptr;             // pinned quality sample for device-resident batches
+
+    // persistent tables
+    uint8_t* d_ref = nullptr;
+    std::vector<uint32_t*> planes;           // device pointers, index = plane id
+    std::vector<uint16_t> plane_key;         // plane id -> key
+    uint16_t lut[kMaxKeys];
+    uint32_t** d_planes = nullptr;           // [kMaxKeys]
+    uint16_t* d_lut = nullptr;               // [kMaxKeys]
+    uint32_t* d_dels = nullptr;
+    int32_t* d_covdiff = nullptr;
+    uint32_t* d_first[4] = {nullptr, nullptr, nullptr, nullptr};
+    uint32_t** d_first_arr = nullptr;        // [4] device copy of d_first
+    uint32_t* d_newkeys = nullptr;           // [32]
+    uint32_t* d_replay = nullptr;            // [32]
+    uint32_t* d_status = nullptr;            // [ST_WORDS]
+    uint32_t* h_status = nullptr;            // pinned [ST_WORDS + 32]
+
+    // batch staging (device copies of host batches)
+    DevBuf b_pos, b_flag, b_mapq, b_keep, b_coff, b_cig, b_soff, b_seq, b_qual;
+    DevBuf b_defer;                          // deferred read list of the tiled kernel
+
+    // genotype
+    DevBuf g_order_ptrs, g_order_keys, g_cand;
+    double* d_elut = nullptr;                // [512] e, 1-e
+    uint32_t* d_out_depth = nullptr;
+    uint32_t* d_out_ad = nullptr;
+    double* d_out_lik = nullptr;
+    uint32_t* d_cand_count = nullptr;
+    uint32_t cand_cap = 0;
+    uint32_t last_cand_count = 0;
+};
+
+static int fail(lvc_handle* h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(h, LVC_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+static int ensure(lvc_handle* h, DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap && b.p) return LVC_OK;
+    size_t want = std::max<size_t>(bytes + bytes / 8, 256);
+    if (b.p) CU(cudaFree(b.p));
+    b.p = nullptr; b.cap = 0;
+    CU(cudaMalloc(&b.p, want));
+    b.cap = want;
+    return LVC_OK;
+}
+
+static TableView table_view(lvc_handle* h) {
+    TableView tv;
+    tv.G = h->G;
+    tv.planes = h->d_planes;
+    tv.lut = h->d_lut;
+    tv.dels = h->d_dels;
+    tv.covdiff = h->d_covdiff;
+    for (int g = 0; g < 4; ++g) tv.first[g] = h->d_first[g];
+    tv.newkeys = h->d_newkeys;
+    tv.status = h->d_status;
+    return tv;
+}
+
+// allocate a plane for `key` (and the group's first-seen table); uploads pointer + lut entry
+static int add_plane(lvc_handle* h, uint16_t key) {
+    if (key >= kMaxKeys) return fail(h, LVC_EINVAL, "plane key %u out of range", key);
+    if (h->lut[key] != kNoPlane) return LVC_OK;
+    const int g = key >> 8;
+    const size_t bytes = (size_t)h->G * 4 * sizeof(uint32_t);
+    if (!h->d_first[g]) {
+        CU(cudaMalloc(&h->d_first[g], bytes));
+        CU(cudaMemsetAsync(h->d_first[g], 0xFF, bytes, h->stream));
+        CU(cudaMemcpyAsync(h->d_first_arr + g, &h->d_first[g], sizeof(uint32_t*), cudaMemcpyHostToDevice, h->stream));
+    }
+    uint32_t* p = nullptr;
+    CU(cudaMalloc(&p, bytes));
+    CU(cudaMemsetAsync(p, 0, bytes, h->stream));
+    const uint16_t id = (uint16_t)h->planes.size();
+    h->planes.push_back(p);
+    h->plane_key.push_back(key);
+    h->lut[key] = id;
+    CU(cudaMemcpyAsync(h->d_planes + id, &h->planes[id], sizeof(uint32_t*), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_lut + key, &h->lut[key], sizeof(uint16_t), cudaMemcpyHostToDevice, h->stream));
+    // pageable sources: the runtime stages them before returning, so the host vectors may move later
+    return LVC_OK;
+}
+
+extern "C" {
+
+int lvc_version(void) { return 1; }
+
+const char* lvc_last_error(const lvc_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int lvc_create(lvc_handle** out, int device, int64_t ref_len, const uint8_t* ref_bytes, int min_base_quality,
+               int min_mapping_quality, void* stream) {
+    lvc_handle* h = nullptr;
+    if (!out || ref_len <= 0 || !ref_bytes) return fail(nullptr, LVC_EINVAL, "lvc_create: bad arguments");
+    if (min_base_quality < 0) min_base_quality = 0;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(nullptr, LVC_ENODEVICE, "lvc_create: no CUDA device visible; this library has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(nullptr, LVC_EINVAL, "lvc_create: device %d of %d", device, ndev);
+    h = new lvc_handle();
+    h->device = device;
+    h->G = ref_len;
+    h->min_bq = min_base_quality;
+    h->min_mq = min_mapping_quality;
+    for (int k = 0; k < kMaxKeys; ++k) h->lut[k] = kNoPlane;
+    auto body = [&]() -> int {
+        CU(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CU(cudaGetDeviceProperties(&prop, device));
+        h->sm_count = prop.multiProcessorCount;
+        if (stream) { h->stream = (cudaStream_t)stream; h->own_stream = false; }
+        else { CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
+        const size_t G = (size_t)ref_len;
+        CU(cudaMalloc(&h->d_ref, G));
+        CU(cudaMemcpyAsync(h->d_ref, ref_bytes, G, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMalloc(&h->d_planes, kMaxKeys * sizeof(uint32_t*)));
+        CU(cudaMemsetAsync(h->d_planes, 0, kMaxKeys * sizeof(uint32_t*), h->stream));
+        CU(cudaMalloc(&h->d_lut, kMaxKeys * sizeof(uint16_t)));
+        CU(cudaMemsetAsync(h->d_lut, 0xFF, kMaxKeys * sizeof(uint16_t), h->stream));
+        CU(cudaMalloc(&h->d_dels, G * sizeof(uint32_t)));
+        CU(cudaMemsetAsync(h->d_dels, 0, G * sizeof(uint32_t), h->stream));
+        CU(cudaMalloc(&h->d_covdiff, (G + 1) * sizeof(int32_t)));
+        CU(cudaMemsetAsync(h->d_covdiff, 0, (G + 1) * sizeof(int32_t), h->stream));
+        CU(cudaMalloc(&h->d_first_arr, 4 * sizeof(uint32_t*)));
+        CU(cudaMemsetAsync(h->d_first_arr, 0, 4 * sizeof(uint32_t*), h->stream));
+        CU(cudaMalloc(&h->d_newkeys, 32 * sizeof(uint32_t)));
+        CU(cudaMemsetAsync(h->d_newkeys, 0, 32 * sizeof(uint32_t), h->stream));
+        CU(cudaMalloc(&h->d_replay, 32 * sizeof(uint32_t)));
+        CU(cudaMemsetAsync(h->d_replay, 0, 32 * sizeof(uint32_t), h->stream));
+        CU(cudaMalloc(&h->d_status, ST_WORDS * sizeof(uint32_t)));
+        CU(cudaMemsetAsync(h->d_status, 0, ST_WORDS * sizeof(uint32_t), h->stream));
+        CU(cudaHostAlloc(&h->h_status, (ST_WORDS + 32) * sizeof(uint32_t), cudaHostAllocDefault));
+        CU(cudaMalloc(&h->d_elut, 512 * sizeof(double)));
+        CU(cudaMalloc(&h->d_out_depth, G * sizeof(uint32_t)));
+        CU(cudaMalloc(&h->d_out_ad, G * 4 * sizeof(uint32_t)));
+        CU(cudaMalloc(&h->d_out_lik, G * 4 * sizeof(double)));
+        CU(cudaMalloc(&h->d_cand_count, sizeof(uint32_t)));
+        CU(cudaMemsetAsync(h->d_cand_count, 0, sizeof(uint32_t), h->stream));
+        CU(cudaFuncSetAttribute(k_deposit_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
+        CU(cudaStreamSynchronize(h->stream));
+        return LVC_OK;
+    };
+    int rc = body();
+    if (rc != LVC_OK) {
+        g_create_error = h->err;
+        lvc_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return LVC_OK;
+}
+
+void lvc_destroy(lvc_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (auto p : h->planes) cudaFree(p);
+    for (int g = 0; g < 4; ++g) cudaFree(h->d_first[g]);
+    cudaFree(h->d_ref); cudaFree(h->d_planes); cudaFree(h->d_lut); cudaFree(h->d_dels); cudaFree(h->d_covdiff);
+    cudaFree(h->d_first_arr); cudaFree(h->d_newkeys); cudaFree(h->d_replay); cudaFree(h->d_status);
+    if (h->h_status) cudaFreeHost(h->h_status);
+    if (h->h_sample) cudaFreeHost(h->h_sample);
+    cudaFree(h->d_elut); cudaFree(h->d_out_depth); cudaFree(h->d_out_ad); cudaFree(h->d_out_lik);
+    cudaFree(h->d_cand_count);
+    for (DevBuf* b : {&h->b_pos, &h->b_flag, &h->b_mapq, &h->b_keep, &h->b_coff, &h->b_cig, &h->b_soff, &h->b_seq,
+                      &h->b_qual, &h->b_defer, &h->g_order_ptrs, &h->g_order_keys, &h->g_cand})
+        cudaFree(b->p);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int lvc_set_stream(lvc_handle* h, void* stream) {
+    if (!h) return LVC_EINVAL;
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    if (h->own_stream) { cudaStreamDestroy(h->stream); h->own_stream = false; }
+    if (stream) h->stream = (cudaStream_t)stream;
+    else { CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
+    return LVC_OK;
+}
+
+int lvc_sync(lvc_handle* h) {
+    if (!h) return LVC_EINVAL;
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    return LVC_OK;
+}
+
+int lvc_set_impl(lvc_handle* h, int impl) {
+    if (!h || impl < 0 || impl > 2) return LVC_EINVAL;
+    h->impl = impl;
+    return LVC_OK;
+}
+
+int lvc_reset(lvc_handle* h) {
+    if (!h) return LVC_EINVAL;
+    CU(cudaSetDevice(h->device));
+    const size_t G = (size_t)h->G;
+    for (auto p : h->planes) CU(cudaMemsetAsync(p, 0, G * 4 * sizeof(uint32_t), h->stream));
+    for (int g = 0; g < 4; ++g)
+        if (h->d_first[g]) CU(cudaMemsetAsync(h->d_first[g], 0xFF, G * 4 * sizeof(uint32_t), h->stream));
+    CU(cudaMemsetAsync(h->d_dels, 0, G * sizeof(uint32_t), h->stream));
+    CU(cudaMemsetAsync(h->d_covdiff, 0, (G + 1) * sizeof(int32_t), h->stream));
+    h->ordinal = 0;
+    CU(cudaStreamSynchronize(h->stream));
+    return LVC_OK;
+}
+
+void* lvc_host_alloc(uint64_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+void lvc_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+// ------------------------------------------------------------------------------------------------
+// host-side admission: SURVEY B2 (read filter) + B4 (htslib bam_plp_push maxcnt rule)
+// ------------------------------------------------------------------------------------------------
+int lvc_admit(uint32_t n, const int32_t* pos, const uint16_t* flag, const uint8_t* mapq, const uint32_t* cigar_off,
+              const uint32_t* cigar, int min_mq, int max_depth, uint8_t* keep) {
+    if (n && (!pos || !flag || !mapq || !cigar_off || !cigar || !keep)) return LVC_EINVAL;
+    // buffered-read end positions: ring of counters indexed by end position relative to a base
+    std::vector<uint32_t> ring;          // counts of buffered reads by end position
+    int64_t ring_base = 0;               // position of ring[0]
+    auto ring_add = [&](int64_t e, int64_t p) {
+        if (ring.empty()) { ring.assign(4096, 0); ring_base = p; }   // every later end is > p
+        if (e < ring_base) return;       // cannot happen (end > pos >= ring_base)
+        size_t off = (size_t)(e - ring_base);
+        if (off >= ring.size()) ring.resize(std::max(ring.size() * 2, off + 1), 0);
+        ring[off]++;
+    };
+    int64_t iter_pos = 0, max_pos = -1;
+    int64_t nbuf = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        keep[i] = 0;
+        const uint32_t f = flag[i];
+        if (f & kFlagFilter) continue;
+        if ((int)mapq[i] < min_mq) continue;
+        if ((f & 0x1u) && !(f & 0x2u)) continue;
+        int64_t rlen = 0;
+        for (uint32_t k = cigar_off[i]; k < cigar_off[i + 1]; ++k) {
+            const uint32_t op = cigar[k] & 15u;
+            if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) rlen += cigar[k] >> 4;
+        }
+        if (rlen == 0) continue;         // malformed: no reference-consuming op (htslib asserts)
+        const int64_t p = pos[i], e = p + rlen;
+        if (p < max_pos) return LVC_EUNSORTED;
+        if (p == iter_pos && nbuf + 1 > (int64_t)max_depth) continue;     // bam_plp_push: cnt > maxcnt
+        max_pos = p;
+        keep[i] = 1;
+        nbuf++;
+        ring_add(e, p);
+        // bam_plp_next: emit columns while max_pos > iter_pos; each built column frees ended reads
+        while (max_pos > iter_pos) {
+            const int64_t c = iter_pos;
+            if (!ring.empty() && c >= ring_base && (size_t)(c - ring_base) < ring.size()) {
+                nbuf -= ring[(size_t)(c - ring_base)];
+                ring[(size_t)(c - ring_base)] = 0;
+            }
+            if (nbuf - 1 == 0) iter_pos = max_pos;     // only the new read is buffered: jump to it
+            else iter_pos = c + 1;
+        }
+        // slide the ring so it does not grow with the genome
+        if (!ring.empty() && iter_pos - ring_base > (int64_t)ring.size() / 2) {
+            const size_t shift = (size_t)(iter_pos - ring_base);
+            if (shift >= ring.size()) { std::fill(ring.begin(), ring.end(), 0); }
+            else {
+                std::move(ring.begin() + shift, ring.end(), ring.begin());
+                std::fill(ring.end() - shift, ring.end(), 0);
+            }
+            ring_base = iter_pos;
+        }
+    }
+    return LVC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// deposit
+// ------------------------------------------------------------------------------------------------
+static int launch_deposit(lvc_handle* h, const BatchView& bv, int replay) {
+    TableView tv = table_view(h);
+    DepositParams dp;
+    dp.min_bq = h->min_bq;
+    dp.min_mq = h->min_mq;
+    dp.ord_base = (uint32_t)h->ordinal;
+    dp.replay = replay;
+    dp.replay_keys = h->d_replay;
+    const uint32_t n = bv.n_reads;
+    if (n == 0) return LVC_OK;
+    const int impl = h->impl == 0 ? 2 : h->impl;
+    if (impl == 1 || replay || h->qprim == 255 || h->lut[h->qprim] == kNoPlane) {
+        k_deposit_general<<<(n + 127) / 128, 128, 0, h->stream>>>(bv, tv, dp, nullptr, n);
+        h->launches++;
+    } else {
+        int rc = ensure(h, h->b_defer, (size_t)n * sizeof(uint32_t));
+        if (rc) return rc;
+        TileParams tp = make_tile_params(n, h->sm_count);
+        tp.qprim = (uint32_t)h->qprim;
+        tp.prim_plane = h->lut[h->qprim];
+        k_deposit_tile<<<tp.grid, kTileThreads, kTileSmemBytes, h->stream>>>(bv, tv, dp, tp, (uint32_t*)h->b_defer.p);
+        h->launches++;
+        // reads the tiled kernel could not take (long / irregular) go through the general kernel;
+        // the count is on the device, so the launch is sized for the worst case and exits early.
+        k_deposit_general_deferred<<<std::min<uint32_t>((n + 127) / 128, 4096), 128, 0, h->stream>>>(
+            bv, tv, dp, (const uint32_t*)h->b_defer.p);
+        h->launches++;
+    }
+    CU(cudaGetLastError());
+    return LVC_OK;
+}
+
+static int deposit_with_replay(lvc_handle* h, const BatchView& bv) {
+    if ((uint64_t)h->ordinal + bv.n_reads >= 0xFFFFFFFFull)
+        return fail(h, LVC_ERANGE, "first-seen ordinal space (2^32-1 reads per handle) exhausted");
+    CU(cudaMemsetAsync(h->d_status, 0, ST_WORDS * sizeof(uint32_t), h->stream));
+    int rc = launch_deposit(h, bv, 0);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(h->h_status, h->d_status, ST_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(h->h_status + ST_WORDS, h->d_newkeys, 32 * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (h->h_status[ST_RANGE_ERR]) {
+        h->ordinal += bv.n_reads;
+        return fail(h, LVC_ERANGE, "%u read(s) extend outside the reference [0, %lld); they were skipped",
+                    h->h_status[ST_RANGE_ERR], (long long)h->G);
+    }
+    if (h->h_status[ST_UNMAPPED]) {
+        // new (allele group, quality) keys: allocate their planes and replay ONLY those keys
+        for (int k = 0; k < kMaxKeys; ++k)
+            if ((h->h_status[ST_WORDS + (k >> 5)] >> (k & 31)) & 1u) {
+                rc = add_plane(h, (uint16_t)k);
+                if (rc) return rc;
+            }
+        CU(cudaMemcpyAsync(h->d_replay, h->d_newkeys, 32 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, h->stream));
+        CU(cudaMemsetAsync(h->d_newkeys, 0, 32 * sizeof(uint32_t), h->stream));
+        CU(cudaMemsetAsync(h->d_status, 0, ST_WORDS * sizeof(uint32_t), h->stream));
+        rc = launch_deposit(h, bv, 1);
+        if (rc) return rc;
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    h->ordinal += bv.n_reads;
+    return LVC_OK;
+}
+
+// Sample qualities: pre-allocate planes for the passing values seen (so the first pass rarely needs a
+// replay) and pick the most frequent passing value as the tiled kernel's register-path quality.
+static int premap_from_sample(lvc_handle* h, const uint8_t* q, uint64_t n, uint64_t stride) {
+    uint32_t hist[256] = {0};
+    for (uint64_t i = 0; i < n; i += stride) hist[q[i]]++;
+    int best = 255;
+    uint32_t best_n = 0;
+    for (int v = h->min_bq; v < 255; ++v)
+        if (hist[v]) {
+            int rc = add_plane(h, (uint16_t)v);
+            if (rc) return rc;
+            if (hist[v] > best_n) { best_n = hist[v]; best = v; }
+        }
+    h->qprim = best;
+    return LVC_OK;
+}
+
+static constexpr uint32_t kSampleRows = 512, kSampleRowBytes = 64;
+
+static int premap_host(lvc_handle* h, const lvc_batch* b) {
+    const uint64_t nq = b->n_qual_bytes;
+    return premap_from_sample(h, b->qual, nq, std::max<uint64_t>(1, nq / 32768));
+}
+
+// device-resident batch: gather a strided sample (kSampleRows rows of 64 bytes) with one 2-D copy
+static int premap_device(lvc_handle* h, const lvc_batch* b) {
+    const uint64_t nq = b->n_qual_bytes;
+    if (nq == 0) { h->qprim = 255; return LVC_OK; }
+    if (!h->h_sample) CU(cudaHostAlloc(&h->h_sample, kSampleRows * kSampleRowBytes, cudaHostAllocDefault));
+    uint64_t rows = kSampleRows, width = kSampleRowBytes;
+    if (nq < rows * width) { rows = 1; width = std::min<uint64_t>(nq, kSampleRows * kSampleRowBytes); }
+    const uint64_t pitch = rows > 1 ? nq / rows : width;
+    CU(cudaMemcpy2DAsync(h->h_sample, width, b->qual, pitch, width, rows, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return premap_from_sample(h, h->h_sample, rows * width, 1);
+}
+
+static int validate_batch(lvc_handle* h, const lvc_batch* b) {
+    if (!h || !b) return LVC_EINVAL;
+    if (b->n_reads == 0) return LVC_OK;
+    if (!b->pos || !b->flag || !b->mapq || !b->keep || !b->cigar_off || !b->cigar || !b->seq_off || !b->seq4 || !b->qual)
+        return fail(h, LVC_EINVAL, "lvc_batch has a null array");
+    return LVC_OK;
+}
+
+int lvc_push_batch(lvc_handle* h, const lvc_batch* b) {
+    int rc = validate_batch(h, b);
+    if (rc) return rc;
+    if (b->n_reads == 0) return LVC_OK;
+    CU(cudaSetDevice(h->device));
+    if (b->cigar_off[b->n_reads] != b->n_cigar_ops || b->seq_off[b->n_reads] != b->n_qual_bytes)
+        return fail(h, LVC_EINVAL, "lvc_batch: n_cigar_ops / n_qual_bytes do not match the offset arrays");
+    const size_t n = b->n_reads;
+    struct { DevBuf* d; const void* s; size_t bytes; } cp[] = {
+        {&h->b_pos, b->pos, n * 4},           {&h->b_flag, b->flag, n * 2},
+        {&h->b_mapq, b->mapq, n},             {&h->b_keep, b->keep, n},
+        {&h->b_coff, b->cigar_off, (n + 1) * 4}, {&h->b_cig, b->cigar, (size_t)b->n_cigar_ops * 4},
+        {&h->b_soff, b->seq_off, (n + 1) * 8},   {&h->b_seq, b->seq4, (size_t)(b->n_qual_bytes + 1) / 2},
+        {&h->b_qual, b->qual, (size_t)b->n_qual_bytes},
+    };
+    for (auto& c : cp) {
+        rc = ensure(h, *c.d, c.bytes + 64);     // +64: the tiled kernel reads whole 16-byte groups
+        if (rc) return rc;
+        if (c.bytes) CU(cudaMemcpyAsync(c.d->p, c.s, c.bytes, cudaMemcpyHostToDevice, h->stream));
+    }
+    rc = premap_host(h, b);
+    if (rc) return rc;
+    BatchView bv;
+    bv.n_reads = b->n_reads;
+    bv.pos = (const int32_t*)h->b_pos.p;       bv.flag = (const uint16_t*)h->b_flag.p;
+    bv.mapq = (const uint8_t*)h->b_mapq.p;     bv.keep = (const uint8_t*)h->b_keep.p;
+    bv.cigar_off = (const uint32_t*)h->b_coff.p; bv.cigar = (const uint32_t*)h->b_cig.p;
+    bv.seq_off = (const uint64_t*)h->b_soff.p; bv.seq4 = (const uint8_t*)h->b_seq.p;
+    bv.qual = (const uint8_t*)h->b_qual.p;
+    return deposit_with_replay(h, bv);
+}
+
+int lvc_push_batch_device(lvc_handle* h, const lvc_batch* b) {
+    int rc = validate_batch(h, b);
+    if (rc) return rc;
+    if (b->n_reads == 0) return LVC_OK;
+    CU(cudaSetDevice(h->device));
+    BatchView bv;
+    bv.n_reads = b->n_reads;
+    bv.pos = b->pos; bv.flag = b->flag; bv.mapq = b->mapq; bv.keep = b->keep;
+    bv.cigar_off = b->cigar_off; bv.cigar = b->cigar; bv.seq_off = b->seq_off; bv.seq4 = b->seq4; bv.qual = b->qual;
+    rc = premap_device(h, b);
+    if (rc) return rc;
+    return deposit_with_replay(h, bv);
+}
+
+// ------------------------------------------------------------------------------------------------
+// genotype
+// ------------------------------------------------------------------------------------------------
+int lvc_genotype_device(lvc_handle* h, int64_t min_total_depth, int64_t min_allele_depth, double min_ratio,
+                        const double* e_lut, const double* om_lut, uint32_t flags) {
+    if (!h || !e_lut || !om_lut) return LVC_EINVAL;
+    CU(cudaSetDevice(h->device));
+    const int np = (int)h->planes.size();
+    // order planes: group 0 first (register path), then the rest
+    std::vector<int> order(np);
+    for (int i = 0; i < np; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return h->plane_key[a] < h->plane_key[b]; });
+    std::vector<uint32_t*> ptrs(std::max(np, 1));
+    std::vector<uint16_t> keys(std::max(np, 1));
+    int n_g0 = 0;
+    for (int i = 0; i < np; ++i) {
+        ptrs[i] = h->planes[order[i]];
+        keys[i] = h->plane_key[order[i]];
+        if ((keys[i] >> 8) == 0) n_g0++;
+    }
+    int rc = ensure(h, h->g_order_ptrs, ptrs.size() * sizeof(uint32_t*));
+    if (rc) return rc;
+    rc = ensure(h, h->g_order_keys, keys.size() * sizeof(uint16_t));
+    if (rc) return rc;
+    if (h->cand_cap == 0) {
+        h->cand_cap = 1u << 16;
+        rc = ensure(h, h->g_cand, (size_t)h->cand_cap * sizeof(lvc_candidate));
+        if (rc) return rc;
+    }
+    CU(cudaMemcpyAsync(h->g_order_ptrs.p, ptrs.data(), ptrs.size() * sizeof(uint32_t*), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->g_order_keys.p, keys.data(), keys.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_elut, e_lut, 256 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_elut + 256, om_lut, 256 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        CU(cudaMemsetAsync(h->d_cand_count, 0, sizeof(uint32_t), h->stream));
+        GenoParams gp;
+        gp.G = h->G; gp.min_total_depth = min_total_depth; gp.min_allele_depth = min_allele_depth;
+        gp.min_ratio = min_ratio; gp.flags = flags; gp.n_planes = np; gp.n_g0 = n_g0; gp.cand_cap = h->cand_cap;
+        const size_t smem = (size_t)std::max(np, 1) * (2 * sizeof(XF) + sizeof(double));
+        const int threads = 128;
+        const unsigned blocks = (unsigned)((h->G + threads - 1) / threads);
+        k_genotype<<<blocks, threads, smem, h->stream>>>(gp, (const uint32_t* const*)h->g_order_ptrs.p,
+                                                        (const uint16_t*)h->g_order_keys.p, h->d_elut, h->d_elut + 256,
+                                                        h->d_dels, h->d_ref, (const uint32_t* const*)h->d_first_arr,
+                                                        h->d_out_depth, h->d_out_ad, h->d_out_lik,
+                                                        (lvc_candidate*)h->g_cand.p, h->d_cand_count);
+        h->launches++;
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(h->h_status, h->d_cand_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        h->last_cand_count = h->h_status[0];
+        if (h->last_cand_count <= h->cand_cap) break;
+        // grow and run once more (rare: more candidates than the buffer)
+        h->cand_cap = h->last_cand_count + h->last_cand_count / 4 + 1024;
+        rc = ensure(h, h->g_cand, (size_t)h->cand_cap * sizeof(lvc_candidate));
+        if (rc) return rc;
+    }
+    return LVC_OK;
+}
+
+int lvc_fetch_candidates(lvc_handle* h, lvc_candidate* out, uint32_t cap, uint32_t* n_out) {
+    if (!h || !n_out) return LVC_EINVAL;
+    CU(cudaSetDevice(h->device));
+    *n_out = h->last_cand_count;
+    const uint32_t n = std::min(cap, h->last_cand_count);
+    if (n && out) {
+        CU(cudaMemcpyAsync(out, h->g_cand.p, (size_t)n * sizeof(lvc_candidate), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    return LVC_OK;
+}
+
+int lvc_genotype(lvc_handle* h, int64_t min_total_depth, int64_t min_allele_depth, double min_ratio, const double* e_lut,
+                 const double* om_lut, uint32_t flags, lvc_candidate* out, uint32_t cap, uint32_t* n_out) {
+    int rc = lvc_genotype_device(h, min_total_depth, min_allele_depth, min_ratio, e_lut, om_lut, flags);
+    if (rc) return rc;
+    return lvc_fetch_candidates(h, out, cap, n_out);
+}
+
+int lvc_copy_dense(lvc_handle* h, uint32_t* depth, uint32_t* ad, double* lik) {
+    if (!h) return LVC_EINVAL;
+    CU(cudaSetDevice(h->device));
+    const size_t G = (size_t)h->G;
+    if (depth) CU(cudaMemcpyAsync(depth, h->d_out_depth, G * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (ad) CU(cudaMemcpyAsync(ad, h->d_out_ad, G * 16, cudaMemcpyDeviceToHost, h->stream));
+    if (lik) CU(cudaMemcpyAsync(lik, h->d_out_lik, G * 32, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return LVC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// table access
+// ------------------------------------------------------------------------------------------------
+int lvc_num_planes(lvc_handle* h) { return h ? (int)h->planes.size() : LVC_EINVAL; }
+
+int lvc_plane_keys(lvc_handle* h, uint16_t* keys_out) {
+    if (!h || !keys_out) return LVC_EINVAL;
+    for (size_t i = 0; i < h->plane_key.size(); ++i) keys_out[i] = h->plane_key[i];
+    return LVC_OK;
+}
+
+int lvc_ensure_plane(lvc_handle* h, uint16_t key) {
+    if (!h) return LVC_EINVAL;
+    CU(cudaSetDevice(h->device));
+    int rc = add_plane(h, key);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    return LVC_OK;
+}
+
+__global__ void k_accumulate_u32(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] += src[i];
+}
+
+static int import_u32(lvc_handle* h, uint32_t* d_dst, const uint32_t* src, size_t n, int accumulate) {
+    if (!accumulate) {
+        CU(cudaMemcpyAsync(d_dst, src, n * 4, cudaMemcpyHostToDevice, h->stream));
+    } else {
+        uint32_t* tmp = nullptr;
+        CU(cudaMalloc(&tmp, n * 4));
+        CU(cudaMemcpyAsync(tmp, src, n * 4, cudaMemcpyHostToDevice, h->stream));
+        k_accumulate_u32<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(d_dst, tmp, n);
+        h->launches++;
+        CU(cudaStreamSynchronize(h->stream));
+        CU(cudaFree(tmp));
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    return LVC_OK;
+}
+
+int lvc_copy_plane(lvc_handle* h, uint16_t key, uint32_t* dst) {
+    if (!h || !dst || key >= kMaxKeys || h->lut[key] == kNoPlane) return fail(h, LVC_EINVAL, "no plane for key %u", key);
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemcpyAsync(dst, h->planes[h->lut[key]], (size_t)h->G * 16, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return LVC_OK;
+}
+
+int lvc_import_plane(lvc_handle* h, uint16_t key, const uint32_t* src, int accumulate) {
+    if (!h || !src) return LVC_EINVAL;
+    CU(cudaSetDevice(h->device));
+    int rc = add_plane(h, key);
+    if (rc) return rc;
+    return import_u32(h, h->planes[h->lut[key]], src, (size_t)h->G * 4, accumulate);
+}
+
+int lvc_copy_dels(lvc_handle* h, uint32_t* dst) {
+    if (!h || !dst) return LVC_EINVAL;
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemcpyAsync(dst, h->d_dels, (size_t)h->G * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return LVC_OK;
+}
+int lvc_import_dels(lvc_handle* h, const uint32_t* src, int accumulate) {
+    if (!h || !src) return LVC_EINVAL;
+    CU(cudaSetDevice(h->device));
+    return import_u32(h, h->d_dels, src, (size_t)h->G, accumulate);
+}
+int lvc_copy_covdiff(lvc_handle* h, int32_t* dst) {
+    if (!h || !dst) return LVC_EINVAL;
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemcpyAsync(dst, h->d_covdiff, (size_t)(h->G + 1) * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return LVC_OK;
+}
+int lvc_import_covdiff(lvc_handle* h, const int32_t* src, int accumulate) {
+    if (!h || !src) return LVC_EINVAL;
+    CU(cudaSetDevice(h->device));
+    return import_u32(h, (uint32_t*)h->d_covdiff, (const uint32_t*)src, (size_t)h->G + 1, accumulate);
+}
+int lvc_copy_first(lvc_handle* h, int group, uint32_t* dst) {
+    if (!h || !dst || group < 0 || group > 3 || !h->d_first[group]) return LVC_EINVAL;
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemcpyAsync(dst, h->d_first[group], (size_t)h->G * 16, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return LVC_OK;
+}
+int lvc_import_first(lvc_handle* h, int group, const uint32_t* src) {
+    if (!h || !src || group < 0 || group > 3) return LVC_EINVAL;
+    CU(cudaSetDevice(h->device));
+    if (!h->d_first[group]) {
+        const size_t bytes = (size_t)h->G * 16;
+        CU(cudaMalloc(&h->d_first[group], bytes));
+        CU(cudaMemcpyAsync(h->d_first_arr + group, &h->d_first[group], sizeof(uint32_t*), cudaMemcpyHostToDevice, h->stream));
+    }
+    CU(cudaMemcpyAsync(h->d_first[group], src, (size_t)h->G * 16, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return LVC_OK;
+}
+uint64_t lvc_ordinal(lvc_handle* h) { return h ? h->ordinal : 0; }
+int lvc_set_ordinal(lvc_handle* h, uint64_t o) {
+    if (!h || o >= 0xFFFFFFFFull) return LVC_EINVAL;
+    h->ordinal = o;
+    return LVC_OK;
+}
+void* lvc_plane_devptr(lvc_handle* h, uint16_t key) {
+    if (!h || key >= kMaxKeys || h->lut[key] == kNoPlane) return nullptr;
+    return h->planes[h->lut[key]];
+}
+void* lvc_dels_devptr(lvc_handle* h) { return h ? h->d_dels : nullptr; }
+void* lvc_covdiff_devptr(lvc_handle* h) { return h ? h->d_covdiff : nullptr; }
+void* lvc_first_devptr(lvc_handle* h, int group) { return (h && group >= 0 && group < 4) ? h->d_first[group] : nullptr; }
+uint64_t lvc_launch_count(lvc_handle* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,79 @@
+// Shared device-side definitions for the live-variant-caller kernels (sm_100a).
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+
+namespace lvc {
+
+constexpr uint16_t kNoPlane = 0xFFFFu;
+constexpr uint32_t kUnsetOrdinal = 0xFFFFFFFFu;
+constexpr int kMaxKeys = 1024;          // 4 allele groups x 256 qualities
+constexpr uint32_t kFlagFilter = 0x4u | 0x100u | 0x200u | 0x400u;   // UNMAP|SECONDARY|QCFAIL|DUP
+
+// status words written by the deposit kernels
+enum { ST_UNMAPPED = 0, ST_RANGE_ERR = 1, ST_DEFERRED = 2, ST_WORDS = 8 };
+
+// BAM nibble -> (group<<2 | slot).  A,C,G,T (1,2,4,8) are group 0 slots 0..3; the other 12 codes fill
+// groups 1..3 in ascending nibble order.  Packed 4 bits per nibble, nibble 0 in the low digit.
+constexpr uint64_t kNibbleToGS = 0xFEDCBA9387625104ull;
+__host__ __device__ __forceinline__ uint32_t nibble_gs(uint32_t nib) {
+    return (uint32_t)(kNibbleToGS >> (nib * 4)) & 0xFu;
+}
+// inverse: (group<<2|slot) -> nibble
+__host__ __device__ __forceinline__ uint32_t gs_nibble(uint32_t gs) {
+    constexpr uint64_t inv = 0xFEDCBA9765308421ull;   // gs 0..15 -> 1,2,4,8, 0,3,5,6, 7,9,10,11, 12..15
+    return (uint32_t)(inv >> (gs * 4)) & 0xFu;
+}
+
+// Persistent per-handle tables as the kernels see them.
+struct TableView {
+    int64_t G;                    // reference length
+    uint32_t* const* planes;      // [n_planes] -> uint32 [G][4]
+    const uint16_t* lut;          // [1024] key -> plane id or kNoPlane
+    uint32_t* dels;               // [G]
+    int32_t* covdiff;             // [G+1]
+    uint32_t* first[4];           // per group [G][4] (nullptr if the group has no plane yet)
+    uint32_t* newkeys;            // [32] bitmap of keys seen without a plane
+    uint32_t* status;             // [ST_WORDS]
+};
+
+// One batch of reads, device pointers (mirrors lvc_batch in include/lvc.h).
+struct BatchView {
+    uint32_t n_reads;
+    const int32_t* pos;
+    const uint16_t* flag;
+    const uint8_t* mapq;
+    const uint8_t* keep;
+    const uint32_t* cigar_off;
+    const uint32_t* cigar;
+    const uint64_t* seq_off;
+    const uint8_t* seq4;
+    const uint8_t* qual;
+};
+
+struct DepositParams {
+    int min_bq;
+    int min_mq;
+    uint32_t ord_base;            // ordinal of read 0 of this batch
+    int replay;                   // 0: normal pass; 1: deposit only keys in `replay_keys`, no dels/cov
+    const uint32_t* replay_keys;  // [32] bitmap (device) when replay
+};
+
+__device__ __forceinline__ bool read_passes_filter(uint32_t flag, uint32_t mapq, uint32_t keep, int min_mq) {
+    // pysam stepper "samtools": flag filter, mapq, ignore_orphans + host admission bit
+    if (!(keep & 1u)) return false;
+    if (flag & kFlagFilter) return false;
+    if ((int)mapq < min_mq) return false;
+    if ((flag & 0x1u) && !(flag & 0x2u)) return false;
+    return true;
+}
+
+__device__ __forceinline__ bool op_consumes_ref(uint32_t op) {   // M D N = X
+    return op == 0 || op == 2 || op == 3 || op == 7 || op == 8;
+}
+__device__ __forceinline__ bool op_consumes_query(uint32_t op) { // M I S = X
+    return op == 0 || op == 1 || op == 4 || op == 7 || op == 8;
+}
+__device__ __forceinline__ bool op_is_match(uint32_t op) { return op == 0 || op == 7 || op == 8; }
+
+}  // namespace lvc

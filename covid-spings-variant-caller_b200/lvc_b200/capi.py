@@ -1,0 +1,294 @@
+"""ctypes binding of liblvc_b200.so (the C-ABI declared in include/lvc.h).
+
+There is NO CPU fallback: if the shared library is missing, or no CUDA device is visible when a
+handle is created, this raises.  Nothing here imports anything from ``oracle/``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblvc_b200.so")
+
+LVC_OK = 0
+ERRORS = {-1: "LVC_EINVAL", -2: "LVC_ECUDA", -3: "LVC_ENOMEM", -4: "LVC_EUNSORTED", -5: "LVC_ERANGE",
+          -6: "LVC_ENODEVICE"}
+GENO_EMIT_ALL = 1
+MAX_DEPTH_DEFAULT = 8000
+
+
+class LvcError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"{ERRORS.get(code, code)}: {msg}")
+        self.code = code
+
+
+class Batch(C.Structure):
+    _fields_ = [("n_reads", C.c_uint32), ("reserved", C.c_uint32), ("n_cigar_ops", C.c_uint64),
+                ("n_qual_bytes", C.c_uint64), ("pos", C.c_void_p), ("flag", C.c_void_p), ("mapq", C.c_void_p),
+                ("keep", C.c_void_p), ("cigar_off", C.c_void_p), ("cigar", C.c_void_p), ("seq_off", C.c_void_p),
+                ("seq4", C.c_void_p), ("qual", C.c_void_p)]
+
+
+class Candidate(C.Structure):
+    _fields_ = [("pos", C.c_int32), ("code", C.c_uint8), ("ref", C.c_uint8), ("pad0", C.c_uint16),
+                ("ad", C.c_uint32), ("dp", C.c_uint32), ("first", C.c_uint32), ("pad1", C.c_uint32),
+                ("L", C.c_double), ("S", C.c_double), ("esum", C.c_double)]
+
+
+CANDIDATE_DTYPE = np.dtype([("pos", "<i4"), ("code", "u1"), ("ref", "u1"), ("pad0", "<u2"), ("ad", "<u4"),
+                            ("dp", "<u4"), ("first", "<u4"), ("pad1", "<u4"), ("L", "<f8"), ("S", "<f8"),
+                            ("esum", "<f8")])
+assert CANDIDATE_DTYPE.itemsize == C.sizeof(Candidate) == 48
+
+_lib: Optional[C.CDLL] = None
+
+# every symbol include/lvc.h declares: (name, restype, argtypes)
+_H = C.c_void_p
+SIGNATURES = [
+    ("lvc_version", C.c_int, []),
+    ("lvc_create", C.c_int, [C.POINTER(_H), C.c_int, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    ("lvc_destroy", None, [_H]),
+    ("lvc_reset", C.c_int, [_H]),
+    ("lvc_last_error", C.c_char_p, [_H]),
+    ("lvc_set_stream", C.c_int, [_H, C.c_void_p]),
+    ("lvc_sync", C.c_int, [_H]),
+    ("lvc_admit", C.c_int, [C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                            C.c_void_p]),
+    ("lvc_push_batch", C.c_int, [_H, C.POINTER(Batch)]),
+    ("lvc_push_batch_device", C.c_int, [_H, C.POINTER(Batch)]),
+    ("lvc_set_impl", C.c_int, [_H, C.c_int]),
+    ("lvc_host_alloc", C.c_void_p, [C.c_uint64]),
+    ("lvc_host_free", None, [C.c_void_p]),
+    ("lvc_genotype", C.c_int, [_H, C.c_int64, C.c_int64, C.c_double, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
+                               C.c_uint32, C.POINTER(C.c_uint32)]),
+    ("lvc_genotype_device", C.c_int, [_H, C.c_int64, C.c_int64, C.c_double, C.c_void_p, C.c_void_p, C.c_uint32]),
+    ("lvc_fetch_candidates", C.c_int, [_H, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]),
+    ("lvc_copy_dense", C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("lvc_num_planes", C.c_int, [_H]),
+    ("lvc_plane_keys", C.c_int, [_H, C.c_void_p]),
+    ("lvc_ensure_plane", C.c_int, [_H, C.c_uint16]),
+    ("lvc_copy_plane", C.c_int, [_H, C.c_uint16, C.c_void_p]),
+    ("lvc_import_plane", C.c_int, [_H, C.c_uint16, C.c_void_p, C.c_int]),
+    ("lvc_copy_dels", C.c_int, [_H, C.c_void_p]),
+    ("lvc_import_dels", C.c_int, [_H, C.c_void_p, C.c_int]),
+    ("lvc_copy_covdiff", C.c_int, [_H, C.c_void_p]),
+    ("lvc_import_covdiff", C.c_int, [_H, C.c_void_p, C.c_int]),
+    ("lvc_copy_first", C.c_int, [_H, C.c_int, C.c_void_p]),
+    ("lvc_import_first", C.c_int, [_H, C.c_int, C.c_void_p]),
+    ("lvc_ordinal", C.c_uint64, [_H]),
+    ("lvc_set_ordinal", C.c_int, [_H, C.c_uint64]),
+    ("lvc_plane_devptr", C.c_void_p, [_H, C.c_uint16]),
+    ("lvc_dels_devptr", C.c_void_p, [_H]),
+    ("lvc_covdiff_devptr", C.c_void_p, [_H]),
+    ("lvc_first_devptr", C.c_void_p, [_H, C.c_int]),
+    ("lvc_launch_count", C.c_uint64, [_H]),
+]
+
+
+def load_library() -> C.CDLL:
+    """Load liblvc_b200.so (built in-tree by __graft_entry__.build()).  Raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} not found: build it with `python __graft_entry__.py` "
+                          "(nvcc, sm_100a).  There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, res, args in SIGNATURES:
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _ptr(a) -> Optional[int]:
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return int(a)
+
+
+def admit(pos: np.ndarray, flag: np.ndarray, mapq: np.ndarray, cigar_off: np.ndarray, cigar: np.ndarray,
+          min_mapq: int, max_depth: int = MAX_DEPTH_DEFAULT) -> np.ndarray:
+    """keep-mask (bit0) of the host-side admission rules; needs no GPU."""
+    lib = load_library()
+    n = len(pos)
+    keep = np.zeros(n, dtype=np.uint8)
+    if n == 0:
+        return keep
+    rc = lib.lvc_admit(n, _ptr(pos), _ptr(flag), _ptr(mapq), _ptr(cigar_off), _ptr(cigar), int(min_mapq),
+                       int(max_depth), _ptr(keep))
+    if rc == -4:
+        raise ValueError("reads are not coordinate sorted (the reference's pileup engine errors out too)")
+    if rc != LVC_OK:
+        raise LvcError(rc, "lvc_admit failed")
+    return keep
+
+
+class Handle:
+    """Owns one lvc_handle (one contig's persistent device tables)."""
+
+    def __init__(self, ref_bytes: bytes, min_base_quality: int, min_mapping_quality: int, device: int = 0,
+                 stream: Optional[int] = None):
+        self.lib = load_library()
+        self.G = len(ref_bytes)
+        self._ref = np.frombuffer(ref_bytes, dtype=np.uint8).copy()
+        h = _H()
+        rc = self.lib.lvc_create(C.byref(h), int(device), self.G, self._ref.ctypes.data, int(min_base_quality),
+                                 int(min_mapping_quality), stream)
+        if rc != LVC_OK:
+            msg = self.lib.lvc_last_error(None).decode()
+            raise LvcError(rc, msg)
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.lvc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != LVC_OK:
+            raise LvcError(rc, self.lib.lvc_last_error(self.h).decode())
+
+    # ---- lifetime
+    def reset(self):
+        self._check(self.lib.lvc_reset(self.h))
+
+    def set_impl(self, impl: int):
+        self._check(self.lib.lvc_set_impl(self.h, impl))
+
+    def set_stream(self, stream: Optional[int]):
+        self._check(self.lib.lvc_set_stream(self.h, stream))
+
+    def sync(self):
+        self._check(self.lib.lvc_sync(self.h))
+
+    # ---- deposit
+    @staticmethod
+    def make_batch(n_reads, n_cigar, n_qual, pos, flag, mapq, keep, cigar_off, cigar, seq_off, seq4, qual) -> Batch:
+        return Batch(int(n_reads), 0, int(n_cigar), int(n_qual), _ptr(pos), _ptr(flag), _ptr(mapq), _ptr(keep),
+                     _ptr(cigar_off), _ptr(cigar), _ptr(seq_off), _ptr(seq4), _ptr(qual))
+
+    def push_batch(self, batch: Batch):
+        self._check(self.lib.lvc_push_batch(self.h, C.byref(batch)))
+
+    def push_batch_device(self, batch: Batch):
+        self._check(self.lib.lvc_push_batch_device(self.h, C.byref(batch)))
+
+    # ---- genotype
+    def genotype(self, min_total_depth: int, min_allele_depth: int, min_ratio: float, e_lut: np.ndarray,
+                 om_lut: np.ndarray, flags: int = 0) -> np.ndarray:
+        cap = 1 << 14
+        while True:
+            out = np.zeros(cap, dtype=CANDIDATE_DTYPE)
+            n = C.c_uint32(0)
+            self._check(self.lib.lvc_genotype(self.h, int(min_total_depth), int(min_allele_depth), float(min_ratio),
+                                              e_lut.ctypes.data, om_lut.ctypes.data, int(flags), out.ctypes.data, cap,
+                                              C.byref(n)))
+            if n.value <= cap:
+                return out[:n.value]
+            cap = n.value
+
+    def genotype_device(self, min_total_depth, min_allele_depth, min_ratio, e_lut, om_lut, flags=0):
+        self._check(self.lib.lvc_genotype_device(self.h, int(min_total_depth), int(min_allele_depth), float(min_ratio),
+                                                 e_lut.ctypes.data, om_lut.ctypes.data, int(flags)))
+
+    def fetch_candidates(self) -> np.ndarray:
+        n = C.c_uint32(0)
+        self._check(self.lib.lvc_fetch_candidates(self.h, None, 0, C.byref(n)))
+        out = np.zeros(max(n.value, 1), dtype=CANDIDATE_DTYPE)
+        self._check(self.lib.lvc_fetch_candidates(self.h, out.ctypes.data, len(out), C.byref(n)))
+        return out[:n.value]
+
+    def copy_dense(self):
+        depth = np.zeros(self.G, dtype=np.uint32)
+        ad = np.zeros((self.G, 4), dtype=np.uint32)
+        lik = np.zeros((self.G, 4), dtype=np.float64)
+        self._check(self.lib.lvc_copy_dense(self.h, depth.ctypes.data, ad.ctypes.data, lik.ctypes.data))
+        return depth, ad, lik
+
+    # ---- tables
+    def plane_keys(self) -> np.ndarray:
+        n = self.lib.lvc_num_planes(self.h)
+        keys = np.zeros(max(n, 1), dtype=np.uint16)
+        self._check(self.lib.lvc_plane_keys(self.h, keys.ctypes.data))
+        return keys[:n]
+
+    def copy_plane(self, key: int) -> np.ndarray:
+        out = np.zeros((self.G, 4), dtype=np.uint32)
+        self._check(self.lib.lvc_copy_plane(self.h, int(key), out.ctypes.data))
+        return out
+
+    def import_plane(self, key: int, arr: np.ndarray, accumulate: bool = False):
+        arr = np.ascontiguousarray(arr, dtype=np.uint32)
+        assert arr.size == self.G * 4
+        self._check(self.lib.lvc_import_plane(self.h, int(key), arr.ctypes.data, int(accumulate)))
+
+    def ensure_plane(self, key: int):
+        self._check(self.lib.lvc_ensure_plane(self.h, int(key)))
+
+    def copy_dels(self) -> np.ndarray:
+        out = np.zeros(self.G, dtype=np.uint32)
+        self._check(self.lib.lvc_copy_dels(self.h, out.ctypes.data))
+        return out
+
+    def import_dels(self, arr, accumulate=False):
+        arr = np.ascontiguousarray(arr, dtype=np.uint32)
+        self._check(self.lib.lvc_import_dels(self.h, arr.ctypes.data, int(accumulate)))
+
+    def copy_covdiff(self) -> np.ndarray:
+        out = np.zeros(self.G + 1, dtype=np.int32)
+        self._check(self.lib.lvc_copy_covdiff(self.h, out.ctypes.data))
+        return out
+
+    def import_covdiff(self, arr, accumulate=False):
+        arr = np.ascontiguousarray(arr, dtype=np.int32)
+        self._check(self.lib.lvc_import_covdiff(self.h, arr.ctypes.data, int(accumulate)))
+
+    def copy_first(self, group: int) -> Optional[np.ndarray]:
+        if not self.lib.lvc_first_devptr(self.h, group):
+            return None
+        out = np.zeros((self.G, 4), dtype=np.uint32)
+        self._check(self.lib.lvc_copy_first(self.h, group, out.ctypes.data))
+        return out
+
+    def import_first(self, group: int, arr):
+        arr = np.ascontiguousarray(arr, dtype=np.uint32)
+        self._check(self.lib.lvc_import_first(self.h, group, arr.ctypes.data))
+
+    @property
+    def ordinal(self) -> int:
+        return int(self.lib.lvc_ordinal(self.h))
+
+    @ordinal.setter
+    def ordinal(self, v: int):
+        self._check(self.lib.lvc_set_ordinal(self.h, int(v)))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.lvc_launch_count(self.h))
+
+    def plane_devptr(self, key: int) -> int:
+        return self.lib.lvc_plane_devptr(self.h, int(key)) or 0
+
+    def dels_devptr(self) -> int:
+        return self.lib.lvc_dels_devptr(self.h) or 0
+
+    def covdiff_devptr(self) -> int:
+        return self.lib.lvc_covdiff_devptr(self.h) or 0
+
+    def first_devptr(self, group: int) -> int:
+        return self.lib.lvc_first_devptr(self.h, group) or 0

@@ -1,0 +1,177 @@
+"""Host-side packing of alignments into the structure-of-arrays batch of include/lvc.h.
+
+Replaces what pysam hands the reference inside process_bam (live_variant_caller.py:55-60): instead of
+a Python PileupColumn iterator, reads are packed once into flat arrays and shipped to the device.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import capi
+
+NIBBLE_CHARS = "=ACMGRSVTWYHKDBN"
+_ASCII_TO_NIBBLE = np.full(256, 15, dtype=np.uint8)       # unknown letters -> N (htslib seq_nt16_table)
+for _i, _c in enumerate(NIBBLE_CHARS):
+    _ASCII_TO_NIBBLE[ord(_c)] = _i
+    _ASCII_TO_NIBBLE[ord(_c.lower())] = _i
+_IS_ACGT_NIBBLE = np.zeros(16, dtype=bool)
+_IS_ACGT_NIBBLE[[1, 2, 4, 8]] = True
+CIGAR_OPS = "MIDNSHP=XB"
+_QUERY_OP = np.zeros(16, dtype=bool)
+_QUERY_OP[[0, 1, 4, 7, 8]] = True
+_REF_OP = np.zeros(16, dtype=bool)
+_REF_OP[[0, 2, 3, 7, 8]] = True
+
+
+class UnsupportedInput(ValueError):
+    """Input the path cannot reproduce bit-exactly yet; raised instead of silently diverging."""
+
+
+@dataclass
+class ReadBatch:
+    """One coordinate-sorted batch of alignments of one contig, packed (numpy, C-contiguous)."""
+    pos: np.ndarray        # int32  [n]
+    flag: np.ndarray       # uint16 [n]
+    mapq: np.ndarray       # uint8  [n]
+    keep: np.ndarray       # uint8  [n]   bit0 admitted (lvc_admit), bit1 ACGT-only hint
+    cigar_off: np.ndarray  # uint32 [n+1]
+    cigar: np.ndarray      # uint32 [n_cigar]
+    seq_off: np.ndarray    # uint64 [n+1]  even byte offsets into qual; seq4 offset = seq_off/2
+    seq4: np.ndarray       # uint8  [seq_off[n]/2 (+pad)]
+    qual: np.ndarray       # uint8  [seq_off[n] (+pad)]
+
+    @property
+    def n_reads(self) -> int:
+        return int(len(self.pos))
+
+    @property
+    def n_cigar(self) -> int:
+        return int(self.cigar_off[-1]) if len(self.cigar_off) else 0
+
+    @property
+    def n_qual(self) -> int:
+        return int(self.seq_off[-1]) if len(self.seq_off) else 0
+
+    def aligned_bases(self) -> int:
+        """metric unit: query bases consumed by M/=/X ops of every read PRESENTED."""
+        ops = self.cigar[: self.n_cigar] & 15
+        lens = self.cigar[: self.n_cigar] >> 4
+        m = (ops == 0) | (ops == 7) | (ops == 8)
+        return int(lens[m].sum(dtype=np.int64))
+
+    def algorithmic_bytes(self, ref_len: int) -> int:
+        """SURVEY 8d formula: sum_reads[20 + 4*n_cigar + ceil(l/2) + l] + 52*G."""
+        lq = query_lengths(self.cigar_off, self.cigar)
+        return int(20 * self.n_reads + 4 * self.n_cigar + ((lq + 1) // 2).sum() + lq.sum() + 52 * ref_len)
+
+    def as_capi(self) -> capi.Batch:
+        return capi.Handle.make_batch(self.n_reads, self.n_cigar, self.n_qual, self.pos, self.flag, self.mapq,
+                                      self.keep, self.cigar_off, self.cigar, self.seq_off, self.seq4, self.qual)
+
+    def slice(self, a: int, b: int) -> "ReadBatch":
+        """reads [a, b) as a new batch sharing the payload arrays (offsets rebased)."""
+        co = self.cigar_off[a:b + 1]
+        so = self.seq_off[a:b + 1]
+        return ReadBatch(self.pos[a:b].copy(), self.flag[a:b].copy(), self.mapq[a:b].copy(), self.keep[a:b].copy(),
+                         (co - co[0]).astype(np.uint32), self.cigar[int(co[0]):int(co[-1])].copy(),
+                         (so - so[0]).astype(np.uint64),
+                         np.concatenate([self.seq4[int(so[0]) // 2:(int(so[-1]) + 1) // 2], np.zeros(64, np.uint8)]),
+                         np.concatenate([self.qual[int(so[0]):int(so[-1])], np.zeros(64, np.uint8)]))
+
+
+def finalize_batch(pos, flag, mapq, cigar_off, cigar, seq_off, seq4, qual, min_mapq: int,
+                   max_depth: int = capi.MAX_DEPTH_DEFAULT, acgt_only: Optional[np.ndarray] = None) -> ReadBatch:
+    """Validate, compute the keep mask (host admission, SURVEY B2+B4) and the ACGT-only hint."""
+    pos = np.ascontiguousarray(pos, dtype=np.int32)
+    flag = np.ascontiguousarray(flag, dtype=np.uint16)
+    mapq = np.ascontiguousarray(mapq, dtype=np.uint8)
+    cigar_off = np.ascontiguousarray(cigar_off, dtype=np.uint32)
+    cigar = np.ascontiguousarray(cigar, dtype=np.uint32)
+    seq_off = np.ascontiguousarray(seq_off, dtype=np.uint64)
+    n = len(pos)
+    nq = int(seq_off[-1]) if n else 0
+    # payload arrays carry 64 bytes of slack: the tiled kernel stages whole 16-byte groups
+    seq4 = _with_slack(np.ascontiguousarray(seq4, dtype=np.uint8), (nq + 1) // 2)
+    qual = _with_slack(np.ascontiguousarray(qual, dtype=np.uint8), nq)
+    if n and (seq_off & np.uint64(1)).any():
+        raise ValueError("seq_off entries must be even")
+    cig_store = cigar if len(cigar) else np.zeros(1, dtype=np.uint32)
+    keep = capi.admit(pos, flag, mapq, cigar_off, cig_store, min_mapq, max_depth)
+    if acgt_only is None:
+        acgt_only = acgt_only_hint(seq4, seq_off, n, query_lengths(cigar_off, cig_store))
+    keep = (keep | (acgt_only.astype(np.uint8) << 1)).astype(np.uint8)
+    return ReadBatch(pos, flag, mapq, keep, cigar_off, cig_store, seq_off, seq4, qual)
+
+
+def _with_slack(a: np.ndarray, used: int, slack: int = 64) -> np.ndarray:
+    if len(a) >= used + slack:
+        return a
+    out = np.zeros(used + slack, dtype=np.uint8)
+    out[:used] = a[:used]
+    return out
+
+
+def query_lengths(cigar_off: np.ndarray, cigar: np.ndarray) -> np.ndarray:
+    """l_qseq per read = sum of the query-consuming CIGAR op lengths (BAM invariant)."""
+    n = len(cigar_off) - 1
+    if n <= 0:
+        return np.zeros(0, dtype=np.int64)
+    nc = int(cigar_off[-1])
+    ops = cigar[:nc] & 15
+    w = np.where(_QUERY_OP[ops], (cigar[:nc] >> 4).astype(np.int64), 0)
+    csum = np.concatenate([[0], np.cumsum(w)])
+    co = cigar_off.astype(np.int64)
+    return csum[co[1:]] - csum[co[:-1]]
+
+
+def acgt_only_hint(seq4: np.ndarray, seq_off: np.ndarray, n: int, lq: Optional[np.ndarray] = None) -> np.ndarray:
+    """bit1 of keep: True iff every base nibble of the read is A, C, G or T (the pad nibble of an
+    odd-length read is ignored)."""
+    if n == 0:
+        return np.zeros(0, dtype=bool)
+    nb = int(seq_off[-1]) // 2
+    by = seq4[:nb]
+    bad_hi = ~_IS_ACGT_NIBBLE[by >> 4]
+    bad_lo = ~_IS_ACGT_NIBBLE[by & 15]
+    starts = (seq_off[:-1] // np.uint64(2)).astype(np.int64)
+    ends = (seq_off[1:] // np.uint64(2)).astype(np.int64)
+    if lq is not None:
+        odd = (lq & 1) == 1
+        bad_lo[starts[odd] + lq[odd] // 2] = False
+    bad = (bad_hi | bad_lo).astype(np.int64)
+    csum = np.concatenate([[0], np.cumsum(bad)])
+    return (csum[ends] - csum[starts]) == 0
+
+
+def pack_reads(reads: Iterable[Tuple[int, int, int, Sequence[Tuple[int, int]], str, Sequence[int]]],
+               min_mapq: int, max_depth: int = capi.MAX_DEPTH_DEFAULT) -> ReadBatch:
+    """reads: iterable of (flag, pos0, mapq, [(op, len)...], seq_str, qual_ints) in coordinate order."""
+    pos, flag, mapq, coff, cig, soff = [], [], [], [0], [], [0]
+    seq_parts: List[np.ndarray] = []
+    qual_parts: List[np.ndarray] = []
+    for f, p, m, ops, seq, qual in reads:
+        ops = [(o, l) for o, l in ops if l > 0]                  # zero-length ops carry no information
+        lq = sum(l for o, l in ops if o in (0, 1, 4, 7, 8))
+        if len(seq) != lq or len(qual) != lq:
+            if any(o in (0, 2, 3, 7, 8) for o, _ in ops):
+                raise UnsupportedInput(f"read at {p}: CIGAR query length {lq} != SEQ/QUAL length "
+                                       f"{len(seq)}/{len(qual)} (the reference needs both to be present)")
+            ops, seq, qual, lq = [], "", [], 0                    # never reaches the pileup: keep the slot only
+        pos.append(p); flag.append(f); mapq.append(m)
+        for o, l in ops:
+            cig.append((l << 4) | o)
+        coff.append(len(cig))
+        nib = _ASCII_TO_NIBBLE[np.frombuffer(seq.encode("ascii"), dtype=np.uint8)] if lq else np.zeros(0, np.uint8)
+        q = np.asarray(qual, dtype=np.uint8)
+        if lq & 1:
+            nib = np.concatenate([nib, np.zeros(1, np.uint8)])
+            q = np.concatenate([q, np.zeros(1, np.uint8)])
+        seq_parts.append(((nib[0::2] << 4) | nib[1::2]).astype(np.uint8))
+        qual_parts.append(q)
+        soff.append(soff[-1] + len(q))
+    seq4 = np.concatenate(seq_parts) if seq_parts else np.zeros(0, np.uint8)
+    qual = np.concatenate(qual_parts) if qual_parts else np.zeros(0, np.uint8)
+    return finalize_batch(pos, flag, mapq, coff, cig, soff, seq4, qual, min_mapq, max_depth)

@@ -1,0 +1,166 @@
+/*
+ * lvc.h -- C-ABI of the B200-native live-variant-caller hot path (liblvc_b200.so).
+ *
+ * The reference (COVID-SpiNGS/covid-spings-variant-caller) is 100% Python and has NO FFI; the drop-in
+ * boundary is the Python class variant_caller/live_variant_caller.py:21 `LiveVariantCaller`.  Each
+ * entry point below cites the reference code it replaces; INTEGRATION.md shows the ctypes binding a
+ * maintainer of the reference would add.  Plain pointers and sizes only -- no torch / numpy types.
+ *
+ * Conventions: every function returning int returns 0 on success and a negative LVC_E* code on
+ * failure; lvc_last_error(h) gives the message.  A handle owns ONE contig's persistent device tables
+ * (the reference's `self.memory`, live_variant_caller.py:31) and one CUDA stream.  Handles are not
+ * thread-safe; the Python shim serialises calls with a lock (the reference calls the class from
+ * un-locked daemon threads, client_server/vc_queue.py:99-111).
+ */
+#ifndef LVC_H_
+#define LVC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LVC_OK 0
+#define LVC_EINVAL (-1)     /* bad argument / malformed batch                                   */
+#define LVC_ECUDA (-2)      /* CUDA runtime error (message has the cudaError string)            */
+#define LVC_ENOMEM (-3)
+#define LVC_EUNSORTED (-4)  /* reads not coordinate sorted (htslib errors out too)   */
+#define LVC_ERANGE (-5)     /* a read extends past the reference / ordinal space exhausted      */
+#define LVC_ENODEVICE (-6)  /* no CUDA device: there is NO CPU fallback                          */
+
+#define LVC_MAX_DEPTH_DEFAULT 8000 /* pysam pileup() default max_depth [EXT], SURVEY B1/B4 */
+
+typedef struct lvc_handle lvc_handle;
+
+/*
+ * One batch of alignments of ONE contig, coordinate sorted, structure-of-arrays.
+ * This is what `pysam.AlignmentFile(...).pileup(...)` consumes inside process_bam
+ * (live_variant_caller.py:54-60).  All pointers are host pointers for lvc_push_batch and device
+ * pointers for lvc_push_batch_device.
+ *
+ *   seq_off[i]  = byte offset of read i's qualities in `qual`; MUST be even; the read's 4-bit bases
+ *                 start at seq4[seq_off[i]/2] (BAM nibble codes "=ACMGRSVTWYHKDBN", high nibble first).
+ *                 l_qseq of a read is the sum of its query-consuming CIGAR ops (BAM invariant).
+ *   cigar       = BAM encoding  len<<4 | op,  op in MIDNSHP=X (0..8).
+ *   keep[i]     = 1 if the read survives the host-side, order-dependent admission rules
+ *                 (htslib max_depth rule; computed by lvc_admit).  flag / mapq / orphan
+ *                 filters are re-evaluated on the device.
+ */
+typedef struct lvc_batch {
+    uint32_t n_reads;
+    uint32_t reserved;
+    uint64_t n_cigar_ops;  /* == cigar_off[n_reads] */
+    uint64_t n_qual_bytes; /* == seq_off[n_reads]   */
+    const int32_t* pos;    /* [n_reads] 0-based leftmost reference position */
+    const uint16_t* flag;  /* [n_reads] */
+    const uint8_t* mapq;   /* [n_reads] */
+    const uint8_t* keep;   /* [n_reads] */
+    const uint32_t* cigar_off; /* [n_reads+1] */
+    const uint32_t* cigar;     /* [n_cigar_ops] */
+    const uint64_t* seq_off;   /* [n_reads+1] */
+    const uint8_t* seq4;       /* [n_qual_bytes/2] */
+    const uint8_t* qual;       /* [n_qual_bytes]   */
+} lvc_batch;
+
+/* One (position, allele) that passed the genotype-stage filters; the host finalises log10/round/
+ * formatting with the host libm so the text matches the reference. */
+typedef struct lvc_candidate {
+    int32_t pos;       /* 0-based */
+    uint8_t code;      /* BAM nibble code of the allele */
+    uint8_t ref;       /* reference byte at pos (as stored in the FASTA) */
+    uint16_t pad0;
+    uint32_t ad;       /* allele depth  = len(snvs[allele])               (live_variant_caller.py:149) */
+    uint32_t dp;       /* totalDepth                                      (live_variant_caller.py:179) */
+    uint32_t first;    /* ordinal of the first read that deposited this allele (dict order) */
+    uint32_t pad1;
+    double L;          /* genotype_likelihood(allele, snvs)               (utils.py:16-24)  */
+    double S;          /* sum of L over the alleles at pos, 1.0 if 0      (live_variant_caller.py:145-146) */
+    double esum;       /* sum of error probabilities of the allele; qual = esum/ad (live_variant_caller.py:168) */
+} lvc_candidate;
+
+#define LVC_GENO_EMIT_ALL 1u /* flags: emit every allele of every gated site (tests / export) */
+
+/* ---- lifetime -------------------------------------------------------------------------------
+ * lvc_create  <- LiveVariantCaller.__init__ (live_variant_caller.py:22-32): thresholds that act at
+ *                deposit time (min_base_quality, min_mapping_quality :57-58) are fixed per handle.
+ *                `ref_bytes` = the contig as stored in the FASTA (case preserved, :78-81).
+ *                `stream` = a cudaStream_t to launch on, or NULL to create a private one.
+ * lvc_destroy <- __del__ (:34-35).      lvc_reset <- reset_memory (:37-38). */
+int lvc_create(lvc_handle** out, int device, int64_t ref_len, const uint8_t* ref_bytes,
+               int min_base_quality, int min_mapping_quality, void* stream);
+void lvc_destroy(lvc_handle* h);
+int lvc_reset(lvc_handle* h);
+const char* lvc_last_error(const lvc_handle* h); /* h may be NULL: error of the last failed lvc_create */
+int lvc_set_stream(lvc_handle* h, void* stream);
+int lvc_sync(lvc_handle* h);
+
+/* ---- host-side admission (no GPU needed) -------------------------------------------------------
+ * Restates the order-dependent part of pysam's pileup engine that process_bam relies on
+ * (live_variant_caller.py:56-60): read-level filter + htslib bam_plp_push max_depth rule
+ * (SURVEY B4).  Writes keep_out[i] in {0,1}.  Returns LVC_EUNSORTED for unsorted input. */
+int lvc_admit(uint32_t n_reads, const int32_t* pos, const uint16_t* flag, const uint8_t* mapq,
+              const uint32_t* cigar_off, const uint32_t* cigar, int min_mapping_quality, int max_depth,
+              uint8_t* keep_out);
+
+/* ---- deposit: process_bam / process_pileup_column / process_svn (live_variant_caller.py:54-103) ----
+ * Walks every kept read's CIGAR on the device and adds its bases/qualities to the persistent
+ * per-position tables.  Accumulates across calls (live batches).  `impl`: 0 = auto, 1 = general
+ * kernel, 2 = tiled fast kernel (general kernel for what it cannot take). */
+int lvc_push_batch(lvc_handle* h, const lvc_batch* host_batch);
+int lvc_push_batch_device(lvc_handle* h, const lvc_batch* device_batch);
+int lvc_set_impl(lvc_handle* h, int impl);
+/* pinned host memory for the SoA buffers (cudaHostAlloc) */
+void* lvc_host_alloc(uint64_t bytes);
+void lvc_host_free(void* p);
+
+/* ---- genotype: prepare_variants (live_variant_caller.py:120-231) + utils.py:9-24 -----------------
+ * e_lut[q] = math.pow(10, q/-10) and om_lut[q] = 1.0 - e_lut[q] MUST be built by the caller with the
+ * host libm (never pow() on the device).  Writes up to `cap` candidates; *n_out is the
+ * number found (may exceed cap: call again with a larger buffer).  Also refreshes the dense
+ * per-position outputs (depth, A/C/G/T depth, A/C/G/T likelihood) readable by lvc_copy_dense. */
+int lvc_genotype(lvc_handle* h, int64_t min_total_depth, int64_t min_allele_depth, double min_evidence_ratio,
+                 const double* e_lut, const double* om_lut, uint32_t flags, lvc_candidate* out, uint32_t cap,
+                 uint32_t* n_out);
+/* device-only variant (no D2H, for timing); lvc_fetch_candidates reads the result back. */
+int lvc_genotype_device(lvc_handle* h, int64_t min_total_depth, int64_t min_allele_depth,
+                        double min_evidence_ratio, const double* e_lut, const double* om_lut, uint32_t flags);
+int lvc_fetch_candidates(lvc_handle* h, lvc_candidate* out, uint32_t cap, uint32_t* n_out);
+int lvc_copy_dense(lvc_handle* h, uint32_t* depth /*[G]*/, uint32_t* ad /*[G*4] A,C,G,T*/,
+                   double* lik /*[G*4]*/);
+
+/* ---- table access: self.memory (live_variant_caller.py:31), checkpoints (:40-52), tests, NCCL ----
+ * A "plane" holds, for one (allele group, quality) key, uint32 counts [G][4].  key = group<<8 | q;
+ * group 0 = A,C,G,T (slots 0..3); groups 1..3 hold the other BAM nibble codes:
+ * {=,M,R,S} {V,W,Y,H} {K,D,B,N}.  dels[G] counts deletion/ref-skip entries that passed the
+ * base-quality rule (totalDepth = sum of all counts + dels).  covdiff[G+1] is a difference array of
+ * read coverage (a site exists in `memory` iff its prefix sum is > 0).  first[group][G][4] is the
+ * ordinal of the first read that deposited (pos, allele), 0xFFFFFFFF if never. */
+int lvc_num_planes(lvc_handle* h);
+int lvc_plane_keys(lvc_handle* h, uint16_t* keys_out /*[lvc_num_planes]*/);
+int lvc_ensure_plane(lvc_handle* h, uint16_t key);
+int lvc_copy_plane(lvc_handle* h, uint16_t key, uint32_t* dst /*[G*4]*/);
+int lvc_import_plane(lvc_handle* h, uint16_t key, const uint32_t* src /*[G*4]*/, int accumulate);
+int lvc_copy_dels(lvc_handle* h, uint32_t* dst /*[G]*/);
+int lvc_import_dels(lvc_handle* h, const uint32_t* src, int accumulate);
+int lvc_copy_covdiff(lvc_handle* h, int32_t* dst /*[G+1]*/);
+int lvc_import_covdiff(lvc_handle* h, const int32_t* src, int accumulate);
+int lvc_copy_first(lvc_handle* h, int group, uint32_t* dst /*[G*4]*/); /* LVC_EINVAL if group unallocated */
+int lvc_import_first(lvc_handle* h, int group, const uint32_t* src);
+uint64_t lvc_ordinal(lvc_handle* h);              /* reads consumed so far (next first-seen ordinal) */
+int lvc_set_ordinal(lvc_handle* h, uint64_t ordinal);
+/* raw device pointers for zero-copy collectives (torch.distributed all_reduce over NCCL) */
+void* lvc_plane_devptr(lvc_handle* h, uint16_t key);
+void* lvc_dels_devptr(lvc_handle* h);
+void* lvc_covdiff_devptr(lvc_handle* h);
+void* lvc_first_devptr(lvc_handle* h, int group);
+
+/* ---- introspection ---------------------------------------------------------------------------- */
+/* number of kernels this library has launched on the handle since creation (bench gpu_launches) */
+uint64_t lvc_launch_count(lvc_handle* h);
+int lvc_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LVC_H_ */

@@ -1,0 +1,170 @@
+"""CPU: C-ABI symbols, host admission (lvc_admit) vs the oracle, packing, readers, record finalisation."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from helpers import GOLD, ROOT, po, synth_small, rows_to_tuples, variants_from_golden
+
+
+def test_abi_exports_every_declared_symbol(lib):
+    hdr = open(os.path.join(ROOT, "include", "lvc.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(lvc_[a-z_0-9]+)\s*\(", hdr))
+    assert len(names) >= 35
+    from lvc_b200 import capi
+    bound = {n for n, _, _ in capi.SIGNATURES}
+    assert names == bound, names ^ bound
+    for n in names:
+        assert hasattr(lib, n), n
+    assert lib.lvc_version() == 1
+    assert ctypes.sizeof(capi.Candidate) == 48
+
+
+def test_no_cpu_fallback_without_gpu(lib):
+    """Creating a handle without a CUDA device must fail loudly (no CPU path)."""
+    from conftest import has_gpu
+    if has_gpu():
+        pytest.skip("a GPU is present")
+    from lvc_b200 import capi
+    with pytest.raises(capi.LvcError) as ei:
+        capi.Handle(b"ACGT" * 10, 0, 0)
+    assert "LVC_ENODEVICE" in str(ei.value)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "covid-spings-variant-caller_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "oracle" not in txt.replace("oracle/", "").lower() or f == "__init__.py" or \
+                    all("import" not in ln for ln in txt.splitlines() if "oracle" in ln.lower()), f
+
+
+def test_lvc_admit_matches_oracle(lib, golden_synth):
+    from lvc_b200 import packing
+    import random
+    # golden scenarios incl. the >8000-reads-per-position one
+    for scen in ("mixed_small", "maxdepth", "amplicon_like"):
+        reads = synth_small.rows_to_reads(golden_synth[scen]["reads"])
+        for mq in (0, 20):
+            b = packing.pack_reads([(r.flag, r.pos, r.mapq, r.cigar, r.seq, r.qual) for r in reads], mq)
+            want = po.admission_mask([r.pos for r in reads], [r.end() for r in reads],
+                                     [po.passes_read_filter(r, mq) for r in reads])
+            assert (b.keep & 1).astype(bool).tolist() == want, scen
+    # random tiny max_depth
+    rng = random.Random(7)
+    for trial in range(40):
+        n = rng.randint(1, 200)
+        rd = []
+        for i in range(n):
+            pos = rng.choice([0, 0, 3, 3, 3, 7, 20, 21, 22, 40, 5000, 5001])
+            ln = rng.randint(1, 25)
+            rd.append(po.Read(rng.choice([0, 16, 0x400, 0x1, 0x3]), pos, rng.choice([60, 5]), [(0, ln)], "A" * ln, [30] * ln))
+        rd = po.samtools_sort(rd)
+        for md in (1, 2, 4, 8000):
+            b = packing.pack_reads([(r.flag, r.pos, r.mapq, r.cigar, r.seq, r.qual) for r in rd], 10, md)
+            want = po.admission_mask([r.pos for r in rd], [r.end() for r in rd],
+                                     [po.passes_read_filter(r, 10) for r in rd], md)
+            assert (b.keep & 1).astype(bool).tolist() == want, (trial, md)
+
+
+def test_unsorted_input_raises(lib):
+    from lvc_b200 import packing
+    with pytest.raises(ValueError):
+        packing.pack_reads([(0, 10, 60, [(0, 5)], "ACGTA", [30] * 5), (0, 3, 60, [(0, 5)], "ACGTA", [30] * 5)], 0)
+
+
+def test_packing_layout(lib):
+    from lvc_b200 import packing
+    b = packing.pack_reads([(0, 1, 60, [(4, 2), (0, 3)], "ACGTN", [1, 2, 3, 4, 5]),
+                            (16, 4, 60, [(0, 4)], "TTGA", [9, 9, 9, 9]),
+                            (0, 9, 60, [(0, 2), (1, 1), (0, 2)], "ACGTA", [30] * 5)], 0)
+    assert b.seq_off.tolist() == [0, 6, 10, 16]
+    assert b.seq4[:3].tolist() == [0x12, 0x48, 0xF0]
+    assert b.seq4[3:5].tolist() == [0x88, 0x41]
+    assert b.qual[:6].tolist() == [1, 2, 3, 4, 5, 0]
+    assert b.cigar[:2].tolist() == [(2 << 4) | 4, (3 << 4) | 0]
+    assert (b.keep & 1).tolist() == [1, 1, 1]
+    assert (b.keep >> 1).tolist() == [0, 1, 1]          # read 0 has an N; the pad nibble of odd reads is ignored
+    assert b.aligned_bases() == 3 + 4 + 4
+    assert b.algorithmic_bytes(100) == 3 * 20 + 4 * 6 + (3 + 2 + 3) + (5 + 4 + 5) + 5200
+
+
+def test_sam_and_bam_readers_agree(lib, tmp_path):
+    from lvc_b200 import samio
+    sam = os.path.join(GOLD, "testfile.sam")
+    contigs, b = samio.read_sam(sam, None, 0)
+    assert contigs == [("NC_045512.2", 29903)] and b.n_reads == 4
+    assert b.pos.tolist() == [10, 24, 24, 24]
+    assert b.aligned_bases() == 1609
+    _, reads = po.read_sam(sam)
+    bam = str(tmp_path / "t.bam")
+    samio.write_bam(bam, contigs, [(r.flag, r.pos, r.mapq, r.cigar, r.seq, r.qual, r.name) for r in reads])
+    contigs2, b2 = samio.read_alignments(bam, "NC_045512.2", 0)
+    assert contigs2 == contigs
+    for f in ("pos", "flag", "mapq", "keep", "cigar_off", "seq_off"):
+        assert getattr(b, f).tolist() == getattr(b2, f).tolist(), f
+    assert b.cigar[:b.n_cigar].tolist() == b2.cigar[:b2.n_cigar].tolist()
+    assert b.qual[:b.n_qual].tolist() == b2.qual[:b2.n_qual].tolist()
+    assert b.seq4[:b.n_qual // 2].tolist() == b2.seq4[:b2.n_qual // 2].tolist()
+    with pytest.raises(ValueError):
+        samio.read_alignments(bam, "chrNope", 0)
+    with pytest.raises(OSError):
+        samio.read_alignments(str(tmp_path / "missing.bam"), None, 0)
+
+
+def test_overlapping_mates_are_refused(lib, tmp_path):
+    from lvc_b200 import samio, packing
+    p = tmp_path / "ov.sam"
+    p.write_text("@SQ\tSN:c\tLN:1000\n"
+                 "a\t99\tc\t11\t60\t50M\t=\t41\t80\t" + "A" * 50 + "\t" + "I" * 50 + "\n"
+                 "a\t147\tc\t41\t60\t50M\t=\t11\t-80\t" + "A" * 50 + "\t" + "I" * 50 + "\n")
+    with pytest.raises(packing.UnsupportedInput):
+        samio.read_sam(str(p), None, 0)
+
+
+def test_record_finalisation_matches_golden(golden_synth):
+    """records.py turns (L, S, esum, AD, DP, first) into the reference's dicts: feed it the ORACLE's numbers."""
+    from lvc_b200 import records
+    from helpers import assert_variants_equal
+    g = golden_synth["deep_underflow"]
+    reads = synth_small.rows_to_reads(g["reads"])
+    th = g["results"]["zero"]["thresholds"]
+    oc = po.OracleCaller(g["ref"], th["minBQ"], th["minMQ"], th["minDP"], th["minAD"], th["ratio"])
+    oc.process_reads(reads)
+    rows = []
+    for p, site in oc.memory.items():
+        snvs = {a: [po.from_phred_scale(q) for q in site["snvs"][a]] for a in site["snvs"]}
+        L = {a: float(po.genotype_likelihood(a, snvs)) for a in snvs}
+        S = 0.0
+        for v in L.values():
+            S += v
+        S = S if S != 0 else 1.0
+        for rank, a in enumerate(snvs):
+            if site["reference"] != a:
+                rows.append((p, records.NIBBLE_CHARS.index(a), ord(site["reference"]), 0, len(snvs[a]),
+                             site["totalDepth"], rank, 0, L[a], S, float(np.sum(snvs[a]))))
+    from lvc_b200.capi import CANDIDATE_DTYPE
+    cands = np.array(rows, dtype=CANDIDATE_DTYPE)
+    got = records.candidates_to_variants(cands)
+    assert_variants_equal(got, variants_from_golden(g["results"]["zero"]["variants"]), "finalise")
+    e, om = records.phred_luts()
+    assert e[30] == 0.001 and om[0] == 0.0
+
+
+def test_vcf_text_layout():
+    from lvc_b200 import records
+    v = [{"start": 9, "stop": 10, "alleles": ("A", "G"), "qual": 0.000316227766, "info":
+          {"DP": 70, "AD": 60, "GL": -35.00824146158652, "PL": 350, "SCORE": 99}},
+         {"start": 9, "stop": 10, "alleles": ("A", "T"), "qual": 0.001, "info":
+          {"DP": 70, "AD": 5, "GL": 0, "PL": 0, "SCORE": 0}}]
+    txt = records.format_vcf(v, [("NC_045512.2", 29903)])
+    assert txt == po.format_vcf(v, [("NC_045512.2", 29903)])
+    lines = txt.strip().split("\n")
+    assert lines[0] == "##fileformat=VCFv4.2" and lines[-3].startswith("#CHROM")
+    assert lines[-2] == "NC_045512.2\t10\t.\tA\tT\t0.001\t.\tDP=70;AD=5;GL=0;PL=0;SCORE=0"
+    assert lines[-1] == "NC_045512.2\t10\t.\tA\tG\t0.000316228\t.\tDP=70;AD=60;GL=-35.0082;PL=350;SCORE=99"
