@@ -51,7 +51,8 @@ struct TileSmem {
     static constexpr uint32_t qo_off = len_off + kTileReads * 4;               // u32 [kTileReads]
     static constexpr uint32_t sn_off = qo_off + kTileReads * 4;                // u32 [kTileReads]
     static constexpr uint32_t so_off = sn_off + kTileReads * 4;                // u64 [kTileReads+1] seq_off copy
-    static constexpr uint32_t items_off = so_off + (kTileReads + 1) * 8 + 8;   // u16 [kTabCols*4]
+    static constexpr uint32_t rix_off = so_off + (kTileReads + 1) * 8 + 8;     // u16 [kTileReads] compacted -> chunk index
+    static constexpr uint32_t items_off = rix_off + kTileReads * 2;            // u16 [kTabCols*4]
     static constexpr uint32_t slab_a_off = items_off + kTabCols * 4 * 2;       // u32 [kMaxSlabs]
     static constexpr uint32_t slab_pre_off = slab_a_off + kMaxSlabs * 4;       // u32 [kMaxSlabs+1]
     static constexpr uint32_t slab_n_off = slab_pre_off + (kMaxSlabs + 1) * 4; // u32 [kMaxSlabs]
@@ -148,12 +149,13 @@ k_deposit_tile(BatchView b, TableView tv, DepositParams dp, TileParams tp, uint3
     uint32_t* s_qo = reinterpret_cast<uint32_t*>(smem + TileSmem::qo_off);
     uint32_t* s_sn = reinterpret_cast<uint32_t*>(smem + TileSmem::sn_off);
     uint64_t* s_so = reinterpret_cast<uint64_t*>(smem + TileSmem::so_off);
+    uint16_t* s_rix = reinterpret_cast<uint16_t*>(smem + TileSmem::rix_off);
     uint16_t* s_items = reinterpret_cast<uint16_t*>(smem + TileSmem::items_off);
     uint32_t* s_slab_a = reinterpret_cast<uint32_t*>(smem + TileSmem::slab_a_off);
     uint32_t* s_slab_pre = reinterpret_cast<uint32_t*>(smem + TileSmem::slab_pre_off);
     uint32_t* s_slab_n = reinterpret_cast<uint32_t*>(smem + TileSmem::slab_n_off);
     uint32_t* s_misc = reinterpret_cast<uint32_t*>(smem + TileSmem::misc_off);
-    // s_misc: [0,1] mbarrier, [2] task counter, [3] n_items, [4] cmin, [5] cmax, [6] maxlen, [7] sub_end
+    // s_misc: [0,1] mbarrier, [2] task counter, [3] n_items, [4] cmin, [5] cmax, [6] maxlen, [8..15] warp counts
     const uint32_t bar = sbase + TileSmem::misc_off;
     const uint32_t q_smem = sbase + TileSmem::qual_off + kSlack;     // staged qualities start here
     const uint32_t s_smem = sbase + TileSmem::seq_off + kSlack;      // staged 4-bit bases start here
@@ -209,7 +211,7 @@ k_deposit_tile(BatchView b, TableView tv, DepositParams dp, TileParams tp, uint3
         __syncthreads();
         {
             int32_t my_pos = 0x7FFFFFFF;
-            uint32_t my_len = 0;
+            uint32_t my_len = 0, my_qo = 0, my_sn = 0;
             if ((uint32_t)tid < n_sub) {
                 const uint32_t r = sub0 + tid, i = chunk0 + r;
                 const int32_t pos = b.pos[i];
@@ -247,13 +249,15 @@ k_deposit_tile(BatchView b, TableView tv, DepositParams dp, TileParams tp, uint3
                         my_len = len;
                         atomicAdd(&tv.covdiff[pos], 1);
                         atomicAdd(&tv.covdiff[pos + len], -1);
-                        s_qo[r - sub0] = (uint32_t)(s_so[r] - qbeg) + qstart;
-                        s_sn[r - sub0] = (uint32_t)(((s_so[r] >> 1) - sbeg16) * 2) + qstart;
+                        my_qo = (uint32_t)(s_so[r] - qbeg) + qstart;
+                        my_sn = (uint32_t)(((s_so[r] >> 1) - sbeg16) * 2) + qstart;
                     }
                 }
                 if (defer) defer_list[atomicAdd(&tv.status[ST_DEFERRED], 1u)] = i;
             }
-            if ((uint32_t)tid < n_sub) { s_pos[tid] = my_pos; s_len[tid] = my_len; }
+            // compact the active (simple, kept) reads: later loops never touch dropped / deferred reads
+            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, my_len != 0);
+            if (lane == 0) s_misc[8 + warp] = __popc(bal);
             // chunk column range over the simple reads
             int32_t lo = my_len ? my_pos : 0x7FFFFFFF;
             int32_t hi = my_len ? (int32_t)(my_pos + my_len) : 0;
@@ -266,8 +270,18 @@ k_deposit_tile(BatchView b, TableView tv, DepositParams dp, TileParams tp, uint3
                 atomicMax(reinterpret_cast<int32_t*>(&s_misc[5]), hi);
                 atomicMax(&s_misc[6], ml);
             }
+            __syncthreads();
+            uint32_t base = 0;
+            for (int w = 0; w < warp; ++w) base += s_misc[8 + w];
+            if (my_len) {
+                const uint32_t idx = base + __popc(bal & ((1u << lane) - 1u));
+                s_pos[idx] = my_pos; s_len[idx] = my_len; s_qo[idx] = my_qo; s_sn[idx] = my_sn;
+                s_rix[idx] = (uint16_t)tid;
+            }
         }
         __syncthreads();
+        uint32_t n_act = 0;
+        for (int w = 0; w < kTileWarps; ++w) n_act += s_misc[8 + w];
         const int32_t cmin = (int32_t)s_misc[4], cmax = (int32_t)s_misc[5];
         const uint32_t maxlen = s_misc[6];
         const bool any_simple = cmax > cmin && cmin != 0x7FFFFFFF;
@@ -280,7 +294,7 @@ k_deposit_tile(BatchView b, TableView tv, DepositParams dp, TileParams tp, uint3
             // per-slab candidate read range [a, a+n) by binary search over the sorted positions
             if (tid < nslab) {
                 const int32_t s_lo = wc0 + tid * kSlabCols, s_hi = s_lo + kSlabCols;
-                uint32_t lo = 0, hi = n_sub;             // first read with pos >= s_hi
+                uint32_t lo = 0, hi = n_act;             // first read with pos >= s_hi
                 while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if (s_pos[m] < s_hi) lo = m + 1; else hi = m; }
                 const uint32_t bnd = lo;
                 const int64_t thr = (int64_t)s_lo - (int64_t)maxlen;   // first read with pos > thr
@@ -356,7 +370,7 @@ k_deposit_tile(BatchView b, TableView tv, DepositParams dp, TileParams tp, uint3
                             acc[0][2] += (sw0 >> 2) & m0; acc[1][2] += (sw1 >> 2) & m1;
                             acc[0][3] += (sw0 >> 3) & m0; acc[1][3] += (sw1 >> 3) & m1;
                             if (other) {
-                                const uint32_t ord = dp.ord_base + chunk0 + sub0 + r;
+                                const uint32_t ord = dp.ord_base + chunk0 + sub0 + s_rix[r];
                                 if (o0) tile_slow_bytes(tv, dp, o0, q0, sw0, (int64_t)col_lane, ord);
                                 if (o1) tile_slow_bytes(tv, dp, o1, q1, sw1, (int64_t)col_lane + 4, ord);
                             }
@@ -418,10 +432,10 @@ k_deposit_tile(BatchView b, TableView tv, DepositParams dp, TileParams tp, uint3
                 const uint32_t e = s_items[it];
                 const int32_t col = wc0 + (int32_t)(e >> 2);
                 const uint32_t want = 1u << (e & 3u);
-                for (uint32_t r0 = 0; r0 < n_sub; r0 += 32) {
+                for (uint32_t r0 = 0; r0 < n_act; r0 += 32) {
                     const uint32_t r = r0 + lane;
                     bool hit = false;
-                    if (r < n_sub) {
+                    if (r < n_act) {
                         const int32_t j = col - s_pos[r];
                         if (j >= 0 && j < (int32_t)s_len[r]) {
                             const uint32_t qa = s_qo[r] + (uint32_t)j;
@@ -434,7 +448,7 @@ k_deposit_tile(BatchView b, TableView tv, DepositParams dp, TileParams tp, uint3
                     }
                     const uint32_t bal = __ballot_sync(0xFFFFFFFFu, hit);
                     if (bal) {
-                        if (lane == 0) atomicMin(&first0[(int64_t)col * 4 + (e & 3u)], chunk_ord0 + r0 + (__ffs(bal) - 1));
+                        if (lane == 0) atomicMin(&first0[(int64_t)col * 4 + (e & 3u)], chunk_ord0 + s_rix[r0 + (__ffs(bal) - 1)]);
                         break;
                     }
                 }

@@ -66,6 +66,28 @@ struct lvc_handle {
     uint32_t* d_cand_count = nullptr;
     uint32_t cand_cap = 0;
     uint32_t last_cand_count = 0;
+    bool geno_pending = false;               // an async genotype launch whose count has not been read yet
+
+    // optional per-kernel timing (CUDA events on the launching stream)
+    bool timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[3];   // 0 tiled deposit, 1 general deposit, 2 genotype
+    std::vector<cudaEvent_t> ev_pool;
+};
+
+static cudaEvent_t get_event(lvc_handle* h) {
+    if (!h->ev_pool.empty()) { cudaEvent_t e = h->ev_pool.back(); h->ev_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+struct KernelTimer {
+    lvc_handle* h; int which; cudaEvent_t a = nullptr, b = nullptr;
+    KernelTimer(lvc_handle* h_, int w) : h(h_), which(w) {
+        if (h->timing) { a = get_event(h); b = get_event(h); cudaEventRecord(a, h->stream); }
+    }
+    ~KernelTimer() {
+        if (h->timing) { cudaEventRecord(b, h->stream); h->ev[which].push_back({a, b}); }
+    }
 };
 
 static int fail(lvc_handle* h, int code, const char* fmt, ...) {
@@ -210,6 +232,8 @@ void lvc_destroy(lvc_handle* h) {
     cudaFree(h->d_first_arr); cudaFree(h->d_newkeys); cudaFree(h->d_replay); cudaFree(h->d_status);
     if (h->h_status) cudaFreeHost(h->h_status);
     if (h->h_sample) cudaFreeHost(h->h_sample);
+    for (int w = 0; w < 3; ++w) for (auto& pr : h->ev[w]) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    for (auto e : h->ev_pool) cudaEventDestroy(e);
     cudaFree(h->d_elut); cudaFree(h->d_out_depth); cudaFree(h->d_out_ad); cudaFree(h->d_out_lik);
     cudaFree(h->d_cand_count);
     for (DevBuf* b : {&h->b_pos, &h->b_flag, &h->b_mapq, &h->b_keep, &h->b_coff, &h->b_cig, &h->b_soff, &h->b_seq,
@@ -339,20 +363,24 @@ static int launch_deposit(lvc_handle* h, const BatchView& bv, int replay) {
     if (n == 0) return LVC_OK;
     const int impl = h->impl == 0 ? 2 : h->impl;
     if (impl == 1 || replay || h->qprim == 255 || h->lut[h->qprim] == kNoPlane) {
-        k_deposit_general<<<(n + 127) / 128, 128, 0, h->stream>>>(bv, tv, dp, nullptr, n);
+        { KernelTimer t(h, 1);
+          k_deposit_general<<<(n + 127) / 128, 128, 0, h->stream>>>(bv, tv, dp, nullptr, n); }
         h->launches++;
     } else {
         int rc = ensure(h, h->b_defer, (size_t)n * sizeof(uint32_t));
         if (rc) return rc;
+        CU(cudaMemsetAsync(h->d_status + ST_DEFERRED, 0, sizeof(uint32_t), h->stream));
         TileParams tp = make_tile_params(n, h->sm_count);
         tp.qprim = (uint32_t)h->qprim;
         tp.prim_plane = h->lut[h->qprim];
-        k_deposit_tile<<<tp.grid, kTileThreads, kTileSmemBytes, h->stream>>>(bv, tv, dp, tp, (uint32_t*)h->b_defer.p);
+        { KernelTimer t(h, 0);
+          k_deposit_tile<<<tp.grid, kTileThreads, kTileSmemBytes, h->stream>>>(bv, tv, dp, tp, (uint32_t*)h->b_defer.p); }
         h->launches++;
         // reads the tiled kernel could not take (long / irregular) go through the general kernel;
         // the count is on the device, so the launch is sized for the worst case and exits early.
-        k_deposit_general_deferred<<<std::min<uint32_t>((n + 127) / 128, 4096), 128, 0, h->stream>>>(
-            bv, tv, dp, (const uint32_t*)h->b_defer.p);
+        { KernelTimer t(h, 1);
+          k_deposit_general_deferred<<<std::min<uint32_t>((n + 127) / 128, 4096), 128, 0, h->stream>>>(
+              bv, tv, dp, (const uint32_t*)h->b_defer.p); }
         h->launches++;
     }
     CU(cudaGetLastError());
@@ -482,13 +510,67 @@ int lvc_push_batch_device(lvc_handle* h, const lvc_batch* b) {
     return deposit_with_replay(h, bv);
 }
 
+int lvc_push_batch_device_async(lvc_handle* h, const lvc_batch* b) {
+    int rc = validate_batch(h, b);
+    if (rc) return rc;
+    if (b->n_reads == 0) return LVC_OK;
+    CU(cudaSetDevice(h->device));
+    if ((uint64_t)h->ordinal + b->n_reads >= 0xFFFFFFFFull)
+        return fail(h, LVC_ERANGE, "first-seen ordinal space (2^32-1 reads per handle) exhausted");
+    BatchView bv;
+    bv.n_reads = b->n_reads;
+    bv.pos = b->pos; bv.flag = b->flag; bv.mapq = b->mapq; bv.keep = b->keep;
+    bv.cigar_off = b->cigar_off; bv.cigar = b->cigar; bv.seq_off = b->seq_off; bv.seq4 = b->seq4; bv.qual = b->qual;
+    rc = launch_deposit(h, bv, 0);
+    if (rc) return rc;
+    h->ordinal += b->n_reads;
+    return LVC_OK;
+}
+
+int lvc_check_async(lvc_handle* h) {
+    if (!h) return LVC_EINVAL;
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemcpyAsync(h->h_status, h->d_status, ST_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    const uint32_t unmapped = h->h_status[ST_UNMAPPED], range = h->h_status[ST_RANGE_ERR];
+    CU(cudaMemsetAsync(h->d_status, 0, ST_WORDS * sizeof(uint32_t), h->stream));
+    CU(cudaMemsetAsync(h->d_newkeys, 0, 32 * sizeof(uint32_t), h->stream));
+    if (range) return fail(h, LVC_ERANGE, "%u read(s) extend outside the reference; they were skipped", range);
+    if (unmapped)
+        return fail(h, LVC_EAGAIN, "%u base(s) had a (allele group, quality) key without a plane during async pushes; "
+                    "their counts are missing -- push the first batch of a stream synchronously", unmapped);
+    return LVC_OK;
+}
+
+int lvc_set_timing(lvc_handle* h, int on) {
+    if (!h) return LVC_EINVAL;
+    h->timing = on != 0;
+    return LVC_OK;
+}
+
+int lvc_get_timing(lvc_handle* h, int which, double* ms_total, uint64_t* n_launches) {
+    if (!h || which < 0 || which > 2 || !ms_total || !n_launches) return LVC_EINVAL;
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    double tot = 0.0;
+    for (auto& pr : h->ev[which]) {
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, pr.first, pr.second));
+        tot += ms;
+        h->ev_pool.push_back(pr.first);
+        h->ev_pool.push_back(pr.second);
+    }
+    *ms_total = tot;
+    *n_launches = h->ev[which].size();
+    h->ev[which].clear();
+    return LVC_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // genotype
 // ------------------------------------------------------------------------------------------------
-int lvc_genotype_device(lvc_handle* h, int64_t min_total_depth, int64_t min_allele_depth, double min_ratio,
-                        const double* e_lut, const double* om_lut, uint32_t flags) {
-    if (!h || !e_lut || !om_lut) return LVC_EINVAL;
-    CU(cudaSetDevice(h->device));
+static int genotype_enqueue(lvc_handle* h, int64_t min_total_depth, int64_t min_allele_depth, double min_ratio,
+                            const double* e_lut, const double* om_lut, uint32_t flags) {
     const int np = (int)h->planes.size();
     // order planes: group 0 first (register path), then the rest
     std::vector<int> order(np);
@@ -515,24 +597,44 @@ int lvc_genotype_device(lvc_handle* h, int64_t min_total_depth, int64_t min_alle
     CU(cudaMemcpyAsync(h->g_order_keys.p, keys.data(), keys.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->d_elut, e_lut, 256 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->d_elut + 256, om_lut, 256 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    for (int attempt = 0; attempt < 2; ++attempt) {
-        CU(cudaMemsetAsync(h->d_cand_count, 0, sizeof(uint32_t), h->stream));
-        GenoParams gp;
-        gp.G = h->G; gp.min_total_depth = min_total_depth; gp.min_allele_depth = min_allele_depth;
-        gp.min_ratio = min_ratio; gp.flags = flags; gp.n_planes = np; gp.n_g0 = n_g0; gp.cand_cap = h->cand_cap;
-        const size_t smem = (size_t)std::max(np, 1) * (2 * sizeof(XF) + sizeof(double));
-        const int threads = 128;
-        const unsigned blocks = (unsigned)((h->G + threads - 1) / threads);
+    CU(cudaMemsetAsync(h->d_cand_count, 0, sizeof(uint32_t), h->stream));
+    GenoParams gp;
+    gp.G = h->G; gp.min_total_depth = min_total_depth; gp.min_allele_depth = min_allele_depth;
+    gp.min_ratio = min_ratio; gp.flags = flags; gp.n_planes = np; gp.n_g0 = n_g0; gp.cand_cap = h->cand_cap;
+    const size_t smem = (size_t)std::max(np, 1) * (2 * sizeof(XF) + sizeof(double));
+    const int threads = 128;
+    const unsigned blocks = (unsigned)((h->G + threads - 1) / threads);
+    {
+        KernelTimer t(h, 2);
         k_genotype<<<blocks, threads, smem, h->stream>>>(gp, (const uint32_t* const*)h->g_order_ptrs.p,
                                                         (const uint16_t*)h->g_order_keys.p, h->d_elut, h->d_elut + 256,
                                                         h->d_dels, h->d_ref, (const uint32_t* const*)h->d_first_arr,
                                                         h->d_out_depth, h->d_out_ad, h->d_out_lik,
                                                         (lvc_candidate*)h->g_cand.p, h->d_cand_count);
-        h->launches++;
-        CU(cudaGetLastError());
-        CU(cudaMemcpyAsync(h->h_status, h->d_cand_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
-        CU(cudaStreamSynchronize(h->stream));
-        h->last_cand_count = h->h_status[0];
+    }
+    h->launches++;
+    CU(cudaGetLastError());
+    h->geno_pending = true;
+    return LVC_OK;
+}
+
+static int genotype_read_count(lvc_handle* h) {
+    CU(cudaMemcpyAsync(h->h_status, h->d_cand_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->last_cand_count = h->h_status[0];
+    h->geno_pending = false;
+    return LVC_OK;
+}
+
+int lvc_genotype_device(lvc_handle* h, int64_t min_total_depth, int64_t min_allele_depth, double min_ratio,
+                        const double* e_lut, const double* om_lut, uint32_t flags) {
+    if (!h || !e_lut || !om_lut) return LVC_EINVAL;
+    CU(cudaSetDevice(h->device));
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        int rc = genotype_enqueue(h, min_total_depth, min_allele_depth, min_ratio, e_lut, om_lut, flags);
+        if (rc) return rc;
+        rc = genotype_read_count(h);
+        if (rc) return rc;
         if (h->last_cand_count <= h->cand_cap) break;
         // grow and run once more (rare: more candidates than the buffer)
         h->cand_cap = h->last_cand_count + h->last_cand_count / 4 + 1024;
@@ -542,11 +644,19 @@ int lvc_genotype_device(lvc_handle* h, int64_t min_total_depth, int64_t min_alle
     return LVC_OK;
 }
 
+int lvc_genotype_device_async(lvc_handle* h, int64_t min_total_depth, int64_t min_allele_depth, double min_ratio,
+                              const double* e_lut, const double* om_lut, uint32_t flags) {
+    if (!h || !e_lut || !om_lut) return LVC_EINVAL;
+    CU(cudaSetDevice(h->device));
+    return genotype_enqueue(h, min_total_depth, min_allele_depth, min_ratio, e_lut, om_lut, flags);
+}
+
 int lvc_fetch_candidates(lvc_handle* h, lvc_candidate* out, uint32_t cap, uint32_t* n_out) {
     if (!h || !n_out) return LVC_EINVAL;
     CU(cudaSetDevice(h->device));
+    if (h->geno_pending) { int rc = genotype_read_count(h); if (rc) return rc; }
     *n_out = h->last_cand_count;
-    const uint32_t n = std::min(cap, h->last_cand_count);
+    const uint32_t n = std::min(std::min(cap, h->last_cand_count), h->cand_cap);
     if (n && out) {
         CU(cudaMemcpyAsync(out, h->g_cand.p, (size_t)n * sizeof(lvc_candidate), cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));

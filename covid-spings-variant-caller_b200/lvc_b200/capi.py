@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "liblvc_b200.so")
 
 LVC_OK = 0
 ERRORS = {-1: "LVC_EINVAL", -2: "LVC_ECUDA", -3: "LVC_ENOMEM", -4: "LVC_EUNSORTED", -5: "LVC_ERANGE",
-          -6: "LVC_ENODEVICE"}
+          -6: "LVC_ENODEVICE", -7: "LVC_EAGAIN"}
 GENO_EMIT_ALL = 1
 MAX_DEPTH_DEFAULT = 8000
 
@@ -62,6 +62,11 @@ SIGNATURES = [
     ("lvc_push_batch", C.c_int, [_H, C.POINTER(Batch)]),
     ("lvc_push_batch_device", C.c_int, [_H, C.POINTER(Batch)]),
     ("lvc_set_impl", C.c_int, [_H, C.c_int]),
+    ("lvc_push_batch_device_async", C.c_int, [_H, C.POINTER(Batch)]),
+    ("lvc_check_async", C.c_int, [_H]),
+    ("lvc_genotype_device_async", C.c_int, [_H, C.c_int64, C.c_int64, C.c_double, C.c_void_p, C.c_void_p, C.c_uint32]),
+    ("lvc_set_timing", C.c_int, [_H, C.c_int]),
+    ("lvc_get_timing", C.c_int, [_H, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     ("lvc_host_alloc", C.c_void_p, [C.c_uint64]),
     ("lvc_host_free", None, [C.c_void_p]),
     ("lvc_genotype", C.c_int, [_H, C.c_int64, C.c_int64, C.c_double, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
@@ -187,6 +192,25 @@ class Handle:
 
     def push_batch_device(self, batch: Batch):
         self._check(self.lib.lvc_push_batch_device(self.h, C.byref(batch)))
+
+    def push_batch_device_async(self, batch: Batch):
+        self._check(self.lib.lvc_push_batch_device_async(self.h, C.byref(batch)))
+
+    def check_async(self):
+        self._check(self.lib.lvc_check_async(self.h))
+
+    def genotype_device_async(self, min_total_depth, min_allele_depth, min_ratio, e_lut, om_lut, flags=0):
+        self._check(self.lib.lvc_genotype_device_async(self.h, int(min_total_depth), int(min_allele_depth),
+                                                       float(min_ratio), e_lut.ctypes.data, om_lut.ctypes.data,
+                                                       int(flags)))
+
+    def set_timing(self, on: bool):
+        self._check(self.lib.lvc_set_timing(self.h, int(on)))
+
+    def get_timing(self, which: int):
+        ms, n = C.c_double(0), C.c_uint64(0)
+        self._check(self.lib.lvc_get_timing(self.h, which, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
 
     # ---- genotype
     def genotype(self, min_total_depth: int, min_allele_depth: int, min_ratio: float, e_lut: np.ndarray,

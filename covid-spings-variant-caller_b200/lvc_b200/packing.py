@@ -175,3 +175,35 @@ def pack_reads(reads: Iterable[Tuple[int, int, int, Sequence[Tuple[int, int]], s
     seq4 = np.concatenate(seq_parts) if seq_parts else np.zeros(0, np.uint8)
     qual = np.concatenate(qual_parts) if qual_parts else np.zeros(0, np.uint8)
     return finalize_batch(pos, flag, mapq, coff, cig, soff, seq4, qual, min_mapq, max_depth)
+
+
+class _Pinned:
+    """one cudaHostAlloc'ed buffer exposed as a numpy array; freed with the object."""
+
+    def __init__(self, a: np.ndarray):
+        import ctypes as C
+        self._lib = capi.load_library()
+        nbytes = max(int(a.nbytes), 1)
+        self.ptr = self._lib.lvc_host_alloc(nbytes)
+        if not self.ptr:
+            raise MemoryError("lvc_host_alloc (cudaHostAlloc) failed")
+        buf = (C.c_uint8 * nbytes).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=a.dtype, count=a.size).reshape(a.shape)
+        self.array[...] = a
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self._lib.lvc_host_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+def pin_batch(b: ReadBatch) -> ReadBatch:
+    """Copy a batch into page-locked host memory so lvc_push_batch's H2D copies run at full PCIe speed."""
+    pins = [_Pinned(getattr(b, f)) for f in ("pos", "flag", "mapq", "keep", "cigar_off", "cigar", "seq_off", "seq4",
+                                              "qual")]
+    out = ReadBatch(*[p.array for p in pins])
+    out._pins = pins            # keep the allocations alive as long as the batch
+    return out

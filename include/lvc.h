@@ -28,6 +28,7 @@ extern "C" {
 #define LVC_EUNSORTED (-4)  /* reads not coordinate sorted (htslib errors out too)   */
 #define LVC_ERANGE (-5)     /* a read extends past the reference / ordinal space exhausted      */
 #define LVC_ENODEVICE (-6)  /* no CUDA device: there is NO CPU fallback                          */
+#define LVC_EAGAIN (-7)     /* async pushes met a new (allele group, quality) key: redo synchronously */
 
 #define LVC_MAX_DEPTH_DEFAULT 8000 /* pysam pileup() default max_depth [EXT], SURVEY B1/B4 */
 
@@ -43,9 +44,12 @@ typedef struct lvc_handle lvc_handle;
  *                 start at seq4[seq_off[i]/2] (BAM nibble codes "=ACMGRSVTWYHKDBN", high nibble first).
  *                 l_qseq of a read is the sum of its query-consuming CIGAR ops (BAM invariant).
  *   cigar       = BAM encoding  len<<4 | op,  op in MIDNSHP=X (0..8).
- *   keep[i]     = 1 if the read survives the host-side, order-dependent admission rules
- *                 (htslib max_depth rule; computed by lvc_admit).  flag / mapq / orphan
- *                 filters are re-evaluated on the device.
+ *   keep[i]     bit0 = the read survives the host-side, order-dependent admission rules (htslib
+ *                 max_depth rule; computed by lvc_admit); flag / mapq / orphan filters
+ *                  are re-evaluated on the device.  bit1 = hint: every base of the read
+ *                 is A, C, G or T (set ONLY if true; reads without it take the general kernel).
+ *   The payload arrays seq4 / qual must be readable for 16 bytes past their end (TMA stages whole
+ *   16-byte groups) and 16-byte aligned at their start.
  */
 typedef struct lvc_batch {
     uint32_t n_reads;
@@ -110,6 +114,12 @@ int lvc_admit(uint32_t n_reads, const int32_t* pos, const uint16_t* flag, const 
 int lvc_push_batch(lvc_handle* h, const lvc_batch* host_batch);
 int lvc_push_batch_device(lvc_handle* h, const lvc_batch* device_batch);
 int lvc_set_impl(lvc_handle* h, int impl);
+/* Stream-ordered variant for back-to-back live batches: enqueues the kernels and returns.  No replay is
+ * possible, so every (allele group, quality) key must already have a plane (true after the first
+ * synchronous push of a run with the same quality alphabet); lvc_check_async() synchronises and
+ * reports LVC_EAGAIN if a key was missing, LVC_ERANGE if a read left the reference. */
+int lvc_push_batch_device_async(lvc_handle* h, const lvc_batch* device_batch);
+int lvc_check_async(lvc_handle* h);
 /* pinned host memory for the SoA buffers (cudaHostAlloc) */
 void* lvc_host_alloc(uint64_t bytes);
 void lvc_host_free(void* p);
@@ -125,6 +135,8 @@ int lvc_genotype(lvc_handle* h, int64_t min_total_depth, int64_t min_allele_dept
 /* device-only variant (no D2H, for timing); lvc_fetch_candidates reads the result back. */
 int lvc_genotype_device(lvc_handle* h, int64_t min_total_depth, int64_t min_allele_depth,
                         double min_evidence_ratio, const double* e_lut, const double* om_lut, uint32_t flags);
+int lvc_genotype_device_async(lvc_handle* h, int64_t min_total_depth, int64_t min_allele_depth,
+                              double min_evidence_ratio, const double* e_lut, const double* om_lut, uint32_t flags);
 int lvc_fetch_candidates(lvc_handle* h, lvc_candidate* out, uint32_t cap, uint32_t* n_out);
 int lvc_copy_dense(lvc_handle* h, uint32_t* depth /*[G]*/, uint32_t* ad /*[G*4] A,C,G,T*/,
                    double* lik /*[G*4]*/);
@@ -158,6 +170,10 @@ void* lvc_first_devptr(lvc_handle* h, int group);
 /* ---- introspection ---------------------------------------------------------------------------- */
 /* number of kernels this library has launched on the handle since creation (bench gpu_launches) */
 uint64_t lvc_launch_count(lvc_handle* h);
+/* per-kernel device time from CUDA events recorded on the handle's stream around every launch while
+ * timing is on.  which: 0 = tiled deposit, 1 = general deposit, 2 = genotype.  Reading resets. */
+int lvc_set_timing(lvc_handle* h, int on);
+int lvc_get_timing(lvc_handle* h, int which, double* ms_total, uint64_t* n_launches);
 int lvc_version(void);
 
 #ifdef __cplusplus

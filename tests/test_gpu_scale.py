@@ -1,0 +1,135 @@
+"""GPU parity at scale: the CUDA path against the C oracle (reference-order streaming products) on the
+synthetic BASELINE workloads, plus size-independent properties (both kernels agree bit for bit;
+re-depositing a batch doubles every count; sum of counts == bases that pass the filters)."""
+import numpy as np
+import pytest
+
+from helpers import close_lik
+
+pytestmark = pytest.mark.gpu
+
+TH = dict(minBQ=30, minMQ=20, minDP=10, minAD=5, ratio=0.10)
+GS_TO_NIB = [1, 2, 4, 8, 0, 3, 5, 6, 7, 9, 10, 11, 12, 13, 14, 15]
+
+
+def device_tables(h):
+    """(ad[G,16] by nibble code, qsum[G,16], first[G,16], dels[G], cov[G]) from the device planes."""
+    G = h.G
+    ad = np.zeros((G, 16), np.uint64)
+    qsum = np.zeros((G, 16), np.uint64)
+    first = np.full((G, 16), 0xFFFFFFFF, np.uint32)
+    for key in h.plane_keys():
+        g, q = int(key) >> 8, int(key) & 255
+        pl = h.copy_plane(int(key)).astype(np.uint64)
+        for s in range(4):
+            nib = GS_TO_NIB[g * 4 + s]
+            ad[:, nib] += pl[:, s]
+            qsum[:, nib] += pl[:, s] * np.uint64(q)
+    for g in range(4):
+        f = h.copy_first(g)
+        if f is not None:
+            for s in range(4):
+                first[:, GS_TO_NIB[g * 4 + s]] = f[:, s]
+    return ad, qsum, first, h.copy_dels(), np.cumsum(h.copy_covdiff()[:-1])
+
+
+def check_against_c_oracle(ref, batches, th, impl, max_depth=8000):
+    from lvc_b200 import capi, records
+    from oracle.c_oracle import COracle
+    e_lut, om_lut = records.phred_luts()
+    h = capi.Handle(ref.encode("latin-1"), th["minBQ"], th["minMQ"], device=0)
+    h.set_impl(impl)
+    co = COracle(ref, th["minBQ"], th["minMQ"], max_depth)
+    for b in batches:
+        h.push_batch(b.as_capi())
+        co.process(b)
+    ad, qsum, first, dels, cov = device_tables(h)
+    assert np.array_equal(ad, co.ad.astype(np.uint64)), "allele depth tables differ"
+    assert np.array_equal(qsum, co.qsum), "quality-sum checksum differs"
+    assert np.array_equal(cov.astype(np.uint32), co.cov), "coverage (site set) differs"
+    assert np.array_equal(ad.sum(axis=1) + dels, co.depth.astype(np.uint64)), "totalDepth differs"
+    assert np.array_equal(first[ad > 0], co.first[co.ad > 0]), "first-seen ordinals differ"
+    # likelihoods + emission
+    L, S, emit, n_emit = co.genotype(th["minDP"], th["minAD"], th["ratio"])
+    cands = h.genotype(th["minDP"], th["minAD"], th["ratio"], e_lut, om_lut)
+    got = sorted((int(c["pos"]), int(c["code"])) for c in cands)
+    want = sorted(zip(*[x.tolist() for x in np.nonzero(emit)]))
+    assert got == want, "emitted (position, allele) set differs"
+    for c in cands:
+        p, code = int(c["pos"]), int(c["code"])
+        assert close_lik(float(c["L"]), float(L[p, code]), int(co.depth[p]) + 4), (p, code, c["L"], L[p, code])
+        assert close_lik(float(c["S"]), float(S[p]), int(co.depth[p]) + 4)
+        assert int(c["dp"]) == int(co.depth[p]) and int(c["ad"]) == int(co.ad[p, code])
+        assert abs(float(c["esum"]) - co.esum[p, code]) <= 1e-10 * co.esum[p, code]
+    depth, dad, dlik = h.copy_dense()
+    assert np.array_equal(depth, co.depth)
+    for s, nib in enumerate((1, 2, 4, 8)):
+        assert np.array_equal(dad[:, s], co.ad[:, nib])
+        a, b = dlik[:, s], L[:, nib]
+        bad = [p for p in np.nonzero(a != b)[0] if not close_lik(float(a[p]), float(b[p]), int(co.depth[p]) + 4)]
+        assert not bad, (nib, bad[:5], a[bad[:5]], b[bad[:5]])
+    h.close()
+    return n_emit
+
+
+@pytest.mark.parametrize("impl", [1, 2])
+def test_amplicon_medium(lib, impl):
+    from lvc_b200 import synth
+    ref, b = synth.amplicon_sample(seed=7, n_pairs=120_000)
+    n = check_against_c_oracle(ref, [b], TH, impl)
+    assert n > 0
+
+
+@pytest.mark.parametrize("th", [dict(minBQ=20, minMQ=0, minDP=5, minAD=2, ratio=0.02),
+                                dict(minBQ=0, minMQ=0, minDP=1, minAD=1, ratio=0.0)])
+def test_amplicon_multi_quality(lib, th):
+    """several passing quality values: the non-primary ones take the tile kernel's per-base path"""
+    from lvc_b200 import synth
+    ref, b = synth.amplicon_sample(seed=8, n_pairs=30_000, min_mapq=th["minMQ"])
+    check_against_c_oracle(ref, [b], th, 2)
+
+
+@pytest.mark.parametrize("impl", [1, 2])
+def test_shotgun_small_genome(lib, impl):
+    from lvc_b200 import synth
+    ref, b = synth.shotgun_sample(seed=9, ref_len=200_000, depth=60.0)
+    check_against_c_oracle(ref, [b], TH, impl)
+
+
+def test_shotgun_low_max_depth(lib):
+    """max_depth admission on shotgun data (drops are position dependent)"""
+    from lvc_b200 import synth
+    ref, b = synth.shotgun_sample(seed=10, ref_len=30_000, depth=400.0, max_depth=200)
+    check_against_c_oracle(ref, [b], TH, 2, max_depth=200)
+
+
+def test_live_batches_ont(lib):
+    from lvc_b200 import synth
+    ref = synth.random_reference(6000, 3)
+    batches = [synth.ont_batch(100 + k, ref, depth=40.0) for k in range(3)]
+    th = dict(minBQ=13, minMQ=20, minDP=10, minAD=3, ratio=0.05)
+    for impl in (1, 2):
+        check_against_c_oracle(ref, batches, th, impl)
+
+
+def test_full_size_config2_properties(lib):
+    """BASELINE configs[1] at full size: C-oracle parity + idempotence-style properties."""
+    from lvc_b200 import synth, capi
+    ref, b = synth.amplicon_sample()
+    assert b.n_reads == 1_993_534 and abs(b.aligned_bases() - 2.99e8) < 1e6
+    assert abs(b.algorithmic_bytes(len(ref)) - 0.498e9) < 2e6          # 0.498 GB
+    check_against_c_oracle(ref, [b], TH, 2)
+    # both kernels agree bit for bit; depositing the batch twice doubles every count
+    tabs = []
+    for impl, times in ((1, 1), (2, 1), (2, 2)):
+        h = capi.Handle(ref.encode("latin-1"), TH["minBQ"], TH["minMQ"], device=0)
+        h.set_impl(impl)
+        for _ in range(times):
+            h.push_batch(b.as_capi())
+        tabs.append(device_tables(h))
+        h.close()
+    for x, y in zip(tabs[0][:2] + tabs[0][3:], tabs[1][:2] + tabs[1][3:]):
+        assert np.array_equal(x, y)
+    assert np.array_equal(tabs[0][2], tabs[1][2])
+    assert np.array_equal(tabs[2][0], 2 * tabs[1][0]) and np.array_equal(tabs[2][1], 2 * tabs[1][1])
+    assert np.array_equal(tabs[2][2], tabs[1][2])                       # first-seen ranks do not move
