@@ -215,7 +215,8 @@ def main():
     dbatch = capi.Handle.make_batch(batch.n_reads, batch.n_cigar, batch.n_qual,
                                     *[t_arr[k].data_ptr() for k in ("pos", "flag", "mapq", "keep", "cigar_off", "cigar",
                                                                     "seq_off", "seq4", "qual")])
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)          # a real (non-null) stream: the library launches on it
+    torch.cuda.set_stream(stream)
     h = capi.Handle(ref.encode("latin-1"), THRESH["minBQ"], THRESH["minMQ"], device=local, stream=stream.cuda_stream)
     h.set_impl(args.kernel_impl)
 

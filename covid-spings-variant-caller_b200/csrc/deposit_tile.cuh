@@ -46,12 +46,13 @@ struct TileSmem {
     static constexpr uint32_t seq_bytes = kSlack + kQCap / 2 + 32 + kSlack;
     static constexpr uint32_t tab_off = seq_off + seq_bytes;                   // u32 [kTabCols*4]
     static constexpr uint32_t tab_bytes = kTabCols * 4 * 4;
-    static constexpr uint32_t pos_off = tab_off + tab_bytes;                   // i32 [kTileReads]
-    static constexpr uint32_t len_off = pos_off + kTileReads * 4;              // u32 [kTileReads]
-    static constexpr uint32_t qo_off = len_off + kTileReads * 4;               // u32 [kTileReads]
-    static constexpr uint32_t sn_off = qo_off + kTileReads * 4;                // u32 [kTileReads]
-    static constexpr uint32_t so_off = sn_off + kTileReads * 4;                // u64 [kTileReads+1] seq_off copy
-    static constexpr uint32_t rix_off = so_off + (kTileReads + 1) * 8 + 8;     // u16 [kTileReads] compacted -> chunk index
+    // per ACTIVE read (compacted, coordinate order), offsets relative to the chunk's first byte
+    static constexpr uint32_t pos_off = tab_off + tab_bytes;                   // i32 [kTileReads] run start column
+    static constexpr uint32_t len_off = pos_off + kTileReads * 4;              // u32 [kTileReads] run length
+    static constexpr uint32_t qo_off = len_off + kTileReads * 4;               // u32 [kTileReads] run's first quality byte
+    static constexpr uint32_t beg_off = qo_off + kTileReads * 4;               // u32 [kTileReads] read's first byte
+    static constexpr uint32_t end_off = beg_off + kTileReads * 4;              // u32 [kTileReads] read's end byte
+    static constexpr uint32_t rix_off = end_off + kTileReads * 4;              // u16 [kTileReads] index within the chunk
     static constexpr uint32_t items_off = rix_off + kTileReads * 2;            // u16 [kTabCols*4]
     static constexpr uint32_t slab_a_off = items_off + kTabCols * 4 * 2;       // u32 [kMaxSlabs]
     static constexpr uint32_t slab_pre_off = slab_a_off + kMaxSlabs * 4;       // u32 [kMaxSlabs+1]
@@ -77,7 +78,6 @@ inline TileParams make_tile_params(uint32_t n_reads, int sm_count) {
     (void)sm_count;
     return tp;
 }
-
 // ---- PTX helpers -------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -139,6 +139,33 @@ __device__ __noinline__ void tile_slow_bytes(const TableView& tv, const DepositP
     }
 }
 
+// one (read, 8 columns) unit of a pass: aligned shared loads -> 8 qualities + 8 spread base nibbles
+struct PassUnit {
+    uint32_t q0, q1, sw0, sw1;
+    int32_t j, len;
+};
+
+__device__ __forceinline__ PassUnit pass_load(uint32_t q_smem, uint32_t s_smem, int32_t qa, int32_t sn_delta,
+                                              int32_t j, int32_t len) {
+    PassUnit u;
+    u.j = j; u.len = len;
+    // 8 qualities, byte aligned from three aligned shared words
+    const uint32_t a = q_smem + (uint32_t)(qa & ~3);
+    const uint32_t x0 = lds32(a), x1 = lds32(a + 4), x2 = lds32(a + 8);
+    const uint32_t sh = (uint32_t)(qa & 3) * 8u;
+    u.q0 = __funnelshift_r(x0, x1, sh);
+    u.q1 = __funnelshift_r(x1, x2, sh);
+    // 8 base nibbles (big-endian within bytes) from two aligned shared words
+    const int32_t ni = qa + sn_delta;
+    const uint32_t sa = s_smem + (uint32_t)((ni >> 1) & ~3);
+    const uint32_t y0 = __byte_perm(lds32(sa), 0, 0x0123);
+    const uint32_t y1 = __byte_perm(lds32(sa + 4), 0, 0x0123);
+    const uint32_t V = __funnelshift_l(y1, y0, (uint32_t)(ni & 7) * 4u);
+    u.sw0 = spread_nibbles(V, 0x2233);
+    u.sw1 = spread_nibbles(V, 0x0011);
+    return u;
+}
+
 __global__ void __launch_bounds__(kTileThreads, 3)
 k_deposit_tile(BatchView b, TableView tv, DepositParams dp, TileParams tp, uint32_t* __restrict__ defer_list) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -147,8 +174,8 @@ k_deposit_tile(BatchView b, TableView tv, DepositParams dp, TileParams tp, uint3
     int32_t* s_pos = reinterpret_cast<int32_t*>(smem + TileSmem::pos_off);
     uint32_t* s_len = reinterpret_cast<uint32_t*>(smem + TileSmem::len_off);
     uint32_t* s_qo = reinterpret_cast<uint32_t*>(smem + TileSmem::qo_off);
-    uint32_t* s_sn = reinterpret_cast<uint32_t*>(smem + TileSmem::sn_off);
-    uint64_t* s_so = reinterpret_cast<uint64_t*>(smem + TileSmem::so_off);
+    uint32_t* s_beg = reinterpret_cast<uint32_t*>(smem + TileSmem::beg_off);
+    uint32_t* s_end = reinterpret_cast<uint32_t*>(smem + TileSmem::end_off);
     uint16_t* s_rix = reinterpret_cast<uint16_t*>(smem + TileSmem::rix_off);
     uint16_t* s_items = reinterpret_cast<uint16_t*>(smem + TileSmem::items_off);
     uint32_t* s_slab_a = reinterpret_cast<uint32_t*>(smem + TileSmem::slab_a_off);
@@ -164,141 +191,156 @@ k_deposit_tile(BatchView b, TableView tv, DepositParams dp, TileParams tp, uint3
     const uint32_t chunk0 = blockIdx.x * kTileReads;
     const uint32_t n_chunk = min((uint32_t)kTileReads, b.n_reads - chunk0);
 
+    // ---- (1) per-read headers: issue the global loads first, then the shared-memory setup
+    const bool mine = (uint32_t)tid < n_chunk;
+    const uint32_t i = chunk0 + (mine ? tid : 0);
+    const int32_t pos = b.pos[i];
+    const uint32_t flag = b.flag[i], mapq = b.mapq[i], keep = b.keep[i];
+    const uint32_t c0 = b.cigar_off[i], c1 = b.cigar_off[i + 1];
+    const uint64_t so0 = b.seq_off[chunk0];
+    const uint64_t so_r = b.seq_off[i], so_r1 = b.seq_off[i + 1];
+
     if (tid == 0) mbar_init(bar, 1);
-    for (uint32_t r = tid; r <= n_chunk; r += kTileThreads) s_so[r] = b.seq_off[chunk0 + r];
-    for (int i = tid; i < kTabCols * 4; i += kTileThreads) s_tab[i] = 0;
+    if (tid < 8) s_misc[2 + tid] = (tid == 2) ? 0x7FFFFFFFu : 0u;     // [4] = cmin = INT_MAX, the others 0
+    for (int k = tid; k < kTabCols * 4; k += kTileThreads) s_tab[k] = 0;
     __syncthreads();
 
     const uint32_t qprim4 = tp.qprim * 0x01010101u;
     const int mbq = dp.min_bq < 1 ? 1 : (dp.min_bq > 128 ? 128 : dp.min_bq);
     const uint32_t ge_add4 = (uint32_t)(0x80 - mbq) * 0x01010101u;
     const bool ge_all = dp.min_bq <= 0;           // every quality passes
+
+    // ---- (2) classify: filter, "simple" test (one contiguous match run + clips), defer the rest
+    uint32_t my_len = 0, my_qstart = 0;
+    {
+        bool defer = false;
+        if (mine && read_passes_filter(flag, mapq, keep, dp.min_mq)) {
+            uint32_t qstart = 0, len = 0, phase_c = 0;
+            bool simple = (c1 - c0) <= (uint32_t)kMaxCigarSimple && c1 > c0;
+            bool has_ref = false;
+            for (uint32_t k = c0; k < c1 && simple; ++k) {
+                const uint32_t c = b.cigar[k], op = c & 15u, l = c >> 4;
+                if (op_is_match(op)) {
+                    if (phase_c == 2) simple = false;
+                    phase_c = 1; len += l; has_ref = true;
+                } else if (op == 4) {
+                    if (phase_c == 0) qstart += l; else phase_c = 2;
+                } else if (op == 5) {
+                    if (phase_c == 1) phase_c = 2;
+                } else simple = false;
+            }
+            if (!simple) {
+                // a record with no reference-consuming op at all is skipped everywhere
+                bool any_ref = false;
+                for (uint32_t k = c0; k < c1; ++k) any_ref |= op_consumes_ref(b.cigar[k] & 15u);
+                defer = any_ref;
+            } else if (!has_ref || len == 0) {
+                // only clips: skipped like the general kernel does
+            } else if ((so_r1 - so_r) > kQCap - 32 || !(keep & 2u)) {
+                defer = true;       // larger than the stage, or base codes beyond A/C/G/T possible
+            } else if (pos < 0 || (int64_t)pos + len > tv.G) {
+                atomicAdd(&tv.status[ST_RANGE_ERR], 1u);
+            } else {
+                my_len = len;
+                my_qstart = qstart;
+            }
+        }
+        if (defer) defer_list[atomicAdd(&tv.status[ST_DEFERRED], 1u)] = i;
+    }
+    // coverage difference array: one atomic per distinct start / end among the warp's reads
+    {
+        const int32_t ks = my_len ? pos : (int32_t)(0x80000000u + lane);
+        const uint32_t ms = __match_any_sync(0xFFFFFFFFu, ks);
+        if (my_len && lane == __ffs(ms) - 1) atomicAdd(&tv.covdiff[pos], (int32_t)__popc(ms));
+        const int32_t ke = my_len ? (int32_t)(pos + my_len) : (int32_t)(0x80000000u + lane);
+        const uint32_t me = __match_any_sync(0xFFFFFFFFu, ke);
+        if (my_len && lane == __ffs(me) - 1) atomicAdd(&tv.covdiff[pos + my_len], -(int32_t)__popc(me));
+    }
+    // ---- (3) compact the active reads; chunk column range
+    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, my_len != 0);
+    if (lane == 0) s_misc[8 + warp] = __popc(bal);
+    {
+        int32_t lo = my_len ? pos : 0x7FFFFFFF;
+        int32_t hi = my_len ? (int32_t)(pos + my_len) : 0;
+        uint32_t ml = my_len;
+        lo = __reduce_min_sync(0xFFFFFFFFu, lo);
+        hi = __reduce_max_sync(0xFFFFFFFFu, hi);
+        ml = __reduce_max_sync(0xFFFFFFFFu, ml);
+        if (lane == 0 && ml) {
+            atomicMin(reinterpret_cast<int32_t*>(&s_misc[4]), lo);
+            atomicMax(reinterpret_cast<int32_t*>(&s_misc[5]), hi);
+            atomicMax(&s_misc[6], ml);
+        }
+    }
+    __syncthreads();
+    uint32_t n_act = 0, my_base = 0;
+#pragma unroll
+    for (int w = 0; w < kTileWarps; ++w) {
+        const uint32_t c = s_misc[8 + w];
+        if (w < warp) my_base += c;
+        n_act += c;
+    }
+    if (n_act == 0) return;                     // nothing to deposit from this chunk: no bytes are staged at all
+    if (my_len) {
+        const uint32_t idx = my_base + __popc(bal & ((1u << lane) - 1u));
+        s_pos[idx] = pos; s_len[idx] = my_len;
+        s_beg[idx] = (uint32_t)(so_r - so0);
+        s_end[idx] = (uint32_t)(so_r1 - so0);
+        s_qo[idx] = (uint32_t)(so_r - so0) + my_qstart;
+        s_rix[idx] = (uint16_t)tid;
+    }
+    __syncthreads();
+    const uint32_t maxlen = s_misc[6];
     uint32_t phase = 0;
 
-    // ---- sub-chunks: maximal runs of reads whose staged bytes fit kQCap (one for 150 bp reads) ----
-    uint32_t sub0 = 0;
-    while (sub0 < n_chunk) {
-        // (1) sub-chunk extent (uniform across the CTA: computed from the shared seq_off copy)
-        uint32_t sub1 = sub0;
-        const uint64_t qbeg = s_so[sub0] & ~15ull;           // 16-byte aligned start of the staged range
-        {
-            // largest sub1 with s_so[sub1] - qbeg <= kQCap  (binary search, s_so is monotone)
-            uint32_t lo = sub0, hi = n_chunk;
+    // ---- (4) sub-ranges of active reads whose bytes fit the stage (one for 150 bp reads)
+    uint32_t a0 = 0;
+    while (a0 < n_act) {
+        const uint64_t qbeg = (so0 + s_beg[a0]) & ~15ull;          // 16-byte aligned start of the staged range
+        const uint32_t qbeg_rel = (uint32_t)(qbeg - so0);          // may wrap below zero: only used mod 2^32
+        uint32_t a1 = n_act;
+        if ((so0 + s_end[n_act - 1]) - qbeg > kQCap) {
+            uint32_t lo = a0 + 1, hi = n_act;                       // largest a1 with end[a1-1] - qbeg <= kQCap
             while (lo < hi) {
                 const uint32_t mid = (lo + hi + 1) >> 1;
-                if (s_so[mid] - qbeg <= kQCap) lo = mid; else hi = mid - 1;
+                if ((so0 + s_end[mid - 1]) - qbeg <= kQCap) lo = mid; else hi = mid - 1;
             }
-            sub1 = lo;
+            a1 = lo;
         }
-        const bool oversize = (sub1 == sub0);               // a single read larger than the stage: defer it
-        if (oversize) sub1 = sub0 + 1;
-        const uint32_t n_sub = sub1 - sub0;
-        const uint64_t qend = s_so[sub1];
-        // (2) stage the bytes: two TMA bulk copies issued by one thread
-        if (!oversize && tid == 0) {
+        const uint64_t qend = so0 + s_end[a1 - 1];
+        const uint64_t sbeg16 = (qbeg >> 1) & ~15ull;
+        const int32_t sn_delta = (int32_t)(qbeg - 2 * sbeg16);      // 0 or 16
+        if (tid == 0) {
             const uint32_t qbytes = (uint32_t)(((qend - qbeg) + 15) & ~15ull);
-            const uint64_t sbeg = qbeg >> 1;                 // qbeg is a multiple of 16 -> sbeg multiple of 8
-            const uint64_t sbeg16 = sbeg & ~15ull;
             const uint32_t sbytes = (uint32_t)((((qend + 1) >> 1) - sbeg16 + 15) & ~15ull);
             mbar_expect_tx(bar, qbytes + sbytes);
             if (qbytes) tma_bulk_g2s(q_smem, b.qual + qbeg, qbytes, bar);
             if (sbytes) tma_bulk_g2s(s_smem, b.seq4 + sbeg16, sbytes, bar);
         }
-        const uint64_t sbeg16 = (qbeg >> 1) & ~15ull;
-
-        // (3) per-read headers: filter, classify, coverage, shared header arrays
-        if (tid < 8) s_misc[2 + tid] = (tid == 2) ? 0x7FFFFFFFu : 0u;     // [4]=cmin=INT_MAX, others 0
-        __syncthreads();
-        {
-            int32_t my_pos = 0x7FFFFFFF;
-            uint32_t my_len = 0, my_qo = 0, my_sn = 0;
-            if ((uint32_t)tid < n_sub) {
-                const uint32_t r = sub0 + tid, i = chunk0 + r;
-                const int32_t pos = b.pos[i];
-                my_pos = pos;
-                const uint32_t flag = b.flag[i], keep = b.keep[i];
-                bool defer = false;
-                if (read_passes_filter(flag, b.mapq[i], keep, dp.min_mq)) {
-                    const uint32_t c0 = b.cigar_off[i], c1 = b.cigar_off[i + 1];
-                    uint32_t qstart = 0, len = 0, phase_c = 0;
-                    bool simple = (c1 - c0) <= (uint32_t)kMaxCigarSimple && c1 > c0;
-                    bool has_ref = false;
-                    for (uint32_t k = c0; k < c1 && simple; ++k) {
-                        const uint32_t c = b.cigar[k], op = c & 15u, l = c >> 4;
-                        if (op_is_match(op)) {
-                            if (phase_c == 2) simple = false;
-                            phase_c = 1; len += l; has_ref = true;
-                        } else if (op == 4) {
-                            if (phase_c == 0) qstart += l; else phase_c = 2;
-                        } else if (op == 5) {
-                            if (phase_c == 1) phase_c = 2;
-                        } else simple = false;
-                    }
-                    if (!simple) {
-                        // is it a record with no reference-consuming op at all? (skipped everywhere)
-                        bool any_ref = false;
-                        for (uint32_t k = c0; k < c1; ++k) any_ref |= op_consumes_ref(b.cigar[k] & 15u);
-                        defer = any_ref;
-                    } else if (!has_ref || len == 0) {
-                        // no match op (e.g. only clips): skipped like the general kernel does
-                    } else if (oversize || !(keep & 2u)) {
-                        defer = true;       // larger than the stage, or base codes beyond A/C/G/T possible
-                    } else if (pos < 0 || (int64_t)pos + len > tv.G) {
-                        atomicAdd(&tv.status[ST_RANGE_ERR], 1u);
-                    } else {
-                        my_len = len;
-                        atomicAdd(&tv.covdiff[pos], 1);
-                        atomicAdd(&tv.covdiff[pos + len], -1);
-                        my_qo = (uint32_t)(s_so[r] - qbeg) + qstart;
-                        my_sn = (uint32_t)(((s_so[r] >> 1) - sbeg16) * 2) + qstart;
-                    }
-                }
-                if (defer) defer_list[atomicAdd(&tv.status[ST_DEFERRED], 1u)] = i;
-            }
-            // compact the active (simple, kept) reads: later loops never touch dropped / deferred reads
-            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, my_len != 0);
-            if (lane == 0) s_misc[8 + warp] = __popc(bal);
-            // chunk column range over the simple reads
-            int32_t lo = my_len ? my_pos : 0x7FFFFFFF;
-            int32_t hi = my_len ? (int32_t)(my_pos + my_len) : 0;
-            uint32_t ml = my_len;
-            lo = __reduce_min_sync(0xFFFFFFFFu, lo);
-            hi = __reduce_max_sync(0xFFFFFFFFu, hi);
-            ml = __reduce_max_sync(0xFFFFFFFFu, ml);
-            if (lane == 0) {
-                atomicMin(reinterpret_cast<int32_t*>(&s_misc[4]), lo);
-                atomicMax(reinterpret_cast<int32_t*>(&s_misc[5]), hi);
-                atomicMax(&s_misc[6], ml);
-            }
+        // column range of this sub-range
+        int32_t cmin = s_pos[a0], cmax = (int32_t)s_misc[5];
+        if (!(a0 == 0 && a1 == n_act)) {
             __syncthreads();
-            uint32_t base = 0;
-            for (int w = 0; w < warp; ++w) base += s_misc[8 + w];
-            if (my_len) {
-                const uint32_t idx = base + __popc(bal & ((1u << lane) - 1u));
-                s_pos[idx] = my_pos; s_len[idx] = my_len; s_qo[idx] = my_qo; s_sn[idx] = my_sn;
-                s_rix[idx] = (uint16_t)tid;
-            }
+            if (tid == 0) s_misc[5] = 0;
+            __syncthreads();
+            for (uint32_t r = a0 + tid; r < a1; r += kTileThreads)
+                atomicMax(reinterpret_cast<int32_t*>(&s_misc[5]), (int32_t)(s_pos[r] + s_len[r]));
+            __syncthreads();
+            cmax = (int32_t)s_misc[5];
         }
-        __syncthreads();
-        uint32_t n_act = 0;
-        for (int w = 0; w < kTileWarps; ++w) n_act += s_misc[8 + w];
-        const int32_t cmin = (int32_t)s_misc[4], cmax = (int32_t)s_misc[5];
-        const uint32_t maxlen = s_misc[6];
-        const bool any_simple = cmax > cmin && cmin != 0x7FFFFFFF;
-        if (!oversize) mbar_wait(bar, phase);      // staged bytes have landed (every thread observes it)
-        if (!oversize) phase ^= 1;
+        bool waited = false;
 
-        // ---- column windows of kTabCols (one for amplicon / deep shotgun chunks) ----
-        for (int32_t wc0 = cmin; any_simple && wc0 < cmax; wc0 += kTabCols) {
+        // ---- column windows of kTabCols (one for amplicon / deep shotgun chunks)
+        for (int32_t wc0 = cmin; wc0 < cmax; wc0 += kTabCols) {
             const int nslab = min(kMaxSlabs, (cmax - wc0 + kSlabCols - 1) / kSlabCols);
-            // per-slab candidate read range [a, a+n) by binary search over the sorted positions
+            // per-slab candidate read range [a, a+n) by binary search over the sorted run starts
             if (tid < nslab) {
                 const int32_t s_lo = wc0 + tid * kSlabCols, s_hi = s_lo + kSlabCols;
-                uint32_t lo = 0, hi = n_act;             // first read with pos >= s_hi
+                uint32_t lo = a0, hi = a1;               // first read with pos >= s_hi
                 while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if (s_pos[m] < s_hi) lo = m + 1; else hi = m; }
                 const uint32_t bnd = lo;
                 const int64_t thr = (int64_t)s_lo - (int64_t)maxlen;   // first read with pos > thr
-                lo = 0; hi = bnd;
+                lo = a0; hi = bnd;
                 while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if ((int64_t)s_pos[m] <= thr) lo = m + 1; else hi = m; }
                 s_slab_a[tid] = lo;
                 s_slab_n[tid] = bnd - lo;
@@ -312,8 +354,9 @@ k_deposit_tile(BatchView b, TableView tv, DepositParams dp, TileParams tp, uint3
             }
             __syncthreads();
             const uint32_t n_tasks = s_slab_pre[nslab];
+            if (!waited) { mbar_wait(bar, phase); phase ^= 1; waited = true; }   // staged bytes have landed
 
-            // ---- tasks: (slab, group of 32 reads) ----
+            // ---- tasks: (slab, group of 32 reads); lane = 8 columns of one read per pass
             const int w4 = lane & 3, sread = lane >> 2;
             for (;;) {
                 uint32_t t = 0;
@@ -326,56 +369,43 @@ k_deposit_tile(BatchView b, TableView tv, DepositParams dp, TileParams tp, uint3
                 const uint32_t rb = min(s_slab_a[k] + s_slab_n[k], ra + 32u);
                 const int32_t col_lane = wc0 + k * kSlabCols + 8 * w4;
                 uint32_t acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
-#pragma unroll 1
-                for (uint32_t r = ra + sread; r < rb; r += 8) {
-                    uint32_t other = 0, q0 = 0, q1 = 0, sw0 = 0, sw1 = 0;
-                    int32_t j = 0;
-                    {
-                        const int32_t pos = s_pos[r];
-                        const int32_t len = (int32_t)s_len[r];
-                        j = col_lane - pos;
-                        if (j > -8 && j < len) {
-                            // --- 8 qualities, byte aligned from three aligned shared words
-                            const int32_t qa = (int32_t)s_qo[r] + j;
-                            const uint32_t a = q_smem + (uint32_t)(qa & ~3);
-                            const uint32_t x0 = lds32(a), x1 = lds32(a + 4), x2 = lds32(a + 8);
-                            const uint32_t sh = (uint32_t)(qa & 3) * 8u;
-                            q0 = __funnelshift_r(x0, x1, sh);
-                            q1 = __funnelshift_r(x1, x2, sh);
-                            // --- 8 base nibbles (big-endian within bytes) from two aligned shared words
-                            const int32_t ni = (int32_t)s_sn[r] + j;
-                            const uint32_t sa = s_smem + (uint32_t)((ni >> 1) & ~3);
-                            const uint32_t y0 = __byte_perm(lds32(sa), 0, 0x0123);
-                            const uint32_t y1 = __byte_perm(lds32(sa + 4), 0, 0x0123);
-                            const uint32_t V = __funnelshift_l(y1, y0, (uint32_t)(ni & 7) * 4u);
-                            sw0 = spread_nibbles(V, 0x2233);
-                            sw1 = spread_nibbles(V, 0x0011);
-                            // --- quality masks
-                            uint32_t p0 = bytes_eq80(q0, qprim4), p1 = bytes_eq80(q1, qprim4);
-                            uint32_t g0 = ge_all ? 0x80808080u : bytes_ge80(q0, ge_add4);
-                            uint32_t g1 = ge_all ? 0x80808080u : bytes_ge80(q1, ge_add4);
-                            if (j < 0 || j + 8 > len) {
-                                // partial overlap at a read edge: keep bytes with 0 <= j+b < len
-                                const int lo = j < 0 ? -j : 0, hi = (len - j) < 8 ? (len - j) : 8;
-                                const uint64_t vm = ((hi >= 8 ? ~0ull : ((1ull << (8 * hi)) - 1ull)) &
-                                                     ~((1ull << (8 * lo)) - 1ull));
-                                const uint32_t v0 = (uint32_t)vm, v1 = (uint32_t)(vm >> 32);
-                                p0 &= v0; p1 &= v1; g0 &= v0; g1 &= v1;
-                            }
-                            const uint32_t o0 = g0 & ~p0, o1 = g1 & ~p1;
-                            other = o0 | o1;
-                            const uint32_t m0 = p0 >> 7, m1 = p1 >> 7;
-                            acc[0][0] += sw0 & m0;        acc[1][0] += sw1 & m1;
-                            acc[0][1] += (sw0 >> 1) & m0; acc[1][1] += (sw1 >> 1) & m1;
-                            acc[0][2] += (sw0 >> 2) & m0; acc[1][2] += (sw1 >> 2) & m1;
-                            acc[0][3] += (sw0 >> 3) & m0; acc[1][3] += (sw1 >> 3) & m1;
-                            if (other) {
-                                const uint32_t ord = dp.ord_base + chunk0 + sub0 + s_rix[r];
-                                if (o0) tile_slow_bytes(tv, dp, o0, q0, sw0, (int64_t)col_lane, ord);
-                                if (o1) tile_slow_bytes(tv, dp, o1, q1, sw1, (int64_t)col_lane + 4, ord);
-                            }
-                        }
+                auto consume = [&](const PassUnit& u, uint32_t r) {
+                    uint32_t p0 = bytes_eq80(u.q0, qprim4), p1 = bytes_eq80(u.q1, qprim4);
+                    uint32_t g0 = ge_all ? 0x80808080u : bytes_ge80(u.q0, ge_add4);
+                    uint32_t g1 = ge_all ? 0x80808080u : bytes_ge80(u.q1, ge_add4);
+                    if (u.j < 0 || u.j + 8 > u.len) {
+                        // partial overlap at a read edge: keep bytes with 0 <= j+b < len
+                        const int lo = u.j < 0 ? -u.j : 0, hi = (u.len - u.j) < 8 ? (u.len - u.j) : 8;
+                        const uint64_t vm = ((hi >= 8 ? ~0ull : ((1ull << (8 * hi)) - 1ull)) & ~((1ull << (8 * lo)) - 1ull));
+                        const uint32_t v0 = (uint32_t)vm, v1 = (uint32_t)(vm >> 32);
+                        p0 &= v0; p1 &= v1; g0 &= v0; g1 &= v1;
                     }
+                    const uint32_t o0 = g0 & ~p0, o1 = g1 & ~p1;
+                    const uint32_t m0 = p0 >> 7, m1 = p1 >> 7;
+                    acc[0][0] += u.sw0 & m0;        acc[1][0] += u.sw1 & m1;
+                    acc[0][1] += (u.sw0 >> 1) & m0; acc[1][1] += (u.sw1 >> 1) & m1;
+                    acc[0][2] += (u.sw0 >> 2) & m0; acc[1][2] += (u.sw1 >> 2) & m1;
+                    acc[0][3] += (u.sw0 >> 3) & m0; acc[1][3] += (u.sw1 >> 3) & m1;
+                    if (o0 | o1) {
+                        const uint32_t ord = dp.ord_base + chunk0 + s_rix[r];
+                        if (o0) tile_slow_bytes(tv, dp, o0, u.q0, u.sw0, (int64_t)col_lane, ord);
+                        if (o1) tile_slow_bytes(tv, dp, o1, u.q1, u.sw1, (int64_t)col_lane + 4, ord);
+                    }
+                };
+                // two independent (read, 8 columns) units per iteration: twice the loads in flight
+#pragma unroll 1
+                for (uint32_t r = ra + sread; r < rb; r += 16) {
+                    const uint32_t r2 = r + 8;
+                    const int32_t jA = col_lane - s_pos[r], lenA = (int32_t)s_len[r];
+                    const bool onA = jA > -8 && jA < lenA;
+                    int32_t jB = 0, lenB = 0;
+                    bool onB = false;
+                    if (r2 < rb) { jB = col_lane - s_pos[r2]; lenB = (int32_t)s_len[r2]; onB = jB > -8 && jB < lenB; }
+                    PassUnit uA, uB;
+                    if (onA) uA = pass_load(q_smem, s_smem, (int32_t)(s_qo[r] - qbeg_rel) + jA, sn_delta, jA, lenA);
+                    if (onB) uB = pass_load(q_smem, s_smem, (int32_t)(s_qo[r2] - qbeg_rel) + jB, sn_delta, jB, lenB);
+                    if (onA) consume(uA, r);
+                    if (onB) consume(uB, r2);
                 }
                 // ---- reduce-scatter over the 8 reads of a pass (lane bits 2..4), fields stay <= 32
                 {
@@ -412,62 +442,116 @@ k_deposit_tile(BatchView b, TableView tv, DepositParams dp, TileParams tp, uint3
             __syncthreads();
 
             // ---- flush the window: one global RED per non-zero (column, allele); collect first-seen work
-            const uint32_t chunk_ord0 = dp.ord_base + chunk0 + sub0;
+            const uint32_t chunk_ord0 = dp.ord_base + chunk0;
             uint32_t* plane = tv.planes[tp.prim_plane];
             uint32_t* first0 = tv.first[0];
             const int ncols = min(kTabCols, cmax - wc0);
-            for (int i = tid; i < ncols * 4; i += kTileThreads) {
-                const uint32_t v = s_tab[i];
+            for (int e = tid; e < ncols * 4; e += kTileThreads) {
+                const uint32_t v = s_tab[e];
                 if (v) {
-                    s_tab[i] = 0;
-                    const int64_t cell = (int64_t)wc0 * 4 + i;
+                    s_tab[e] = 0;
+                    const int64_t cell = (int64_t)wc0 * 4 + e;
                     atomicAdd(&plane[cell], v);
-                    if (first0[cell] > chunk_ord0) s_items[atomicAdd(&s_misc[3], 1u)] = (uint16_t)i;
+                    if (first0[cell] > chunk_ord0 + s_rix[a0]) s_items[atomicAdd(&s_misc[3], 1u)] = (uint16_t)e;
                 }
             }
             __syncthreads();
             const uint32_t n_items = s_misc[3];
-            // exact first-seen ordinal for new (column, allele) pairs: scan the chunk's reads in order
-            for (uint32_t it = warp; it < n_items; it += kTileWarps) {
-                const uint32_t e = s_items[it];
-                const int32_t col = wc0 + (int32_t)(e >> 2);
-                const uint32_t want = 1u << (e & 3u);
-                for (uint32_t r0 = 0; r0 < n_act; r0 += 32) {
-                    const uint32_t r = r0 + lane;
-                    bool hit = false;
-                    if (r < n_act) {
-                        const int32_t j = col - s_pos[r];
-                        if (j >= 0 && j < (int32_t)s_len[r]) {
-                            const uint32_t qa = s_qo[r] + (uint32_t)j;
-                            const uint32_t q = (lds32(q_smem + (qa & ~3u)) >> ((qa & 3u) * 8u)) & 255u;
-                            const uint32_t ni = s_sn[r] + (uint32_t)j;
-                            const uint32_t by = (lds32(s_smem + ((ni >> 1) & ~3u)) >> (((ni >> 1) & 3u) * 8u)) & 255u;
-                            const uint32_t nib = (ni & 1u) ? (by & 15u) : (by >> 4);
-                            hit = (q == tp.qprim) && (nib == want);
+            if (n_items) {
+                // exact first-seen ordinal for new (column, allele) pairs: scan the active reads in order
+                for (uint32_t it = warp; it < n_items; it += kTileWarps) {
+                    const uint32_t e = s_items[it];
+                    const int32_t col = wc0 + (int32_t)(e >> 2);
+                    const uint32_t want = 1u << (e & 3u);
+                    for (uint32_t r0 = a0; r0 < a1; r0 += 32) {
+                        const uint32_t r = r0 + lane;
+                        bool hit = false;
+                        if (r < a1) {
+                            const int32_t j = col - s_pos[r];
+                            if (j >= 0 && j < (int32_t)s_len[r]) {
+                                const uint32_t qa = (s_qo[r] - qbeg_rel) + (uint32_t)j;
+                                const uint32_t q = (lds32(q_smem + (qa & ~3u)) >> ((qa & 3u) * 8u)) & 255u;
+                                const uint32_t ni = qa + (uint32_t)sn_delta;
+                                const uint32_t by = (lds32(s_smem + ((ni >> 1) & ~3u)) >> (((ni >> 1) & 3u) * 8u)) & 255u;
+                                const uint32_t nib = (ni & 1u) ? (by & 15u) : (by >> 4);
+                                hit = (q == tp.qprim) && (nib == want);
+                            }
+                        }
+                        const uint32_t hb = __ballot_sync(0xFFFFFFFFu, hit);
+                        if (hb) {
+                            if (lane == 0)
+                                atomicMin(&first0[(int64_t)col * 4 + (e & 3u)], chunk_ord0 + s_rix[r0 + (__ffs(hb) - 1)]);
+                            break;
                         }
                     }
-                    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, hit);
-                    if (bal) {
-                        if (lane == 0) atomicMin(&first0[(int64_t)col * 4 + (e & 3u)], chunk_ord0 + s_rix[r0 + (__ffs(bal) - 1)]);
-                        break;
-                    }
                 }
+                __syncthreads();
+                if (tid == 0) s_misc[3] = 0;
             }
             __syncthreads();
-            if (tid == 0) s_misc[3] = 0;
-            __syncthreads();
         }
+        if (!waited) { mbar_wait(bar, phase); phase ^= 1; }       // never leave a bulk copy in flight
         __syncthreads();
-        sub0 = sub1;
+        a0 = a1;
     }
 }
 
-// general kernel over the deferred list; the count lives on the device (status[ST_DEFERRED])
+// General path over the deferred list, one WARP per read: the lanes stride over the bases of each match
+// op (coalesced loads, 32 reductions in flight) while the CIGAR walk itself is warp-uniform.  The count
+// of deferred reads lives on the device (status[ST_DEFERRED]).
 __global__ void __launch_bounds__(128) k_deposit_general_deferred(BatchView b, TableView tv, DepositParams dp,
                                                                   const uint32_t* __restrict__ list) {
     const uint32_t n = tv.status[ST_DEFERRED];
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x)
-        deposit_read_general(b, tv, dp, list[t]);
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < n; t += warps) {
+        const uint32_t i = list[t];
+        if (!read_passes_filter(b.flag[i], b.mapq[i], b.keep[i], dp.min_mq)) continue;
+        const uint32_t c0 = b.cigar_off[i], c1 = b.cigar_off[i + 1];
+        int64_t rlen = 0;
+        uint32_t lq = 0;
+        for (uint32_t k = c0; k < c1; ++k) {
+            const uint32_t c = b.cigar[k], op = c & 15u, len = c >> 4;
+            if (op_consumes_ref(op)) rlen += len;
+            if (op_consumes_query(op)) lq += len;
+        }
+        if (rlen == 0) continue;
+        const int64_t pos = b.pos[i];
+        if (pos < 0 || pos + rlen > tv.G) {
+            if (lane == 0) atomicAdd(&tv.status[ST_RANGE_ERR], 1u);
+            continue;
+        }
+        if (!dp.replay && lane == 0) {
+            atomicAdd(&tv.covdiff[pos], 1);
+            atomicAdd(&tv.covdiff[pos + rlen], -1);
+        }
+        const uint64_t qb = b.seq_off[i];
+        const uint8_t* qual = b.qual + qb;
+        const uint8_t* seq = b.seq4 + (qb >> 1);
+        const uint32_t ord = dp.ord_base + i;
+        int64_t r = pos;
+        uint32_t qi = 0;
+        for (uint32_t k = c0; k < c1; ++k) {
+            const uint32_t c = b.cigar[k], op = c & 15u, len = c >> 4;
+            if (op_is_match(op)) {
+                for (uint32_t j = lane; j < len; j += 32) {
+                    const uint32_t q = qual[qi + j];
+                    if ((int)q < dp.min_bq) continue;
+                    const uint32_t byte = seq[(qi + j) >> 1];
+                    const uint32_t nib = ((qi + j) & 1u) ? (byte & 15u) : (byte >> 4);
+                    deposit_base(tv, dp, r + j, nib, q, ord);
+                }
+                qi += len; r += len;
+            } else if (op == 2 || op == 3) {
+                const uint32_t q = (qi < lq) ? (uint32_t)qual[qi] : 0u;
+                if (!dp.replay && (int)q >= dp.min_bq)
+                    for (uint32_t j = lane; j < len; j += 32) atomicAdd(&tv.dels[r + j], 1u);
+                r += len;
+            } else if (op == 1 || op == 4) {
+                qi += len;
+            }
+        }
+    }
 }
 
 }  // namespace lvc

@@ -379,7 +379,7 @@ static int launch_deposit(lvc_handle* h, const BatchView& bv, int replay) {
         // reads the tiled kernel could not take (long / irregular) go through the general kernel;
         // the count is on the device, so the launch is sized for the worst case and exits early.
         { KernelTimer t(h, 1);
-          k_deposit_general_deferred<<<std::min<uint32_t>((n + 127) / 128, 4096), 128, 0, h->stream>>>(
+          k_deposit_general_deferred<<<std::min<uint32_t>((n + 3) / 4, (uint32_t)h->sm_count * 16u), 128, 0, h->stream>>>(
               bv, tv, dp, (const uint32_t*)h->b_defer.p); }
         h->launches++;
     }
