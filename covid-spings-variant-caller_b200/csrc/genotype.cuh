@@ -69,10 +69,18 @@ struct GenoParams {
     int64_t min_allele_depth;
     double min_ratio;
     uint32_t flags;
-    int n_planes;            // all planes, ordered so that the n_g0 group-0 planes come first
-    int n_g0;
+    int n_planes;            // all planes, ordered by key (group 0 first)
+    int grp_begin[5];        // planes of group g are [grp_begin[g], grp_begin[g+1])
+    int batch;               // planes resident in shared memory at once (<= kGenoPlaneBatch)
     uint32_t cand_cap;
 };
+
+constexpr int kGenoThreads = 256;            // 64 positions x 4 allele slots
+constexpr int kGenoPlaneBatch = 96;          // planes whose power tables are resident at once
+constexpr int kGenoPowBits = 32;
+// shared: per resident plane 32 powers e^(2^k) and (1-e)^(2^k) in extended range + e as a double
+constexpr size_t kGenoSmemPerPlane = 2 * kGenoPowBits * sizeof(XF) + sizeof(double);
+constexpr size_t kGenoSmemBytes = (size_t)kGenoPlaneBatch * kGenoSmemPerPlane;
 
 struct AlleleStat {
     XF pe;       // prod e
@@ -81,138 +89,145 @@ struct AlleleStat {
     uint32_t ad;
 };
 
-__device__ __forceinline__ void stat_init(AlleleStat& s) {
-    s.pe = xf_one(); s.p1 = xf_one(); s.es = 0.0; s.ad = 0;
-}
-__device__ __forceinline__ void stat_add(AlleleStat& s, uint32_t n, XF e, XF om, double ed) {
-    s.ad += n;
-    s.pe = xf_mul(s.pe, xf_pow(e, n));
-    s.p1 = xf_mul(s.p1, xf_pow(om, n));
-    s.es += (double)n * ed;
+__device__ __forceinline__ XF xf_shfl_xor(XF v, int lanemask) {
+    XF r;
+    r.m = __shfl_xor_sync(0xFFFFFFFFu, v.m, lanemask);
+    r.x = __shfl_xor_sync(0xFFFFFFFFu, v.x, lanemask);
+    return r;
 }
 
-// plane_ptrs[k], plane_keys[k] for k < n_planes (ordered: group 0 first); e_lut / om_lut [256].
-__global__ void __launch_bounds__(128) k_genotype(GenoParams gp, const uint32_t* const* __restrict__ plane_ptrs,
-                                                  const uint16_t* __restrict__ plane_keys,
-                                                  const double* __restrict__ e_lut, const double* __restrict__ om_lut,
-                                                  const uint32_t* __restrict__ dels, const uint8_t* __restrict__ ref,
-                                                  const uint32_t* const* __restrict__ first,   // [4] device array of ptrs
-                                                  uint32_t* __restrict__ out_depth, uint32_t* __restrict__ out_ad,
-                                                  double* __restrict__ out_lik, lvc_candidate* __restrict__ cand,
-                                                  uint32_t* __restrict__ cand_count) {
-    extern __shared__ unsigned char smem_raw[];
-    // per-plane constants staged once per CTA: e, 1-e as XF and e as double
-    XF* s_e = reinterpret_cast<XF*>(smem_raw);
-    XF* s_om = s_e + gp.n_planes;
-    double* s_ed = reinterpret_cast<double*>(s_om + gp.n_planes);
-    for (int k = threadIdx.x; k < gp.n_planes; k += blockDim.x) {
-        const uint32_t q = plane_keys[k] & 255u;
-        s_e[k] = xf_from_double(e_lut[q]);
-        s_om[k] = xf_from_double(om_lut[q]);
-        s_ed[k] = e_lut[q];
+// x^n from the table of x^(2^k): one extended multiply per set bit of n
+__device__ __forceinline__ XF xf_pow_tab(const XF* __restrict__ tab, uint32_t n) {
+    XF r = xf_one();
+    while (n) {
+        const int k = __ffs(n) - 1;
+        n &= n - 1;
+        r = xf_mul(r, tab[k]);
     }
-    __syncthreads();
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= gp.G) return;
+    return r;
+}
+
+// One thread per (position, allele slot); the 4 slots of a position sit in 4 adjacent lanes and are
+// combined with shuffles.  Alleles of the rare groups 1..3 are handled by the same lanes in turn.
+__global__ void __launch_bounds__(kGenoThreads) k_genotype(GenoParams gp, const uint32_t* const* __restrict__ plane_ptrs,
+                                                           const uint16_t* __restrict__ plane_keys,
+                                                           const double* __restrict__ e_lut,
+                                                           const double* __restrict__ om_lut,
+                                                           const uint32_t* __restrict__ dels,
+                                                           const uint8_t* __restrict__ ref,
+                                                           const uint32_t* const* __restrict__ first,
+                                                           uint32_t* __restrict__ out_depth, uint32_t* __restrict__ out_ad,
+                                                           double* __restrict__ out_lik, lvc_candidate* __restrict__ cand,
+                                                           uint32_t* __restrict__ cand_count) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    XF* s_pow_e = reinterpret_cast<XF*>(smem_raw);                                 // [batch][32]
+    XF* s_pow_om = s_pow_e + gp.batch * kGenoPowBits;                               // [batch][32]
+    double* s_ed = reinterpret_cast<double*>(s_pow_om + gp.batch * kGenoPowBits);
+
+    const int tid = threadIdx.x;
+    const int slot = tid & 3;
+    const int64_t p = (int64_t)blockIdx.x * (kGenoThreads / 4) + (tid >> 2);
+    const bool live = p < gp.G;
+    const int64_t pc = live ? p : gp.G - 1;          // clamp: every lane takes part in the shuffles
 
     AlleleStat st[4];
 #pragma unroll
-    for (int s = 0; s < 4; ++s) stat_init(st[s]);
-    uint64_t depth = dels[p];
-    // ---- group 0 (A,C,G,T): register resident
-    for (int k = 0; k < gp.n_g0; ++k) {
-        const uint4 c = *reinterpret_cast<const uint4*>(plane_ptrs[k] + p * 4);
-        if ((c.x | c.y | c.z | c.w) == 0u) continue;
-        const XF e = s_e[k], om = s_om[k];
-        const double ed = s_ed[k];
-        if (c.x) stat_add(st[0], c.x, e, om, ed);
-        if (c.y) stat_add(st[1], c.y, e, om, ed);
-        if (c.z) stat_add(st[2], c.z, e, om, ed);
-        if (c.w) stat_add(st[3], c.w, e, om, ed);
-    }
-    // ---- groups 1..3 (the other 12 nibble codes): rare, local-memory resident
-    AlleleStat ot[12];
-    bool any_other = false;
-    if (gp.n_planes > gp.n_g0) {
-        for (int s = 0; s < 12; ++s) stat_init(ot[s]);
-        for (int k = gp.n_g0; k < gp.n_planes; ++k) {
-            const uint4 c = *reinterpret_cast<const uint4*>(plane_ptrs[k] + p * 4);
-            if ((c.x | c.y | c.z | c.w) == 0u) continue;
-            any_other = true;
-            const int g = (plane_keys[k] >> 8) - 1;
-            const XF e = s_e[k], om = s_om[k];
-            const double ed = s_ed[k];
-            if (c.x) stat_add(ot[g * 4 + 0], c.x, e, om, ed);
-            if (c.y) stat_add(ot[g * 4 + 1], c.y, e, om, ed);
-            if (c.z) stat_add(ot[g * 4 + 2], c.z, e, om, ed);
-            if (c.w) stat_add(ot[g * 4 + 3], c.w, e, om, ed);
+    for (int g = 0; g < 4; ++g) { st[g].pe = xf_one(); st[g].p1 = xf_one(); st[g].es = 0.0; st[g].ad = 0; }
+
+    for (int b0 = 0; b0 < gp.n_planes; b0 += gp.batch) {
+        const int nb = min(gp.batch, gp.n_planes - b0);
+        __syncthreads();
+        // power tables: thread t builds the 32 squarings of one base (e or 1-e of one plane)
+        for (int t = tid; t < 2 * nb; t += kGenoThreads) {
+            const int k = t >> 1;
+            const uint32_t q = plane_keys[b0 + k] & 255u;
+            const bool is_om = t & 1;
+            XF v = xf_from_double(is_om ? om_lut[q] : e_lut[q]);
+            XF* dst = (is_om ? s_pow_om : s_pow_e) + k * kGenoPowBits;
+            for (int i = 0; i < kGenoPowBits; ++i) { dst[i] = v; v = xf_mul(v, v); }
+            if (!is_om) s_ed[k] = e_lut[q];
         }
-    }
-    // total product of e over every allele, total depth
-    XF tot = xf_one();
+        __syncthreads();
 #pragma unroll
-    for (int s = 0; s < 4; ++s) {
-        if (st[s].ad) { tot = xf_mul(tot, st[s].pe); depth += st[s].ad; }
-    }
-    if (any_other) {
-        for (int s = 0; s < 12; ++s)
-            if (ot[s].ad) { tot = xf_mul(tot, ot[s].pe); depth += ot[s].ad; }
-    }
-    // L(a) = prod(1-e | a) * prod over b != a of prod(e | b)      (utils.py:16-24)
-    double L[4];
-    double S = 0.0;
-#pragma unroll
-    for (int s = 0; s < 4; ++s) {
-        L[s] = 0.0;
-        if (st[s].ad) {
-            L[s] = xf_to_double(xf_mul(st[s].p1, xf_div(tot, st[s].pe)));
-            S += L[s];
-        }
-    }
-    double Lo[12];
-    if (any_other) {
-        for (int s = 0; s < 12; ++s) {
-            Lo[s] = 0.0;
-            if (ot[s].ad) {
-                Lo[s] = xf_to_double(xf_mul(ot[s].p1, xf_div(tot, ot[s].pe)));
-                S += Lo[s];
+        for (int g = 0; g < 4; ++g) {
+            const int k0 = max(gp.grp_begin[g], b0), k1 = min(gp.grp_begin[g + 1], b0 + nb);
+            for (int k = k0; k < k1; ++k) {
+                const uint32_t n = plane_ptrs[k][pc * 4 + slot];
+                if (n) {
+                    const int kk = k - b0;
+                    st[g].ad += n;
+                    st[g].es += (double)n * s_ed[kk];
+                    st[g].pe = xf_mul(st[g].pe, xf_pow_tab(s_pow_e + kk * kGenoPowBits, n));
+                    st[g].p1 = xf_mul(st[g].p1, xf_pow_tab(s_pow_om + kk * kGenoPowBits, n));
+                }
             }
         }
     }
-    if (S == 0.0) S = 1.0;                                           // live_variant_caller.py:146
+    // ---- combine the (up to 16) alleles of the position
+    const bool has_other = gp.grp_begin[4] > gp.grp_begin[1];
+    XF own = st[0].ad ? st[0].pe : xf_one();                  // product of e over this lane's alleles
+    uint32_t own_ad = st[0].ad;
+    if (has_other) {
+#pragma unroll
+        for (int g = 1; g < 4; ++g) { if (st[g].ad) own = xf_mul(own, st[g].pe); own_ad += st[g].ad; }
+    }
+    const XF v1 = xf_shfl_xor(own, 1);
+    const XF pair = xf_mul(own, v1);
+    const XF opp = xf_shfl_xor(pair, 2);
+    const XF others_lanes = xf_mul(v1, opp);                  // product over the other three lanes
+    uint32_t dsum = own_ad + __shfl_xor_sync(0xFFFFFFFFu, own_ad, 1);
+    dsum += __shfl_xor_sync(0xFFFFFFFFu, dsum, 2);
+    const uint64_t depth = (uint64_t)dels[pc] + dsum;
+    // L(a) = prod(1-e | a) * prod over b != a of prod(e | b)      (utils.py:16-24)
+    double L[4];
+    double Ssum = 0.0;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        L[g] = 0.0;
+        if ((g == 0 || has_other) && st[g].ad) {
+            XF others = others_lanes;
+            if (has_other) {
+#pragma unroll
+                for (int h = 0; h < 4; ++h)
+                    if (h != g && st[h].ad) others = xf_mul(others, st[h].pe);
+            }
+            L[g] = xf_to_double(xf_mul(st[g].p1, others));
+            Ssum += L[g];
+        }
+    }
+    Ssum += __shfl_xor_sync(0xFFFFFFFFu, Ssum, 1);
+    Ssum += __shfl_xor_sync(0xFFFFFFFFu, Ssum, 2);
+    const double S = Ssum == 0.0 ? 1.0 : Ssum;                                   // live_variant_caller.py:146
+    if (!live) return;
     const uint32_t depth32 = (uint32_t)(depth > 0xFFFFFFFFull ? 0xFFFFFFFFull : depth);
-    out_depth[p] = depth32;
-    *reinterpret_cast<uint4*>(out_ad + p * 4) = make_uint4(st[0].ad, st[1].ad, st[2].ad, st[3].ad);
-    *reinterpret_cast<double2*>(out_lik + p * 4) = make_double2(L[0], L[1]);
-    *reinterpret_cast<double2*>(out_lik + p * 4 + 2) = make_double2(L[2], L[3]);
+    if (slot == 0) out_depth[p] = depth32;
+    out_ad[p * 4 + slot] = st[0].ad;
+    out_lik[p * 4 + slot] = L[0];
 
     if ((int64_t)depth < gp.min_total_depth) return;                 // :131
     if (depth == 0) return;
     const uint8_t rb = ref[p];
     const bool all = gp.flags & 1u;
     const double ddepth = (double)depth;
-    auto emit = [&](uint32_t gs, const AlleleStat& a, double Lval) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        if (!((g == 0 || has_other) && st[g].ad)) continue;
+        const uint32_t gs = (uint32_t)(g * 4 + slot);
         const uint32_t nib = gs_nibble(gs);
         const char letter = "=ACMGRSVTWYHKDBN"[nib];
-        bool ok = all || ((uint8_t)letter != rb && (int64_t)a.ad >= gp.min_allele_depth &&
-                          ((double)a.ad / ddepth) >= gp.min_ratio);              // :151-155
-        if (!ok) return;
-        const uint32_t slot = atomicAdd(cand_count, 1u);
-        if (slot >= gp.cand_cap) return;
+        const bool ok = all || ((uint8_t)letter != rb && (int64_t)st[g].ad >= gp.min_allele_depth &&
+                                ((double)st[g].ad / ddepth) >= gp.min_ratio);     // :151-155
+        if (!ok) continue;
+        const uint32_t idx = atomicAdd(cand_count, 1u);
+        if (idx >= gp.cand_cap) continue;
         lvc_candidate c;
         c.pos = (int32_t)p; c.code = (uint8_t)nib; c.ref = rb; c.pad0 = 0;
-        c.ad = a.ad; c.dp = depth32;
-        const uint32_t* f = first[gs >> 2];
-        c.first = f ? f[p * 4 + (gs & 3u)] : kUnsetOrdinal;
-        c.pad1 = 0; c.L = Lval; c.S = S; c.esum = a.es;
-        cand[slot] = c;
-    };
-#pragma unroll
-    for (int s = 0; s < 4; ++s)
-        if (st[s].ad) emit((uint32_t)s, st[s], L[s]);
-    if (any_other)
-        for (int s = 0; s < 12; ++s)
-            if (ot[s].ad) emit((uint32_t)(4 + s), ot[s], Lo[s]);
+        c.ad = st[g].ad; c.dp = depth32;
+        const uint32_t* f = first[g];
+        c.first = f ? f[p * 4 + slot] : kUnsetOrdinal;
+        c.pad1 = 0; c.L = L[g]; c.S = S; c.esum = st[g].es;
+        cand[idx] = c;
+    }
 }
 
 }  // namespace lvc

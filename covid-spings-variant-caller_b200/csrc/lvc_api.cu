@@ -67,6 +67,9 @@ struct lvc_handle {
     uint32_t cand_cap = 0;
     uint32_t last_cand_count = 0;
     bool geno_pending = false;               // an async genotype launch whose count has not been read yet
+    size_t geno_planes_uploaded = (size_t)-1; // number of planes the device-side ordered plane list reflects
+    double lut_host[512];                    // last uploaded e / 1-e tables
+    bool lut_valid = false;
 
     // optional per-kernel timing (CUDA events on the launching stream)
     bool timing = false;
@@ -208,7 +211,9 @@ int lvc_create(lvc_handle** out, int device, int64_t ref_len, const uint8_t* ref
         CU(cudaMalloc(&h->d_out_lik, G * 4 * sizeof(double)));
         CU(cudaMalloc(&h->d_cand_count, sizeof(uint32_t)));
         CU(cudaMemsetAsync(h->d_cand_count, 0, sizeof(uint32_t), h->stream));
-        CU(cudaFuncSetAttribute(k_deposit_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
+        CU(cudaFuncSetAttribute(k_deposit_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
+        CU(cudaFuncSetAttribute(k_deposit_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
+        CU(cudaFuncSetAttribute(k_genotype, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGenoSmemBytes));
         CU(cudaStreamSynchronize(h->stream));
         return LVC_OK;
     };
@@ -369,12 +374,15 @@ static int launch_deposit(lvc_handle* h, const BatchView& bv, int replay) {
     } else {
         int rc = ensure(h, h->b_defer, (size_t)n * sizeof(uint32_t));
         if (rc) return rc;
-        CU(cudaMemsetAsync(h->d_status + ST_DEFERRED, 0, sizeof(uint32_t), h->stream));
+        CU(cudaMemsetAsync(h->d_status + ST_DEFERRED, 0, 2 * sizeof(uint32_t), h->stream));   // deferred count + chunk counter
         TileParams tp = make_tile_params(n, h->sm_count);
         tp.qprim = (uint32_t)h->qprim;
         tp.prim_plane = h->lut[h->qprim];
         { KernelTimer t(h, 0);
-          k_deposit_tile<<<tp.grid, kTileThreads, kTileSmemBytes, h->stream>>>(bv, tv, dp, tp, (uint32_t*)h->b_defer.p); }
+          if (h->min_bq <= 0)
+              k_deposit_tile<true><<<tp.grid, kTileThreads, kTileSmemBytes, h->stream>>>(bv, tv, dp, tp, (uint32_t*)h->b_defer.p);
+          else
+              k_deposit_tile<false><<<tp.grid, kTileThreads, kTileSmemBytes, h->stream>>>(bv, tv, dp, tp, (uint32_t*)h->b_defer.p); }
         h->launches++;
         // reads the tiled kernel could not take (long / irregular) go through the general kernel;
         // the count is on the device, so the launch is sized for the worst case and exits early.
@@ -578,12 +586,13 @@ static int genotype_enqueue(lvc_handle* h, int64_t min_total_depth, int64_t min_
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return h->plane_key[a] < h->plane_key[b]; });
     std::vector<uint32_t*> ptrs(std::max(np, 1));
     std::vector<uint16_t> keys(std::max(np, 1));
-    int n_g0 = 0;
+    int grp_begin[5] = {0, 0, 0, 0, 0};
     for (int i = 0; i < np; ++i) {
         ptrs[i] = h->planes[order[i]];
         keys[i] = h->plane_key[order[i]];
-        if ((keys[i] >> 8) == 0) n_g0++;
+        grp_begin[(keys[i] >> 8) + 1] = i + 1;
     }
+    for (int g = 1; g <= 4; ++g) grp_begin[g] = std::max(grp_begin[g], grp_begin[g - 1]);
     int rc = ensure(h, h->g_order_ptrs, ptrs.size() * sizeof(uint32_t*));
     if (rc) return rc;
     rc = ensure(h, h->g_order_keys, keys.size() * sizeof(uint16_t));
@@ -593,17 +602,27 @@ static int genotype_enqueue(lvc_handle* h, int64_t min_total_depth, int64_t min_
         rc = ensure(h, h->g_cand, (size_t)h->cand_cap * sizeof(lvc_candidate));
         if (rc) return rc;
     }
-    CU(cudaMemcpyAsync(h->g_order_ptrs.p, ptrs.data(), ptrs.size() * sizeof(uint32_t*), cudaMemcpyHostToDevice, h->stream));
-    CU(cudaMemcpyAsync(h->g_order_keys.p, keys.data(), keys.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, h->stream));
-    CU(cudaMemcpyAsync(h->d_elut, e_lut, 256 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    CU(cudaMemcpyAsync(h->d_elut + 256, om_lut, 256 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (h->geno_planes_uploaded != (size_t)np) {     // planes are only ever appended: the count identifies the set
+        CU(cudaMemcpyAsync(h->g_order_ptrs.p, ptrs.data(), ptrs.size() * sizeof(uint32_t*), cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(h->g_order_keys.p, keys.data(), keys.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, h->stream));
+        h->geno_planes_uploaded = (size_t)np;
+    }
+    if (!h->lut_valid || memcmp(h->lut_host, e_lut, 256 * sizeof(double)) != 0 ||
+        memcmp(h->lut_host + 256, om_lut, 256 * sizeof(double)) != 0) {
+        memcpy(h->lut_host, e_lut, 256 * sizeof(double));
+        memcpy(h->lut_host + 256, om_lut, 256 * sizeof(double));
+        CU(cudaMemcpyAsync(h->d_elut, h->lut_host, 512 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        h->lut_valid = true;
+    }
     CU(cudaMemsetAsync(h->d_cand_count, 0, sizeof(uint32_t), h->stream));
     GenoParams gp;
     gp.G = h->G; gp.min_total_depth = min_total_depth; gp.min_allele_depth = min_allele_depth;
-    gp.min_ratio = min_ratio; gp.flags = flags; gp.n_planes = np; gp.n_g0 = n_g0; gp.cand_cap = h->cand_cap;
-    const size_t smem = (size_t)std::max(np, 1) * (2 * sizeof(XF) + sizeof(double));
-    const int threads = 128;
-    const unsigned blocks = (unsigned)((h->G + threads - 1) / threads);
+    gp.min_ratio = min_ratio; gp.flags = flags; gp.n_planes = np; gp.cand_cap = h->cand_cap;
+    for (int g = 0; g < 5; ++g) gp.grp_begin[g] = grp_begin[g];
+    gp.batch = std::max(1, std::min(np, kGenoPlaneBatch));
+    const size_t smem = (size_t)gp.batch * kGenoSmemPerPlane;
+    const int threads = kGenoThreads;
+    const unsigned blocks = (unsigned)((h->G + (threads / 4) - 1) / (threads / 4));
     {
         KernelTimer t(h, 2);
         k_genotype<<<blocks, threads, smem, h->stream>>>(gp, (const uint32_t* const*)h->g_order_ptrs.p,
