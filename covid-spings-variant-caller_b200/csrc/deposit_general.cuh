@@ -85,6 +85,58 @@ __device__ __forceinline__ void deposit_read_general(const BatchView& b, const T
     }
 }
 
+// The same walk with one WARP per read: the lanes stride over the bases of each match op (coalesced loads,
+// 32 reductions in flight) while the CIGAR walk itself is warp-uniform.  Used by the tiled kernel for the
+// reads it cannot take.
+__device__ __noinline__ void deposit_read_warp(const BatchView& b, const TableView& tv, const DepositParams& dp,
+                                               uint32_t i, uint32_t lane) {
+    if (!read_passes_filter(b.flag[i], b.mapq[i], b.keep[i], dp.min_mq)) return;
+    const uint32_t c0 = b.cigar_off[i], c1 = b.cigar_off[i + 1];
+    int64_t rlen = 0;
+    uint32_t lq = 0;
+    for (uint32_t k = c0; k < c1; ++k) {
+        const uint32_t c = b.cigar[k], op = c & 15u, len = c >> 4;
+        if (op_consumes_ref(op)) rlen += len;
+        if (op_consumes_query(op)) lq += len;
+    }
+    if (rlen == 0) return;
+    const int64_t pos = b.pos[i];
+    if (pos < 0 || pos + rlen > tv.G) {
+        if (lane == 0) atomicAdd(&tv.status[ST_RANGE_ERR], 1u);
+        return;
+    }
+    if (!dp.replay && lane == 0) {
+        atomicAdd(&tv.covdiff[pos], 1);
+        atomicAdd(&tv.covdiff[pos + rlen], -1);
+    }
+    const uint64_t qb = b.seq_off[i];
+    const uint8_t* qual = b.qual + qb;
+    const uint8_t* seq = b.seq4 + (qb >> 1);
+    const uint32_t ord = dp.ord_base + i;
+    int64_t r = pos;
+    uint32_t qi = 0;
+    for (uint32_t k = c0; k < c1; ++k) {
+        const uint32_t c = b.cigar[k], op = c & 15u, len = c >> 4;
+        if (op_is_match(op)) {
+            for (uint32_t j = lane; j < len; j += 32) {
+                const uint32_t q = qual[qi + j];
+                if ((int)q < dp.min_bq) continue;
+                const uint32_t byte = seq[(qi + j) >> 1];
+                const uint32_t nib = ((qi + j) & 1u) ? (byte & 15u) : (byte >> 4);
+                deposit_base(tv, dp, r + j, nib, q, ord);
+            }
+            qi += len; r += len;
+        } else if (op == 2 || op == 3) {
+            const uint32_t q = (qi < lq) ? (uint32_t)qual[qi] : 0u;
+            if (!dp.replay && (int)q >= dp.min_bq)
+                for (uint32_t j = lane; j < len; j += 32) atomicAdd(&tv.dels[r + j], 1u);
+            r += len;
+        } else if (op == 1 || op == 4) {
+            qi += len;
+        }
+    }
+}
+
 // reads [0, n) or, when `list` != nullptr, the reads list[0..n)
 __global__ void __launch_bounds__(128) k_deposit_general(BatchView b, TableView tv, DepositParams dp,
                                                          const uint32_t* __restrict__ list, uint32_t n) {

@@ -3,7 +3,7 @@
 // Replaces the per-(column, read) loop of live_variant_caller.py:69-70,89-103 and the htslib CIGAR walk
 // behind it for every read with at most kMaxRunsPerRead match runs (all Illumina reads, with or
 // without an indel).  Reads with more runs / very long reads / base codes beyond A,C,G,T are
-// appended to a deferred list that the general kernel (one warp per read) processes right after.
+// handled by the same CTA on the general path (one warp per read) once its tiles are flushed.
 //
 // Work decomposition (B200: 148 SMs, 3 persistent CTAs per SM at ~73 KB shared memory each)
 //   CTA    = persistent; pulls chunks of kTileReads consecutive (coordinate-sorted) reads from a global
@@ -61,7 +61,8 @@ struct TileSmem {
     static constexpr uint32_t rd_off = len_off + kMaxRuns * 2;                 // u16 [kMaxRuns] run start - read start
     static constexpr uint32_t rix_off = rd_off + kMaxRuns * 2;                 // u16 [kMaxRuns] window<<8 | read index in chunk
     static constexpr uint32_t items_off = rix_off + kMaxRuns * 2;              // u16 [kTabCols*4]
-    static constexpr uint32_t slab_a_off = items_off + kTabCols * 4 * 2;       // u32 [kMaxSlabs]
+    static constexpr uint32_t dlist_off = items_off + kTabCols * 4 * 2;        // u16 [kTileReads] reads left to the general path
+    static constexpr uint32_t slab_a_off = dlist_off + kTileReads * 2;         // u32 [kMaxSlabs]
     static constexpr uint32_t slab_pre_off = slab_a_off + kMaxSlabs * 4;       // u32 [kMaxSlabs+1]
     static constexpr uint32_t slab_n_off = slab_pre_off + (kMaxSlabs + 1) * 4; // u32 [kMaxSlabs]
     static constexpr uint32_t misc_off = (slab_n_off + kMaxSlabs * 4 + 15) & ~15u;   // mbarrier + scalars
@@ -211,7 +212,7 @@ __device__ __forceinline__ void hdr_load2(const BatchView& b, ReadHdr& h, int mi
 
 template <bool GE_ALL>
 __global__ void __launch_bounds__(kTileThreads, 3)
-k_deposit_tile(BatchView b, TableView tv, DepositParams dp, TileParams tp, uint32_t* __restrict__ defer_list) {
+k_deposit_tile(BatchView b, TableView tv, DepositParams dp, TileParams tp) {
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t sbase = smem_u32(smem);
     uint32_t* s_tab = reinterpret_cast<uint32_t*>(smem + TileSmem::tab_off);
@@ -221,11 +222,12 @@ k_deposit_tile(BatchView b, TableView tv, DepositParams dp, TileParams tp, uint3
     uint16_t* s_rd = reinterpret_cast<uint16_t*>(smem + TileSmem::rd_off);
     uint16_t* s_rix = reinterpret_cast<uint16_t*>(smem + TileSmem::rix_off);
     uint16_t* s_items = reinterpret_cast<uint16_t*>(smem + TileSmem::items_off);
+    uint16_t* s_dlist = reinterpret_cast<uint16_t*>(smem + TileSmem::dlist_off);
     uint32_t* s_slab_a = reinterpret_cast<uint32_t*>(smem + TileSmem::slab_a_off);
     uint32_t* s_slab_pre = reinterpret_cast<uint32_t*>(smem + TileSmem::slab_pre_off);
     uint32_t* s_slab_n = reinterpret_cast<uint32_t*>(smem + TileSmem::slab_n_off);
     uint32_t* s_misc = reinterpret_cast<uint32_t*>(smem + TileSmem::misc_off);
-    // s_misc: [0,1] mbarrier  [2] task counter  [3] n_items  [4] window max end column (long reads only)
+    // s_misc: [0,1] mbarrier  [2] task counter  [3] n_items  [4] window max end column (long reads only)  [6] deferred reads
     //         [5] run table end (overflow only)
     //         [8..11] min read byte, max read end byte, max reference span, max end column   [32..39] runs per warp
     const uint32_t bar = sbase + TileSmem::misc_off;
@@ -246,12 +248,52 @@ k_deposit_tile(BatchView b, TableView tv, DepositParams dp, TileParams tp, uint3
     uint32_t* wc = s_misc + 32;                                      // runs per warp
     if (tid == 0) {
         mbar_init(bar, 1);
-        s_misc[3] = 0;
+        s_misc[3] = 0; s_misc[6] = 0;
         sc[0] = 0xFFFFFFFFu; sc[1] = 0; sc[2] = 0; sc[3] = 0;
     }
     for (int k = tid; k < kTabCols * 4; k += kTileThreads) s_tab[k] = 0;
     hdr_load2(b, hd, dp.min_mq);       // CIGAR ops, only for reads that pass the read-level filter
     __syncthreads();
+    // byte extent of the reads that pass the read-level filter (a superset of what will be deposited):
+    // known before the CIGARs arrive, so the bulk copy overlaps classification
+    const uint32_t so_rel = hd.so - (uint32_t)so0, so1_rel = hd.so1 - (uint32_t)so0;
+    {
+        const bool pass = read_passes_filter(hd.flag, hd.mapq, hd.keep, dp.min_mq) && (hd.keep & 2u) &&
+                          (so1_rel - so_rel) <= kMaxReadBytes && so1_rel > so_rel;
+        uint32_t lo = pass ? so_rel : 0xFFFFFFFFu, hi = pass ? so1_rel : 0u;
+        lo = __reduce_min_sync(0xFFFFFFFFu, lo);
+        hi = __reduce_max_sync(0xFFFFFFFFu, hi);
+        if (lane == 0 && hi) { atomicMin(&sc[0], lo); atomicMax(&sc[1], hi); }
+    }
+    __syncthreads();
+    const uint32_t min_rel = sc[0], max_rel = sc[1];
+    if (max_rel == 0) {
+        // no read of this chunk can take the tiled path: hand over what must be deposited and leave
+        if (read_passes_filter(hd.flag, hd.mapq, hd.keep, dp.min_mq) && hd.nc) {
+            bool any_ref = false;
+            for (uint32_t k = 0; k < hd.nc; ++k) any_ref |= op_consumes_ref(b.cigar[hd.c0 + k] & 15u);
+            if (any_ref) s_dlist[atomicAdd(&s_misc[6], 1u)] = (uint16_t)tid;
+        }
+        __syncthreads();
+        const uint32_t n_def = s_misc[6];
+        for (uint32_t d = warp; d < n_def; d += kTileWarps) deposit_read_warp(b, tv, dp, cur * kTileReads + s_dlist[d], lane);
+        return;
+    }
+    // staging base: 16-byte aligned start of the first such read; window 0 is staged right away
+    const uint64_t base_abs = (so0 + min_rel) & ~15ull;
+    const uint32_t base_rel = (uint32_t)(base_abs - so0);            // may wrap below zero: used mod 2^32
+    auto stage_window = [&](uint32_t win) {
+        const uint64_t qbeg = base_abs + (uint64_t)win * kWinStride;      // 16-byte aligned
+        const uint64_t qend_all = so0 + max_rel;
+        const uint64_t qend = qend_all < qbeg + kQCap ? qend_all : qbeg + kQCap;
+        const uint64_t sbeg16 = (qbeg >> 1) & ~15ull;
+        const uint32_t qbytes = (uint32_t)(((qend - qbeg) + 15) & ~15ull);
+        const uint32_t sbytes = (uint32_t)((((qend + 1) >> 1) - sbeg16 + 15) & ~15ull);
+        mbar_expect_tx(bar, qbytes + sbytes);
+        if (qbytes) tma_bulk_g2s(q_smem, b.qual + qbeg, qbytes, bar);
+        if (sbytes) tma_bulk_g2s(s_smem, b.seq4 + sbeg16, sbytes, bar);
+    };
+    if (tid == 0) stage_window(0);
     uint32_t phase = 0;
     {
         const uint32_t chunk0 = cur * kTileReads;
@@ -330,20 +372,14 @@ k_deposit_tile(BatchView b, TableView tv, DepositParams dp, TileParams tp, uint3
                        b3 = __ballot_sync(0xFFFFFFFFu, nr >= 3);
         const uint32_t lt = (1u << lane) - 1u;
         const uint32_t wprefix = __popc(b1 & lt) + __popc(b2 & lt) + __popc(b3 & lt);
-        const uint32_t so_rel = hd.so - (uint32_t)so0, so1_rel = hd.so1 - (uint32_t)so0;
         {
-            uint32_t lo = nr ? so_rel : 0xFFFFFFFFu, hi = nr ? so1_rel : 0u, sp = nr ? rspan : 0u;
+            uint32_t sp = nr ? rspan : 0u;
             int32_t ce = nr ? (int32_t)(hd.pos + rspan) : 0;
-            lo = __reduce_min_sync(0xFFFFFFFFu, lo);
-            hi = __reduce_max_sync(0xFFFFFFFFu, hi);
             sp = __reduce_max_sync(0xFFFFFFFFu, sp);
             ce = __reduce_max_sync(0xFFFFFFFFu, ce);
             if (lane == 0) {
                 wc[warp] = __popc(b1) + __popc(b2) + __popc(b3);
-                if (hi) {
-                    atomicMin(&sc[0], lo); atomicMax(&sc[1], hi); atomicMax(&sc[2], sp);
-                    atomicMax(reinterpret_cast<int32_t*>(&sc[3]), ce);
-                }
+                if (sp) { atomicMax(&sc[2], sp); atomicMax(reinterpret_cast<int32_t*>(&sc[3]), ce); }
             }
         }
         __syncthreads();                                                   // barrier A
@@ -354,7 +390,7 @@ k_deposit_tile(BatchView b, TableView tv, DepositParams dp, TileParams tp, uint3
             if (w < warp) my_base += c;
             n_runs += c;
         }
-        const uint32_t min_rel = sc[0], max_rel = sc[1], maxspan = sc[2];
+        const uint32_t maxspan = sc[2];
         const int32_t chunk_cmax = (int32_t)sc[3];
         if (n_runs > (uint32_t)kMaxRuns) {                                // run table full (indel-dense chunk): rare
             // reads whose runs do not fit are handed to the general kernel; the table ends where the first
@@ -370,7 +406,7 @@ k_deposit_tile(BatchView b, TableView tv, DepositParams dp, TileParams tp, uint3
             n_runs = s_misc[5];
         }
         const bool active = rspan != 0;                                   // deposited by this kernel
-        if (defer) defer_list[atomicAdd(&tv.status[ST_DEFERRED], 1u)] = i;
+        if (defer) s_dlist[atomicAdd(&s_misc[6], 1u)] = (uint16_t)tid;
         {
             // coverage difference array: one atomic per distinct start / end among the warp's reads
             const int32_t ks = active ? hd.pos : (int32_t)(0x80000000u + lane);
@@ -384,9 +420,6 @@ k_deposit_tile(BatchView b, TableView tv, DepositParams dp, TileParams tp, uint3
                 if ((uint32_t)k < nd)
                     for (uint32_t j = 0; j < del_len[k]; ++j) atomicAdd(&tv.dels[del_pos[k] + j], 1u);
         }
-        // staging base: 16-byte aligned start of the first read that has runs
-        const uint64_t base_abs = (so0 + min_rel) & ~15ull;
-        const uint32_t base_rel = (uint32_t)(base_abs - so0);            // may wrap below zero: used mod 2^32
         if (n_runs) {
             if (nr) {
                 const uint32_t off = so_rel - base_rel;                   // read's first byte relative to the base
@@ -418,20 +451,11 @@ k_deposit_tile(BatchView b, TableView tv, DepositParams dp, TileParams tp, uint3
                     while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if ((uint32_t)(s_rix[m] >> 8) <= win) lo = m + 1; else hi = m; }
                     a1 = lo;
                 }
-                if (a1 == a0) continue;
+                if (a1 == a0 && win > 0) continue;
                 const uint32_t w_rel = win * kWinStride;                   // window start relative to the base
                 const uint64_t qbeg = base_abs + w_rel;                    // 16-byte aligned
-                const uint64_t qend_all = so0 + max_rel;
-                const uint64_t qend = qend_all < qbeg + kQCap ? qend_all : qbeg + kQCap;
-                const uint64_t sbeg16 = (qbeg >> 1) & ~15ull;
-                const int32_t sn_delta = (int32_t)(qbeg - 2 * sbeg16);      // 0 or 16
-                if (tid == 0) {
-                    const uint32_t qbytes = (uint32_t)(((qend - qbeg) + 15) & ~15ull);
-                    const uint32_t sbytes = (uint32_t)((((qend + 1) >> 1) - sbeg16 + 15) & ~15ull);
-                    mbar_expect_tx(bar, qbytes + sbytes);
-                    if (qbytes) tma_bulk_g2s(q_smem, b.qual + qbeg, qbytes, bar);
-                    if (sbytes) tma_bulk_g2s(s_smem, b.seq4 + sbeg16, sbytes, bar);
-                }
+                const int32_t sn_delta = (int32_t)(qbeg - 2 * ((qbeg >> 1) & ~15ull));      // 0 or 16
+                if (win > 0 && tid == 0) stage_window(win);
                 // column range of these runs
                 const int32_t cmin = s_pos[a0] - (int32_t)s_rd[a0];
                 int32_t cmax = chunk_cmax;                                 // chunk-wide (an upper bound for any window)
@@ -627,65 +651,13 @@ k_deposit_tile(BatchView b, TableView tv, DepositParams dp, TileParams tp, uint3
                 if (win + 1 < n_win) __syncthreads();                      // staging buffer is reused by the next window
                 a0 = a1;
             }
+        } else {
+            mbar_wait(bar, phase);                                         // window 0 was staged speculatively
         }
-    }
-}
-
-// General path over the deferred list, one WARP per read: the lanes stride over the bases of each match
-// op (coalesced loads, 32 reductions in flight) while the CIGAR walk itself is warp-uniform.  The count
-// of deferred reads lives on the device (status[ST_DEFERRED]).
-__global__ void __launch_bounds__(128) k_deposit_general_deferred(BatchView b, TableView tv, DepositParams dp,
-                                                                  const uint32_t* __restrict__ list) {
-    const uint32_t n = tv.status[ST_DEFERRED];
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < n; t += warps) {
-        const uint32_t i = list[t];
-        if (!read_passes_filter(b.flag[i], b.mapq[i], b.keep[i], dp.min_mq)) continue;
-        const uint32_t c0 = b.cigar_off[i], c1 = b.cigar_off[i + 1];
-        int64_t rlen = 0;
-        uint32_t lq = 0;
-        for (uint32_t k = c0; k < c1; ++k) {
-            const uint32_t c = b.cigar[k], op = c & 15u, len = c >> 4;
-            if (op_consumes_ref(op)) rlen += len;
-            if (op_consumes_query(op)) lq += len;
-        }
-        if (rlen == 0) continue;
-        const int64_t pos = b.pos[i];
-        if (pos < 0 || pos + rlen > tv.G) {
-            if (lane == 0) atomicAdd(&tv.status[ST_RANGE_ERR], 1u);
-            continue;
-        }
-        if (!dp.replay && lane == 0) {
-            atomicAdd(&tv.covdiff[pos], 1);
-            atomicAdd(&tv.covdiff[pos + rlen], -1);
-        }
-        const uint64_t qb = b.seq_off[i];
-        const uint8_t* qual = b.qual + qb;
-        const uint8_t* seq = b.seq4 + (qb >> 1);
-        const uint32_t ord = dp.ord_base + i;
-        int64_t r = pos;
-        uint32_t qi = 0;
-        for (uint32_t k = c0; k < c1; ++k) {
-            const uint32_t c = b.cigar[k], op = c & 15u, len = c >> 4;
-            if (op_is_match(op)) {
-                for (uint32_t j = lane; j < len; j += 32) {
-                    const uint32_t q = qual[qi + j];
-                    if ((int)q < dp.min_bq) continue;
-                    const uint32_t byte = seq[(qi + j) >> 1];
-                    const uint32_t nib = ((qi + j) & 1u) ? (byte & 15u) : (byte >> 4);
-                    deposit_base(tv, dp, r + j, nib, q, ord);
-                }
-                qi += len; r += len;
-            } else if (op == 2 || op == 3) {
-                const uint32_t q = (qi < lq) ? (uint32_t)qual[qi] : 0u;
-                if (!dp.replay && (int)q >= dp.min_bq)
-                    for (uint32_t j = lane; j < len; j += 32) atomicAdd(&tv.dels[r + j], 1u);
-                r += len;
-            } else if (op == 1 || op == 4) {
-                qi += len;
-            }
-        }
+        // ---- reads the tiled path could not take (many runs, long, exotic base codes): general path, one warp each
+        __syncthreads();
+        const uint32_t n_def = s_misc[6];
+        for (uint32_t d = warp; d < n_def; d += kTileWarps) deposit_read_warp(b, tv, dp, chunk0 + s_dlist[d], lane);
     }
 }
 

@@ -372,23 +372,14 @@ static int launch_deposit(lvc_handle* h, const BatchView& bv, int replay) {
           k_deposit_general<<<(n + 127) / 128, 128, 0, h->stream>>>(bv, tv, dp, nullptr, n); }
         h->launches++;
     } else {
-        int rc = ensure(h, h->b_defer, (size_t)n * sizeof(uint32_t));
-        if (rc) return rc;
-        CU(cudaMemsetAsync(h->d_status + ST_DEFERRED, 0, 2 * sizeof(uint32_t), h->stream));   // deferred count + chunk counter
         TileParams tp = make_tile_params(n, h->sm_count);
         tp.qprim = (uint32_t)h->qprim;
         tp.prim_plane = h->lut[h->qprim];
         { KernelTimer t(h, 0);
           if (h->min_bq <= 0)
-              k_deposit_tile<true><<<tp.grid, kTileThreads, kTileSmemBytes, h->stream>>>(bv, tv, dp, tp, (uint32_t*)h->b_defer.p);
+              k_deposit_tile<true><<<tp.grid, kTileThreads, kTileSmemBytes, h->stream>>>(bv, tv, dp, tp);
           else
-              k_deposit_tile<false><<<tp.grid, kTileThreads, kTileSmemBytes, h->stream>>>(bv, tv, dp, tp, (uint32_t*)h->b_defer.p); }
-        h->launches++;
-        // reads the tiled kernel could not take (long / irregular) go through the general kernel;
-        // the count is on the device, so the launch is sized for the worst case and exits early.
-        { KernelTimer t(h, 1);
-          k_deposit_general_deferred<<<std::min<uint32_t>((n + 3) / 4, (uint32_t)h->sm_count * 16u), 128, 0, h->stream>>>(
-              bv, tv, dp, (const uint32_t*)h->b_defer.p); }
+              k_deposit_tile<false><<<tp.grid, kTileThreads, kTileSmemBytes, h->stream>>>(bv, tv, dp, tp); }
         h->launches++;
     }
     CU(cudaGetLastError());
