@@ -12,7 +12,7 @@ from typing import Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblvc_b200.so")
+LIB_PATH = os.environ.get("LVC_LIB_PATH") or os.path.join(_HERE, "liblvc_b200.so")   # override: kernel experiments
 
 LVC_OK = 0
 ERRORS = {-1: "LVC_EINVAL", -2: "LVC_ECUDA", -3: "LVC_ENOMEM", -4: "LVC_EUNSORTED", -5: "LVC_ERANGE",
