@@ -65,6 +65,7 @@ __device__ __forceinline__ double xf_to_double(XF a) {
 
 struct GenoParams {
     int64_t G;
+    int64_t p0, p1;          // positions [p0, p1) are genotyped (the whole contig by default)
     int64_t min_total_depth;
     int64_t min_allele_depth;
     double min_ratio;
@@ -126,9 +127,9 @@ __global__ void __launch_bounds__(kGenoThreads) k_genotype(GenoParams gp, const 
 
     const int tid = threadIdx.x;
     const int slot = tid & 3;
-    const int64_t p = (int64_t)blockIdx.x * (kGenoThreads / 4) + (tid >> 2);
-    const bool live = p < gp.G;
-    const int64_t pc = live ? p : gp.G - 1;          // clamp: every lane takes part in the shuffles
+    const int64_t p = gp.p0 + (int64_t)blockIdx.x * (kGenoThreads / 4) + (tid >> 2);
+    const bool live = p < gp.p1;
+    const int64_t pc = live ? p : gp.p1 - 1;         // clamp: every lane takes part in the shuffles
 
     AlleleStat st[4];
 #pragma unroll

@@ -66,6 +66,7 @@ struct lvc_handle {
     uint32_t* d_cand_count = nullptr;
     uint32_t cand_cap = 0;
     uint32_t last_cand_count = 0;
+    int64_t geno_p0 = 0, geno_p1 = -1;       // genotype position range (p1 < 0: whole contig)
     bool geno_pending = false;               // an async genotype launch whose count has not been read yet
     size_t geno_planes_uploaded = (size_t)-1; // number of planes the device-side ordered plane list reflects
     double lut_host[512];                    // last uploaded e / 1-e tables
@@ -607,13 +608,14 @@ static int genotype_enqueue(lvc_handle* h, int64_t min_total_depth, int64_t min_
     }
     CU(cudaMemsetAsync(h->d_cand_count, 0, sizeof(uint32_t), h->stream));
     GenoParams gp;
-    gp.G = h->G; gp.min_total_depth = min_total_depth; gp.min_allele_depth = min_allele_depth;
+    gp.G = h->G; gp.p0 = h->geno_p0; gp.p1 = h->geno_p1 < 0 ? h->G : h->geno_p1; gp.min_total_depth = min_total_depth; gp.min_allele_depth = min_allele_depth;
     gp.min_ratio = min_ratio; gp.flags = flags; gp.n_planes = np; gp.cand_cap = h->cand_cap;
     for (int g = 0; g < 5; ++g) gp.grp_begin[g] = grp_begin[g];
     gp.batch = std::max(1, std::min(np, kGenoPlaneBatch));
     const size_t smem = (size_t)gp.batch * kGenoSmemPerPlane;
     const int threads = kGenoThreads;
-    const unsigned blocks = (unsigned)((h->G + (threads / 4) - 1) / (threads / 4));
+    const unsigned blocks = (unsigned)((gp.p1 - gp.p0 + (threads / 4) - 1) / (threads / 4));
+    if (gp.p1 <= gp.p0) { h->last_cand_count = 0; h->geno_pending = false; return LVC_OK; }
     {
         KernelTimer t(h, 2);
         k_genotype<<<blocks, threads, smem, h->stream>>>(gp, (const uint32_t* const*)h->g_order_ptrs.p,
@@ -659,6 +661,15 @@ int lvc_genotype_device_async(lvc_handle* h, int64_t min_total_depth, int64_t mi
     if (!h || !e_lut || !om_lut) return LVC_EINVAL;
     CU(cudaSetDevice(h->device));
     return genotype_enqueue(h, min_total_depth, min_allele_depth, min_ratio, e_lut, om_lut, flags);
+}
+
+int lvc_set_genotype_range(lvc_handle* h, int64_t p0, int64_t p1) {
+    if (!h) return LVC_EINVAL;
+    if (p1 < 0) { h->geno_p0 = 0; h->geno_p1 = -1; return LVC_OK; }
+    if (p0 < 0 || p1 > h->G || p0 > p1) return fail(h, LVC_EINVAL, "genotype range [%lld, %lld) outside [0, %lld)",
+                                                    (long long)p0, (long long)p1, (long long)h->G);
+    h->geno_p0 = p0; h->geno_p1 = p1;
+    return LVC_OK;
 }
 
 int lvc_fetch_candidates(lvc_handle* h, lvc_candidate* out, uint32_t cap, uint32_t* n_out) {

@@ -73,6 +73,7 @@ SIGNATURES = [
                                C.c_uint32, C.POINTER(C.c_uint32)]),
     ("lvc_genotype_device", C.c_int, [_H, C.c_int64, C.c_int64, C.c_double, C.c_void_p, C.c_void_p, C.c_uint32]),
     ("lvc_fetch_candidates", C.c_int, [_H, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]),
+    ("lvc_set_genotype_range", C.c_int, [_H, C.c_int64, C.c_int64]),
     ("lvc_copy_dense", C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("lvc_num_planes", C.c_int, [_H]),
     ("lvc_plane_keys", C.c_int, [_H, C.c_void_p]),
@@ -236,6 +237,9 @@ class Handle:
         out = np.zeros(max(n.value, 1), dtype=CANDIDATE_DTYPE)
         self._check(self.lib.lvc_fetch_candidates(self.h, out.ctypes.data, len(out), C.byref(n)))
         return out[:n.value]
+
+    def set_genotype_range(self, p0: int, p1: int):
+        self._check(self.lib.lvc_set_genotype_range(self.h, int(p0), int(p1)))
 
     def copy_dense(self):
         depth = np.zeros(self.G, dtype=np.uint32)

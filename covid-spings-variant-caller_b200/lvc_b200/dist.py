@@ -1,0 +1,167 @@
+"""Multi-GPU sharding of the hot path (one process per GPU, torch.distributed for the plumbing).
+
+The path shards in exactly two ways:
+
+* independent samples -> GPUs (:func:`assign_samples`): state is per caller instance
+  (live_variant_caller.py:31-32), so there is NO communication; records are gathered on the host.
+* one sample, contiguous chunks of the coordinate-sorted reads -> GPUs (:func:`shard_reads`): deposits
+  are commutative integer adds, so the per-rank tables combine with ONE exchange step,
+  an integer sum (counts, deletion counts, coverage) and a min (first-seen ordinals), done here
+  with NCCL all-reduce over NVLink directly on the library's device tables (zero copy).
+  The order-dependent admission (max_depth keep mask) is computed BEFORE sharding, and each rank's
+  first-seen ordinals start at its chunk's global read index, so the result is bit-identical to a
+  single-GPU run.
+
+Nothing here is a data-path collective for the multi-sample workload; do not add one.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Sequence, Tuple
+
+import numpy as np
+
+from .packing import ReadBatch, query_lengths
+
+_BIAS = -2 ** 31      # int32 view of 0x80000000: makes unsigned order == signed order for the MIN reduce
+
+
+def assign_samples(n_samples: int, world_size: int, rank: int) -> List[int]:
+    """samples of a plate -> ranks, static round robin."""
+    return list(range(rank, n_samples, world_size))
+
+
+def shard_reads(batch: ReadBatch, world_size: int) -> List[Tuple[int, int]]:
+    """[a, b) read ranges, contiguous in coordinate order and balanced by query bases."""
+    n = batch.n_reads
+    if n == 0:
+        return [(0, 0)] * world_size
+    lq = query_lengths(batch.cigar_off, batch.cigar).astype(np.int64)
+    csum = np.cumsum(lq)
+    total = int(csum[-1])
+    cuts = [0]
+    for r in range(1, world_size):
+        cuts.append(int(np.searchsorted(csum, total * r / world_size, side="left")))
+    cuts.append(n)
+    cuts = [min(max(c, 0), n) for c in cuts]
+    for i in range(1, len(cuts)):
+        cuts[i] = max(cuts[i], cuts[i - 1])
+    return [(cuts[i], cuts[i + 1]) for i in range(world_size)]
+
+
+def key_union(local_keys: Sequence[int], group=None) -> List[int]:
+    """union over ranks of the (allele group, quality) plane keys (1024-bit bitmap all-reduce)."""
+    import torch
+    import torch.distributed as dist
+    bm = torch.zeros(1024, dtype=torch.int32)
+    for k in local_keys:
+        bm[int(k)] = 1
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else bm.device
+        bm = bm.to(dev)
+        dist.all_reduce(bm, op=dist.ReduceOp.MAX, group=group)
+        bm = bm.cpu()
+    return [int(k) for k in torch.nonzero(bm).flatten().tolist()]
+
+
+def reduce_tables(tables: Dict[str, "object"], group=None) -> None:
+    """In-place all-reduce of a dict of int32 tensors: names starting with 'first' take the unsigned
+    MIN (through an order-preserving bias), everything else the integer SUM.  Works on CPU tensors with
+    gloo (tests) and on CUDA tensors with NCCL (production)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return
+    for name in sorted(tables):
+        t = tables[name]
+        assert t.dtype == torch.int32, name
+        if name.startswith("first"):
+            t.bitwise_xor_(torch.tensor(_BIAS, dtype=torch.int32, device=t.device))
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+            t.bitwise_xor_(torch.tensor(_BIAS, dtype=torch.int32, device=t.device))
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+
+
+class _DevArray:
+    """exposes a raw device pointer of the library as a __cuda_array_interface__ object"""
+
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (int(ptr), False), "version": 2}
+
+
+def device_tables(handle) -> Dict[str, "object"]:
+    """zero-copy int32 torch views of a handle's persistent device tables (after key agreement)."""
+    import torch
+    dev = torch.device("cuda", torch.cuda.current_device())
+    G = handle.G
+    out = {}
+    for k in handle.plane_keys():
+        out[f"plane{int(k):04d}"] = torch.as_tensor(_DevArray(handle.plane_devptr(int(k)), G * 4), device=dev)
+    out["dels"] = torch.as_tensor(_DevArray(handle.dels_devptr(), G), device=dev)
+    out["covdiff"] = torch.as_tensor(_DevArray(handle.covdiff_devptr(), G + 1), device=dev)
+    for g in range(4):
+        p = handle.first_devptr(g)
+        if p:
+            out[f"first{g}"] = torch.as_tensor(_DevArray(p, G * 4), device=dev)
+    return out
+
+
+def allreduce_handle(handle, group=None) -> int:
+    """Make every rank's handle hold the tables of ALL ranks' reads (NCCL all-reduce over NVLink).
+    Returns the number of bytes this rank contributed to the collective."""
+    import torch
+    import torch.distributed as dist
+    handle.sync()
+    for k in key_union([int(k) for k in handle.plane_keys()], group):
+        handle.ensure_plane(k)               # a plane also brings its group's first-seen table
+    tabs = device_tables(handle)
+    torch.cuda.synchronize()
+    reduce_tables(tabs, group)
+    torch.cuda.synchronize()
+    if dist.is_initialized():
+        o = torch.tensor([handle.ordinal], dtype=torch.int64, device=next(iter(tabs.values())).device)
+        dist.all_reduce(o, op=dist.ReduceOp.MAX, group=group)
+        handle.ordinal = int(o.item())
+    return sum(t.numel() * 4 for t in tabs.values())
+
+
+def position_slice(G: int, world_size: int, rank: int) -> Tuple[int, int]:
+    """contiguous slice of positions a rank genotypes after the table reduce"""
+    per = (G + world_size - 1) // world_size
+    return min(rank * per, G), min((rank + 1) * per, G)
+
+
+def process_batch_sharded(caller, batch: ReadBatch, group=None) -> int:
+    """One sample, read-chunk sharding: `batch` is the WHOLE coordinate-sorted batch with
+    its keep mask (identical on every rank); every rank deposits its contiguous chunk, the tables are
+    all-reduced over NCCL, and each rank is left genotyping its own slice of positions.
+    `caller` is a variant_caller.live_variant_caller.LiveVariantCaller.  Returns the bytes reduced."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    h = caller._handle
+    base = h.ordinal
+    if rank != 0:
+        # after the previous all-reduce every rank holds the FULL tables; only rank 0 keeps that history,
+        # the others contribute just this batch's delta (sum over ranks == history + all deltas)
+        h.reset()
+    a, b = shard_reads(batch, world)[rank]
+    h.ordinal = base + a                      # first-seen ordinals are global read indices
+    if b > a:
+        h.push_batch(batch.slice(a, b).as_capi())
+    h.ordinal = base + batch.n_reads
+    n = allreduce_handle(h, group)
+    p0, p1 = position_slice(h.G, world, rank)
+    h.set_genotype_range(p0, p1)
+    return n
+
+
+def gather_variants(caller, group=None) -> List[dict]:
+    """records of every rank's position slice, merged in position order on every rank"""
+    import torch.distributed as dist
+    mine = caller.prepare_variants()
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return mine
+    parts = [None] * dist.get_world_size(group)
+    dist.all_gather_object(parts, mine, group=group)
+    return [v for part in parts for v in part]

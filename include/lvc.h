@@ -138,6 +138,9 @@ int lvc_genotype_device(lvc_handle* h, int64_t min_total_depth, int64_t min_alle
 int lvc_genotype_device_async(lvc_handle* h, int64_t min_total_depth, int64_t min_allele_depth,
                               double min_evidence_ratio, const double* e_lut, const double* om_lut, uint32_t flags);
 int lvc_fetch_candidates(lvc_handle* h, lvc_candidate* out, uint32_t cap, uint32_t* n_out);
+/* restrict the genotype pass to positions [p0, p1) (multi-GPU: each rank genotypes its slice of the reduced
+ * tables); p1 < 0 restores the whole contig.  Dense outputs outside the range keep their previous values. */
+int lvc_set_genotype_range(lvc_handle* h, int64_t p0, int64_t p1);
 int lvc_copy_dense(lvc_handle* h, uint32_t* depth /*[G]*/, uint32_t* ad /*[G*4] A,C,G,T*/,
                    double* lik /*[G*4]*/);
 

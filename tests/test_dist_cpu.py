@@ -1,0 +1,101 @@
+"""CPU, world_size 2 over gloo: the host-side logic of the multi-GPU paths (sharding plans and the
+table reduction), checked against the oracle.  The CUDA path itself is covered by tests/test_gpu_*."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from helpers import po, synth_small, rows_to_tuples
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, rows, ref, q):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (root, os.path.join(root, "covid-spings-variant-caller_b200"), os.path.join(root, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch
+    import torch.distributed as dist
+    from lvc_b200 import packing, dist as ldist
+    from oracle.c_oracle import COracle
+    from helpers import rows_to_tuples as r2t
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    batch = packing.pack_reads(r2t(rows), 0)                 # keep mask computed on the WHOLE batch
+    a, b = ldist.shard_reads(batch, world)[rank]
+    mine = batch.slice(a, b)
+    co = COracle(ref, 13, 0, max_depth=10 ** 9)              # admission already applied: replay the keep mask
+    mine_kept = _apply_keep(mine)
+    co.st.ordinal = a                                        # global read index of the chunk's first read
+    co.process(mine_kept)
+    first = co.first.astype(np.uint32).view(np.int32).reshape(-1).copy()
+    tabs = {"plane_ad": torch.from_numpy(co.ad.astype(np.int32).reshape(-1).copy()),
+            "dels": torch.from_numpy((co.depth.astype(np.int64) - co.ad.sum(axis=1)).astype(np.int32)),
+            "covdiff": torch.from_numpy(np.diff(np.concatenate([[0], co.cov.astype(np.int64), [0]])).astype(np.int32)),
+            "first0": torch.from_numpy(first)}
+    keys = ldist.key_union([rank + 1, 7])
+    ldist.reduce_tables(tabs)
+    if rank == 0:
+        q.put((keys, {k: v.numpy().copy() for k, v in tabs.items()}, ldist.assign_samples(7, world, 0),
+               ldist.assign_samples(7, world, 1)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _apply_keep(b):
+    """emulate 'admission happened before sharding': drop the reads whose keep bit is 0 by failing their mapq"""
+    from lvc_b200 import packing
+    mq = b.mapq.copy()
+    fl = b.flag.copy()
+    fl[(b.keep & 1) == 0] |= 0x400
+    return packing.ReadBatch(b.pos, fl, mq, b.keep, b.cigar_off, b.cigar, b.seq_off, b.seq4, b.qual)
+
+
+def test_read_chunk_sharding_reduces_to_the_single_process_tables(lib, golden_synth):
+    import torch.multiprocessing as mp
+    from lvc_b200 import packing
+    from oracle.c_oracle import COracle
+    g = golden_synth["amplicon_like"]
+    rows, ref = g["reads"], g["ref"]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, rows, ref, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    keys, tabs, s0, s1 = q.get(timeout=120)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert keys == [1, 2, 7]
+    assert s0 == [0, 2, 4, 6] and s1 == [1, 3, 5]
+    whole = packing.pack_reads(rows_to_tuples(rows), 0)
+    co = COracle(ref, 13, 0)
+    co.process(whole)
+    assert np.array_equal(tabs["plane_ad"].reshape(-1, 16), co.ad.astype(np.int32))
+    assert np.array_equal(tabs["dels"], (co.depth.astype(np.int64) - co.ad.sum(axis=1)).astype(np.int32))
+    assert np.array_equal(np.cumsum(tabs["covdiff"])[:-1], co.cov.astype(np.int64))
+    assert np.array_equal(tabs["first0"].view(np.uint32).reshape(-1, 16), co.first)
+
+
+def test_shard_reads_balanced_and_contiguous(lib, golden_synth):
+    from lvc_b200 import packing, dist as ldist
+    b = packing.pack_reads(rows_to_tuples(golden_synth["mixed_small"]["reads"]), 0)
+    for world in (1, 2, 3, 8):
+        parts = ldist.shard_reads(b, world)
+        assert parts[0][0] == 0 and parts[-1][1] == b.n_reads
+        assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
+        lq = packing.query_lengths(b.cigar_off, b.cigar)
+        loads = [int(lq[a:c].sum()) for a, c in parts]
+        assert max(loads) - min(loads) <= 2 * int(lq.max()) + 1
+    sl = b.slice(5, 40)
+    assert sl.n_reads == 35 and sl.pos.tolist() == b.pos[5:40].tolist()
+    assert sl.qual[:sl.n_qual].tolist() == b.qual[int(b.seq_off[5]):int(b.seq_off[40])].tolist()

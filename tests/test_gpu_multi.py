@@ -1,0 +1,86 @@
+"""GPU, 2 ranks over NCCL (skipped on a single-GPU box): read-chunk sharding with the all-reduce of the
+integer tables must reproduce the single-GPU tables and records bit for bit, across live batches."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from helpers import rows_to_tuples, assert_variants_equal
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, rows, ref, q):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (root, os.path.join(root, "covid-spings-variant-caller_b200"), os.path.join(root, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch
+    import torch.distributed as dist
+    from lvc_b200 import packing, dist as ldist
+    from variant_caller.live_variant_caller import LiveVariantCaller
+    from helpers import rows_to_tuples as r2t, memory_tables
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    fa = f"/tmp/lvc_multi_{rank}.fasta"
+    with open(fa, "w") as fh:
+        fh.write(">c\n" + ref + "\n")
+    th = dict(minBQ=13, minMQ=0, minDP=3, minAD=2, ratio=0.05)
+    lvc = LiveVariantCaller(fa, th["minBQ"], th["minMQ"], th["minDP"], th["minAD"], th["ratio"], 1, device=rank)
+    out = []
+    for k in range(3):                                   # three live batches
+        sel = list(range(k, len(rows), 3))
+        batch = packing.pack_reads(r2t([rows[i] for i in sel]), th["minMQ"])
+        ldist.process_batch_sharded(lvc, batch)
+        out.append(ldist.gather_variants(lvc))
+    lvc._handle.set_genotype_range(0, -1)
+    mem = memory_tables(lvc.memory)
+    if rank == 0:
+        q.put((out, mem))
+    dist.barrier()
+    lvc.close()
+    dist.destroy_process_group()
+
+
+def test_two_ranks_equal_one(lib, golden_synth, tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from lvc_b200 import packing
+    from variant_caller.live_variant_caller import LiveVariantCaller
+    from helpers import memory_tables
+    g = golden_synth["amplicon_like"]
+    rows, ref = g["reads"], g["ref"]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, rows, ref, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out, mem = q.get(timeout=300)
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    fa = str(tmp_path / "c.fasta")
+    with open(fa, "w") as fh:
+        fh.write(">c\n" + ref + "\n")
+    th = dict(minBQ=13, minMQ=0, minDP=3, minAD=2, ratio=0.05)
+    one = LiveVariantCaller(fa, th["minBQ"], th["minMQ"], th["minDP"], th["minAD"], th["ratio"], 1, device=0)
+    for k in range(3):
+        sel = list(range(k, len(rows), 3))
+        one.process_batch(packing.pack_reads(rows_to_tuples([rows[i] for i in sel]), th["minMQ"]))
+        assert_variants_equal(out[k], one.prepare_variants(), f"batch {k}")
+    assert mem == memory_tables(one.memory)
+    one.close()
