@@ -68,8 +68,10 @@ class ReadBatch:
         return int(20 * self.n_reads + 4 * self.n_cigar + ((lq + 1) // 2).sum() + lq.sum() + 52 * ref_len)
 
     def as_capi(self) -> capi.Batch:
-        return capi.Handle.make_batch(self.n_reads, self.n_cigar, self.n_qual, self.pos, self.flag, self.mapq,
-                                      self.keep, self.cigar_off, self.cigar, self.seq_off, self.seq4, self.qual)
+        b = capi.Handle.make_batch(self.n_reads, self.n_cigar, self.n_qual, self.pos, self.flag, self.mapq,
+                                   self.keep, self.cigar_off, self.cigar, self.seq_off, self.seq4, self.qual)
+        b._keepalive = self         # the struct only carries raw pointers: keep the arrays alive with it
+        return b
 
     def slice(self, a: int, b: int) -> "ReadBatch":
         """reads [a, b) as a new batch sharing the payload arrays (offsets rebased)."""
