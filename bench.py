@@ -278,6 +278,7 @@ def main():
     for _ in range(2):
         lvc.process_batch(pinned)
         variants = lvc.prepare_variants()
+    payload0 = lvc._handle.h2d_payload_bytes
     barrier()
     torch.cuda.synchronize()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -295,6 +296,8 @@ def main():
         e2e_ms = float(t.item())
     e2e_value = world * bases * args.e2e_steps / (e2e_ms * 1e-3)
     d2h = len(variants) * 48 + 4 + 32 * 4 + 8 * 4
+    # bytes actually copied per step: the small per-read arrays in full + the payload of admitted reads only
+    h2d = h2d - ((batch.n_qual + 1) // 2 + batch.n_qual) + (lvc._handle.h2d_payload_bytes - payload0) // args.e2e_steps
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()

@@ -72,16 +72,26 @@ struct GenoParams {
     uint32_t flags;
     int n_planes;            // all planes, ordered by key (group 0 first)
     int grp_begin[5];        // planes of group g are [grp_begin[g], grp_begin[g+1])
-    int batch;               // planes resident in shared memory at once (<= kGenoPlaneBatch)
     uint32_t cand_cap;
 };
 
 constexpr int kGenoThreads = 256;            // 64 positions x 4 allele slots
-constexpr int kGenoPlaneBatch = 96;          // planes whose power tables are resident at once
 constexpr int kGenoPowBits = 32;
-// shared: per resident plane 32 powers e^(2^k) and (1-e)^(2^k) in extended range + e as a double
-constexpr size_t kGenoSmemPerPlane = 2 * kGenoPowBits * sizeof(XF) + sizeof(double);
-constexpr size_t kGenoSmemBytes = (size_t)kGenoPlaneBatch * kGenoSmemPerPlane;
+
+// Power tables, built once per (plane set, phred table) and cached on the device: for every plane the 32
+// repeated squarings e^(2^k) and (1-e)^(2^k) in extended range.  Layout: [plane][e | 1-e][32].
+__global__ void k_pow_tables(int n_planes, const uint16_t* __restrict__ plane_keys, const double* __restrict__ e_lut,
+                             const double* __restrict__ om_lut, XF* __restrict__ pow_tab, double* __restrict__ ed) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * n_planes) return;
+    const int k = t >> 1;
+    const bool is_om = t & 1;
+    const uint32_t q = plane_keys[k] & 255u;
+    XF v = xf_from_double(is_om ? om_lut[q] : e_lut[q]);
+    XF* dst = pow_tab + (size_t)t * kGenoPowBits;
+    for (int i = 0; i < kGenoPowBits; ++i) { dst[i] = v; v = xf_mul(v, v); }
+    if (!is_om) ed[k] = e_lut[q];
+}
 
 struct AlleleStat {
     XF pe;       // prod e
@@ -111,20 +121,14 @@ __device__ __forceinline__ XF xf_pow_tab(const XF* __restrict__ tab, uint32_t n)
 // One thread per (position, allele slot); the 4 slots of a position sit in 4 adjacent lanes and are
 // combined with shuffles.  Alleles of the rare groups 1..3 are handled by the same lanes in turn.
 __global__ void __launch_bounds__(kGenoThreads) k_genotype(GenoParams gp, const uint32_t* const* __restrict__ plane_ptrs,
-                                                           const uint16_t* __restrict__ plane_keys,
-                                                           const double* __restrict__ e_lut,
-                                                           const double* __restrict__ om_lut,
+                                                           const XF* __restrict__ pow_tab,
+                                                           const double* __restrict__ ed_tab,
                                                            const uint32_t* __restrict__ dels,
                                                            const uint8_t* __restrict__ ref,
                                                            const uint32_t* const* __restrict__ first,
                                                            uint32_t* __restrict__ out_depth, uint32_t* __restrict__ out_ad,
                                                            double* __restrict__ out_lik, lvc_candidate* __restrict__ cand,
                                                            uint32_t* __restrict__ cand_count) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    XF* s_pow_e = reinterpret_cast<XF*>(smem_raw);                                 // [batch][32]
-    XF* s_pow_om = s_pow_e + gp.batch * kGenoPowBits;                               // [batch][32]
-    double* s_ed = reinterpret_cast<double*>(s_pow_om + gp.batch * kGenoPowBits);
-
     const int tid = threadIdx.x;
     const int slot = tid & 3;
     const int64_t p = gp.p0 + (int64_t)blockIdx.x * (kGenoThreads / 4) + (tid >> 2);
@@ -135,32 +139,15 @@ __global__ void __launch_bounds__(kGenoThreads) k_genotype(GenoParams gp, const 
 #pragma unroll
     for (int g = 0; g < 4; ++g) { st[g].pe = xf_one(); st[g].p1 = xf_one(); st[g].es = 0.0; st[g].ad = 0; }
 
-    for (int b0 = 0; b0 < gp.n_planes; b0 += gp.batch) {
-        const int nb = min(gp.batch, gp.n_planes - b0);
-        __syncthreads();
-        // power tables: thread t builds the 32 squarings of one base (e or 1-e of one plane)
-        for (int t = tid; t < 2 * nb; t += kGenoThreads) {
-            const int k = t >> 1;
-            const uint32_t q = plane_keys[b0 + k] & 255u;
-            const bool is_om = t & 1;
-            XF v = xf_from_double(is_om ? om_lut[q] : e_lut[q]);
-            XF* dst = (is_om ? s_pow_om : s_pow_e) + k * kGenoPowBits;
-            for (int i = 0; i < kGenoPowBits; ++i) { dst[i] = v; v = xf_mul(v, v); }
-            if (!is_om) s_ed[k] = e_lut[q];
-        }
-        __syncthreads();
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-            const int k0 = max(gp.grp_begin[g], b0), k1 = min(gp.grp_begin[g + 1], b0 + nb);
-            for (int k = k0; k < k1; ++k) {
-                const uint32_t n = plane_ptrs[k][pc * 4 + slot];
-                if (n) {
-                    const int kk = k - b0;
-                    st[g].ad += n;
-                    st[g].es += (double)n * s_ed[kk];
-                    st[g].pe = xf_mul(st[g].pe, xf_pow_tab(s_pow_e + kk * kGenoPowBits, n));
-                    st[g].p1 = xf_mul(st[g].p1, xf_pow_tab(s_pow_om + kk * kGenoPowBits, n));
-                }
+    for (int g = 0; g < 4; ++g) {
+        for (int k = gp.grp_begin[g]; k < gp.grp_begin[g + 1]; ++k) {
+            const uint32_t n = plane_ptrs[k][pc * 4 + slot];
+            if (n) {
+                st[g].ad += n;
+                st[g].es += (double)n * ed_tab[k];
+                st[g].pe = xf_mul(st[g].pe, xf_pow_tab(pow_tab + (size_t)(2 * k) * kGenoPowBits, n));
+                st[g].p1 = xf_mul(st[g].p1, xf_pow_tab(pow_tab + (size_t)(2 * k + 1) * kGenoPowBits, n));
             }
         }
     }

@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -33,6 +34,8 @@ struct lvc_handle {
     int impl = 0;
     int sm_count = 148;
     uint64_t launches = 0;
+    bool zero_copy_ok = true;                // read page-locked caller payload in place (LVC_ZERO_COPY=0 disables)
+    uint64_t h2d_payload_bytes = 0;          // payload bytes actually copied by lvc_push_batch (cumulative)
     uint64_t ordinal = 0;
     int qprim = 255;                         // primary quality of the current batch (tiled kernel)
     uint8_t* h_sample = nullptr;             // pinned quality sample for device-resident batches
@@ -58,7 +61,7 @@ struct lvc_handle {
     DevBuf b_defer;                          // deferred read list of the tiled kernel
 
     // genotype
-    DevBuf g_order_ptrs, g_order_keys, g_cand;
+    DevBuf g_order_ptrs, g_order_keys, g_cand, g_pow, g_ed;
     double* d_elut = nullptr;                // [512] e, 1-e
     uint32_t* d_out_depth = nullptr;
     uint32_t* d_out_ad = nullptr;
@@ -179,6 +182,7 @@ int lvc_create(lvc_handle** out, int device, int64_t ref_len, const uint8_t* ref
     h->min_bq = min_base_quality;
     h->min_mq = min_mapping_quality;
     for (int k = 0; k < kMaxKeys; ++k) h->lut[k] = kNoPlane;
+    if (const char* zc = getenv("LVC_ZERO_COPY")) h->zero_copy_ok = atoi(zc) != 0;
     auto body = [&]() -> int {
         CU(cudaSetDevice(device));
         cudaDeviceProp prop;
@@ -214,7 +218,6 @@ int lvc_create(lvc_handle** out, int device, int64_t ref_len, const uint8_t* ref
         CU(cudaMemsetAsync(h->d_cand_count, 0, sizeof(uint32_t), h->stream));
         CU(cudaFuncSetAttribute(k_deposit_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
         CU(cudaFuncSetAttribute(k_deposit_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
-        CU(cudaFuncSetAttribute(k_genotype, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGenoSmemBytes));
         CU(cudaStreamSynchronize(h->stream));
         return LVC_OK;
     };
@@ -243,7 +246,7 @@ void lvc_destroy(lvc_handle* h) {
     cudaFree(h->d_elut); cudaFree(h->d_out_depth); cudaFree(h->d_out_ad); cudaFree(h->d_out_lik);
     cudaFree(h->d_cand_count);
     for (DevBuf* b : {&h->b_pos, &h->b_flag, &h->b_mapq, &h->b_keep, &h->b_coff, &h->b_cig, &h->b_soff, &h->b_seq,
-                      &h->b_qual, &h->b_defer, &h->g_order_ptrs, &h->g_order_keys, &h->g_cand})
+                      &h->b_qual, &h->b_defer, &h->g_order_ptrs, &h->g_order_keys, &h->g_cand, &h->g_pow, &h->g_ed})
         cudaFree(b->p);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -472,17 +475,60 @@ int lvc_push_batch(lvc_handle* h, const lvc_batch* b) {
     if (b->cigar_off[b->n_reads] != b->n_cigar_ops || b->seq_off[b->n_reads] != b->n_qual_bytes)
         return fail(h, LVC_EINVAL, "lvc_batch: n_cigar_ops / n_qual_bytes do not match the offset arrays");
     const size_t n = b->n_reads;
-    struct { DevBuf* d; const void* s; size_t bytes; } cp[] = {
-        {&h->b_pos, b->pos, n * 4},           {&h->b_flag, b->flag, n * 2},
-        {&h->b_mapq, b->mapq, n},             {&h->b_keep, b->keep, n},
-        {&h->b_coff, b->cigar_off, (n + 1) * 4}, {&h->b_cig, b->cigar, (size_t)b->n_cigar_ops * 4},
-        {&h->b_soff, b->seq_off, (n + 1) * 8},   {&h->b_seq, b->seq4, (size_t)(b->n_qual_bytes + 1) / 2},
-        {&h->b_qual, b->qual, (size_t)b->n_qual_bytes},
+    struct { DevBuf* d; const void* s; size_t bytes; bool copy; } cp[] = {
+        {&h->b_pos, b->pos, n * 4, true},           {&h->b_flag, b->flag, n * 2, true},
+        {&h->b_mapq, b->mapq, n, true},             {&h->b_keep, b->keep, n, true},
+        {&h->b_coff, b->cigar_off, (n + 1) * 4, true}, {&h->b_cig, b->cigar, (size_t)b->n_cigar_ops * 4, true},
+        {&h->b_soff, b->seq_off, (n + 1) * 8, true},   {&h->b_seq, b->seq4, (size_t)(b->n_qual_bytes + 1) / 2, false},
+        {&h->b_qual, b->qual, (size_t)b->n_qual_bytes, false},
     };
     for (auto& c : cp) {
         rc = ensure(h, *c.d, c.bytes + 64);     // +64: the tiled kernel reads whole 16-byte groups
         if (rc) return rc;
-        if (c.bytes) CU(cudaMemcpyAsync(c.d->p, c.s, c.bytes, cudaMemcpyHostToDevice, h->stream));
+        if (c.bytes && c.copy) CU(cudaMemcpyAsync(c.d->p, c.s, c.bytes, cudaMemcpyHostToDevice, h->stream));
+    }
+    // Payload (4-bit bases + qualities).  If the caller's buffers are page-locked (lvc_host_alloc / cudaHostAlloc)
+    // the kernels read them IN PLACE over PCIe: every chunk's TMA bulk copy pulls exactly the bytes of the reads
+    // that will be deposited, with thousands of requests in flight, and reads dropped by the host admission are
+    // never transferred.  Otherwise only the byte ranges of admitted reads are copied (pageable memory).
+    const uint8_t* dev_qual = (const uint8_t*)h->b_qual.p;
+    const uint8_t* dev_seq = (const uint8_t*)h->b_seq.p;
+    bool zero_copy = false;
+    if (h->zero_copy_ok) {
+        cudaPointerAttributes aq, as;
+        if (cudaPointerGetAttributes(&aq, b->qual) == cudaSuccess && cudaPointerGetAttributes(&as, b->seq4) == cudaSuccess &&
+            aq.type == cudaMemoryTypeHost && as.type == cudaMemoryTypeHost && aq.devicePointer && as.devicePointer &&
+            ((uintptr_t)aq.devicePointer & 15u) == 0 && ((uintptr_t)as.devicePointer & 15u) == 0) {
+            dev_qual = (const uint8_t*)aq.devicePointer;
+            dev_seq = (const uint8_t*)as.devicePointer;
+            zero_copy = true;
+            // account the bytes the kernels will pull over PCIe: the payload of admitted reads
+            uint64_t live = 0;
+            for (size_t i = 0; i < n; ++i)
+                if (b->keep[i] & 1u) live += b->seq_off[i + 1] - b->seq_off[i];
+            h->h2d_payload_bytes += live + live / 2;
+        } else {
+            cudaGetLastError();
+        }
+    }
+    if (!zero_copy) {
+        const uint32_t kGap = 64;                 // merge live ranges separated by fewer dropped reads than this
+        size_t i = 0;
+        while (i < n) {
+            while (i < n && !(b->keep[i] & 1u)) ++i;
+            if (i >= n) break;
+            size_t j = i, last_live = i;
+            while (j < n && j - last_live <= kGap) { if (b->keep[j] & 1u) last_live = j; ++j; }
+            const size_t end = last_live + 1;
+            const uint64_t q0 = b->seq_off[i] & ~15ull, q1 = std::min<uint64_t>((b->seq_off[end] + 15) & ~15ull, b->n_qual_bytes);
+            if (q1 > q0) {
+                CU(cudaMemcpyAsync((uint8_t*)h->b_qual.p + q0, b->qual + q0, q1 - q0, cudaMemcpyHostToDevice, h->stream));
+                const uint64_t s0 = q0 >> 1, s1 = std::min<uint64_t>((q1 + 1) >> 1, (b->n_qual_bytes + 1) >> 1);
+                CU(cudaMemcpyAsync((uint8_t*)h->b_seq.p + s0, b->seq4 + s0, s1 - s0, cudaMemcpyHostToDevice, h->stream));
+                h->h2d_payload_bytes += (q1 - q0) + (s1 - s0);
+            }
+            i = end;
+        }
     }
     rc = premap_host(h, b);
     if (rc) return rc;
@@ -491,8 +537,8 @@ int lvc_push_batch(lvc_handle* h, const lvc_batch* b) {
     bv.pos = (const int32_t*)h->b_pos.p;       bv.flag = (const uint16_t*)h->b_flag.p;
     bv.mapq = (const uint8_t*)h->b_mapq.p;     bv.keep = (const uint8_t*)h->b_keep.p;
     bv.cigar_off = (const uint32_t*)h->b_coff.p; bv.cigar = (const uint32_t*)h->b_cig.p;
-    bv.seq_off = (const uint64_t*)h->b_soff.p; bv.seq4 = (const uint8_t*)h->b_seq.p;
-    bv.qual = (const uint8_t*)h->b_qual.p;
+    bv.seq_off = (const uint64_t*)h->b_soff.p; bv.seq4 = dev_seq;
+    bv.qual = dev_qual;
     return deposit_with_replay(h, bv);
 }
 
@@ -594,10 +640,12 @@ static int genotype_enqueue(lvc_handle* h, int64_t min_total_depth, int64_t min_
         rc = ensure(h, h->g_cand, (size_t)h->cand_cap * sizeof(lvc_candidate));
         if (rc) return rc;
     }
+    bool tables_stale = false;
     if (h->geno_planes_uploaded != (size_t)np) {     // planes are only ever appended: the count identifies the set
         CU(cudaMemcpyAsync(h->g_order_ptrs.p, ptrs.data(), ptrs.size() * sizeof(uint32_t*), cudaMemcpyHostToDevice, h->stream));
         CU(cudaMemcpyAsync(h->g_order_keys.p, keys.data(), keys.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, h->stream));
         h->geno_planes_uploaded = (size_t)np;
+        tables_stale = true;
     }
     if (!h->lut_valid || memcmp(h->lut_host, e_lut, 256 * sizeof(double)) != 0 ||
         memcmp(h->lut_host + 256, om_lut, 256 * sizeof(double)) != 0) {
@@ -605,22 +653,30 @@ static int genotype_enqueue(lvc_handle* h, int64_t min_total_depth, int64_t min_
         memcpy(h->lut_host + 256, om_lut, 256 * sizeof(double));
         CU(cudaMemcpyAsync(h->d_elut, h->lut_host, 512 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
         h->lut_valid = true;
+        tables_stale = true;
+    }
+    if (tables_stale && np > 0) {
+        rc = ensure(h, h->g_pow, (size_t)np * 2 * kGenoPowBits * sizeof(XF));
+        if (rc) return rc;
+        rc = ensure(h, h->g_ed, (size_t)np * sizeof(double));
+        if (rc) return rc;
+        k_pow_tables<<<(2 * np + 63) / 64, 64, 0, h->stream>>>(np, (const uint16_t*)h->g_order_keys.p, h->d_elut,
+                                                               h->d_elut + 256, (XF*)h->g_pow.p, (double*)h->g_ed.p);
+        h->launches++;
     }
     CU(cudaMemsetAsync(h->d_cand_count, 0, sizeof(uint32_t), h->stream));
     GenoParams gp;
     gp.G = h->G; gp.p0 = h->geno_p0; gp.p1 = h->geno_p1 < 0 ? h->G : h->geno_p1; gp.min_total_depth = min_total_depth; gp.min_allele_depth = min_allele_depth;
     gp.min_ratio = min_ratio; gp.flags = flags; gp.n_planes = np; gp.cand_cap = h->cand_cap;
     for (int g = 0; g < 5; ++g) gp.grp_begin[g] = grp_begin[g];
-    gp.batch = std::max(1, std::min(np, kGenoPlaneBatch));
-    const size_t smem = (size_t)gp.batch * kGenoSmemPerPlane;
     const int threads = kGenoThreads;
     const unsigned blocks = (unsigned)((gp.p1 - gp.p0 + (threads / 4) - 1) / (threads / 4));
     if (gp.p1 <= gp.p0) { h->last_cand_count = 0; h->geno_pending = false; return LVC_OK; }
     {
         KernelTimer t(h, 2);
-        k_genotype<<<blocks, threads, smem, h->stream>>>(gp, (const uint32_t* const*)h->g_order_ptrs.p,
-                                                        (const uint16_t*)h->g_order_keys.p, h->d_elut, h->d_elut + 256,
-                                                        h->d_dels, h->d_ref, (const uint32_t* const*)h->d_first_arr,
+        k_genotype<<<blocks, threads, 0, h->stream>>>(gp, (const uint32_t* const*)h->g_order_ptrs.p,
+                                                     (const XF*)h->g_pow.p, (const double*)h->g_ed.p,
+                                                     h->d_dels, h->d_ref, (const uint32_t* const*)h->d_first_arr,
                                                         h->d_out_depth, h->d_out_ad, h->d_out_lik,
                                                         (lvc_candidate*)h->g_cand.p, h->d_cand_count);
     }
@@ -817,5 +873,6 @@ void* lvc_dels_devptr(lvc_handle* h) { return h ? h->d_dels : nullptr; }
 void* lvc_covdiff_devptr(lvc_handle* h) { return h ? h->d_covdiff : nullptr; }
 void* lvc_first_devptr(lvc_handle* h, int group) { return (h && group >= 0 && group < 4) ? h->d_first[group] : nullptr; }
 uint64_t lvc_launch_count(lvc_handle* h) { return h ? h->launches : 0; }
+uint64_t lvc_h2d_payload_bytes(lvc_handle* h) { return h ? h->h2d_payload_bytes : 0; }
 
 }  // extern "C"

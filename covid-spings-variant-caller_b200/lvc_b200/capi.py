@@ -93,6 +93,7 @@ SIGNATURES = [
     ("lvc_covdiff_devptr", C.c_void_p, [_H]),
     ("lvc_first_devptr", C.c_void_p, [_H, C.c_int]),
     ("lvc_launch_count", C.c_uint64, [_H]),
+    ("lvc_h2d_payload_bytes", C.c_uint64, [_H]),
 ]
 
 
@@ -308,6 +309,10 @@ class Handle:
     @property
     def launch_count(self) -> int:
         return int(self.lib.lvc_launch_count(self.h))
+
+    @property
+    def h2d_payload_bytes(self) -> int:
+        return int(self.lib.lvc_h2d_payload_bytes(self.h))
 
     def plane_devptr(self, key: int) -> int:
         return self.lib.lvc_plane_devptr(self.h, int(key)) or 0

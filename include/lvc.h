@@ -173,6 +173,9 @@ void* lvc_first_devptr(lvc_handle* h, int group);
 /* ---- introspection ---------------------------------------------------------------------------- */
 /* number of kernels this library has launched on the handle since creation (bench gpu_launches) */
 uint64_t lvc_launch_count(lvc_handle* h);
+/* cumulative payload bytes (seq4 + qual) lvc_push_batch actually copied host->device: the bytes of reads the
+ * host admission dropped are never shipped */
+uint64_t lvc_h2d_payload_bytes(lvc_handle* h);
 /* per-kernel device time from CUDA events recorded on the handle's stream around every launch while
  * timing is on.  which: 0 = tiled deposit, 1 = general deposit, 2 = genotype.  Reading resets. */
 int lvc_set_timing(lvc_handle* h, int on);

@@ -133,3 +133,26 @@ def test_full_size_config2_properties(lib):
     assert np.array_equal(tabs[0][2], tabs[1][2])
     assert np.array_equal(tabs[2][0], 2 * tabs[1][0]) and np.array_equal(tabs[2][1], 2 * tabs[1][1])
     assert np.array_equal(tabs[2][2], tabs[1][2])                       # first-seen ranks do not move
+
+
+def test_pinned_host_buffers_are_read_in_place(lib):
+    """page-locked caller buffers: the kernels read the payload over PCIe in place (no payload H2D copy);
+    results must equal the copy path and the oracle"""
+    from lvc_b200 import synth, capi, packing
+    from oracle.c_oracle import COracle
+    ref, b = synth.amplicon_sample(seed=11, n_pairs=60_000)
+    pinned = packing.pin_batch(b)
+    tabs = []
+    for batch in (b, pinned):
+        h = capi.Handle(ref.encode("latin-1"), TH["minBQ"], TH["minMQ"], device=0)
+        h.push_batch(batch.as_capi())
+        h.push_batch(batch.as_capi())
+        tabs.append(device_tables(h))
+        h.close()
+    for x, y in zip(tabs[0], tabs[1]):
+        assert np.array_equal(x, y)
+    co = COracle(ref, TH["minBQ"], TH["minMQ"])
+    co.process(b)
+    co.process(b)
+    assert np.array_equal(tabs[1][0], co.ad.astype(np.uint64))
+    assert np.array_equal(tabs[1][2][tabs[1][0] > 0], co.first[co.ad > 0])
