@@ -13,6 +13,7 @@
 #include "lvc_common.cuh"
 #include "deposit_general.cuh"
 #include "deposit_tile.cuh"
+#include "deposit_tile4.cuh"
 #include "genotype.cuh"
 
 using namespace lvc;
@@ -218,6 +219,8 @@ int lvc_create(lvc_handle** out, int device, int64_t ref_len, const uint8_t* ref
         CU(cudaMemsetAsync(h->d_cand_count, 0, sizeof(uint32_t), h->stream));
         CU(cudaFuncSetAttribute(k_deposit_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
         CU(cudaFuncSetAttribute(k_deposit_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
+        CU(cudaFuncSetAttribute(k_deposit_tile4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTile4SmemBytes));
+        CU(cudaFuncSetAttribute(k_deposit_tile4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTile4SmemBytes));
         CU(cudaStreamSynchronize(h->stream));
         return LVC_OK;
     };
@@ -270,7 +273,7 @@ int lvc_sync(lvc_handle* h) {
 }
 
 int lvc_set_impl(lvc_handle* h, int impl) {
-    if (!h || impl < 0 || impl > 2) return LVC_EINVAL;
+    if (!h || impl < 0 || impl > 4 || impl == 3) return LVC_EINVAL;
     h->impl = impl;
     return LVC_OK;
 }
@@ -380,7 +383,12 @@ static int launch_deposit(lvc_handle* h, const BatchView& bv, int replay) {
         tp.qprim = (uint32_t)h->qprim;
         tp.prim_plane = h->lut[h->qprim];
         { KernelTimer t(h, 0);
-          if (h->min_bq <= 0)
+          if (impl == 4) {
+              if (h->min_bq <= 0)
+                  k_deposit_tile4<true><<<tp.grid, kTileThreads, kTile4SmemBytes, h->stream>>>(bv, tv, dp, tp);
+              else
+                  k_deposit_tile4<false><<<tp.grid, kTileThreads, kTile4SmemBytes, h->stream>>>(bv, tv, dp, tp);
+          } else if (h->min_bq <= 0)
               k_deposit_tile<true><<<tp.grid, kTileThreads, kTileSmemBytes, h->stream>>>(bv, tv, dp, tp);
           else
               k_deposit_tile<false><<<tp.grid, kTileThreads, kTileSmemBytes, h->stream>>>(bv, tv, dp, tp); }

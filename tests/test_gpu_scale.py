@@ -72,7 +72,7 @@ def check_against_c_oracle(ref, batches, th, impl, max_depth=8000):
     return n_emit
 
 
-@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("impl", [1, 2, 4])
 def test_amplicon_medium(lib, impl):
     from lvc_b200 import synth
     ref, b = synth.amplicon_sample(seed=7, n_pairs=120_000)
@@ -87,9 +87,10 @@ def test_amplicon_multi_quality(lib, th):
     from lvc_b200 import synth
     ref, b = synth.amplicon_sample(seed=8, n_pairs=30_000, min_mapq=th["minMQ"])
     check_against_c_oracle(ref, [b], th, 2)
+    check_against_c_oracle(ref, [b], th, 4)
 
 
-@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("impl", [1, 2, 4])
 def test_shotgun_small_genome(lib, impl):
     from lvc_b200 import synth
     ref, b = synth.shotgun_sample(seed=9, ref_len=200_000, depth=60.0)
@@ -101,6 +102,7 @@ def test_shotgun_low_max_depth(lib):
     from lvc_b200 import synth
     ref, b = synth.shotgun_sample(seed=10, ref_len=30_000, depth=400.0, max_depth=200)
     check_against_c_oracle(ref, [b], TH, 2, max_depth=200)
+    check_against_c_oracle(ref, [b], TH, 4, max_depth=200)
 
 
 def test_live_batches_ont(lib):
@@ -108,7 +110,7 @@ def test_live_batches_ont(lib):
     ref = synth.random_reference(6000, 3)
     batches = [synth.ont_batch(100 + k, ref, depth=40.0) for k in range(3)]
     th = dict(minBQ=13, minMQ=20, minDP=10, minAD=3, ratio=0.05)
-    for impl in (1, 2):
+    for impl in (1, 2, 4):
         check_against_c_oracle(ref, batches, th, impl)
 
 
@@ -121,7 +123,7 @@ def test_full_size_config2_properties(lib):
     check_against_c_oracle(ref, [b], TH, 2)
     # both kernels agree bit for bit; depositing the batch twice doubles every count
     tabs = []
-    for impl, times in ((1, 1), (2, 1), (2, 2)):
+    for impl, times in ((1, 1), (4, 1), (2, 2)):
         h = capi.Handle(ref.encode("latin-1"), TH["minBQ"], TH["minMQ"], device=0)
         h.set_impl(impl)
         for _ in range(times):
