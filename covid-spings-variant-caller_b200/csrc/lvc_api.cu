@@ -373,7 +373,7 @@ static int launch_deposit(lvc_handle* h, const BatchView& bv, int replay) {
     dp.replay_keys = h->d_replay;
     const uint32_t n = bv.n_reads;
     if (n == 0) return LVC_OK;
-    const int impl = h->impl == 0 ? 2 : h->impl;
+    const int impl = h->impl == 0 ? 4 : h->impl;
     if (impl == 1 || replay || h->qprim == 255 || h->lut[h->qprim] == kNoPlane) {
         { KernelTimer t(h, 1);
           k_deposit_general<<<(n + 127) / 128, 128, 0, h->stream>>>(bv, tv, dp, nullptr, n); }

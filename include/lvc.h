@@ -109,8 +109,9 @@ int lvc_admit(uint32_t n_reads, const int32_t* pos, const uint16_t* flag, const 
 
 /* ---- deposit: process_bam / process_pileup_column / process_svn (live_variant_caller.py:54-103) ----
  * Walks every kept read's CIGAR on the device and adds its bases/qualities to the persistent
- * per-position tables.  Accumulates across calls (live batches).  `impl`: 0 = auto, 1 = general
- * kernel, 2 = tiled fast kernel (general kernel for what it cannot take). */
+ * per-position tables.  Accumulates across calls (live batches).  `impl`: 0 = auto (= 4), 1 = general
+ * kernel only, 2 = tiled kernel staging the raw payload with TMA, 4 = tiled kernel staging 4-bit keys (both use the
+ * general path for what they cannot take). */
 int lvc_push_batch(lvc_handle* h, const lvc_batch* host_batch);
 int lvc_push_batch_device(lvc_handle* h, const lvc_batch* device_batch);
 int lvc_set_impl(lvc_handle* h, int impl);
