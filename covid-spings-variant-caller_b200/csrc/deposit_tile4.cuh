@@ -338,8 +338,12 @@ k_deposit_tile4(BatchView b, TableView tv, DepositParams dp, TileParams tp) {
                                 const uint32_t g80 = GE_ALL ? 0x80808080u : bytes_ge80(qw[w], ge_add4);
                                 oth |= g80 & ~e80[w];
                             }
-                            const uint32_t k0 = s0 & (flags_to_nibbles(e80[0]) | (flags_to_nibbles(e80[1]) << 16));
-                            const uint32_t k1 = s1 & (flags_to_nibbles(e80[2]) | (flags_to_nibbles(e80[3]) << 16));
+                            // byte flags of 8 bases -> nibble mask: gather the even / odd bases' flag bytes (PRMT),
+                            // widen each flag to its nibble with a multiply (fma pipe)
+                            const uint32_t ev0 = __byte_perm(e80[0], e80[1], 0x6420), od0 = __byte_perm(e80[0], e80[1], 0x7531);
+                            const uint32_t ev1 = __byte_perm(e80[2], e80[3], 0x6420), od1 = __byte_perm(e80[2], e80[3], 0x7531);
+                            const uint32_t k0 = s0 & (((ev0 >> 7) * 0x0Fu) | ((od0 >> 7) * 0xF0u));
+                            const uint32_t k1 = s1 & (((ev1 >> 7) * 0x0Fu) | ((od1 >> 7) * 0xF0u));
                             asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(k_smem + 8u * gg), "r"(k0), "r"(k1) : "memory");
                             if (oth) {
                                 // rare: a passing quality other than the primary one -> deposit the base individually
