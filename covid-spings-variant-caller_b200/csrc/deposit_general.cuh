@@ -31,7 +31,7 @@ __device__ __forceinline__ void deposit_base(const TableView& tv, const DepositP
     if (f[cell] > ord) atomicMin(&f[cell], ord);
 }
 
-// Walk one read.  `lane_active` lets the caller run it for a subset of threads.
+// Walk one read (one thread).
 __device__ __forceinline__ void deposit_read_general(const BatchView& b, const TableView& tv, const DepositParams& dp,
                                                      uint32_t i) {
     const uint32_t flag = b.flag[i];
@@ -137,13 +137,10 @@ __device__ __noinline__ void deposit_read_warp(const BatchView& b, const TableVi
     }
 }
 
-// reads [0, n) or, when `list` != nullptr, the reads list[0..n)
-__global__ void __launch_bounds__(128) k_deposit_general(BatchView b, TableView tv, DepositParams dp,
-                                                         const uint32_t* __restrict__ list, uint32_t n) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n) return;
-    const uint32_t i = list ? list[t] : t;
-    deposit_read_general(b, tv, dp, i);
+// one thread per read of the batch
+__global__ void __launch_bounds__(128) k_deposit_general(BatchView b, TableView tv, DepositParams dp, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) deposit_read_general(b, tv, dp, i);
 }
 
 }  // namespace lvc

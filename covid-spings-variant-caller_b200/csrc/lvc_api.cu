@@ -59,7 +59,6 @@ struct lvc_handle {
 
     // batch staging (device copies of host batches)
     DevBuf b_pos, b_flag, b_mapq, b_keep, b_coff, b_cig, b_soff, b_seq, b_qual;
-    DevBuf b_defer;                          // deferred read list of the tiled kernel
 
     // genotype
     DevBuf g_order_ptrs, g_order_keys, g_cand, g_pow, g_ed;
@@ -249,7 +248,7 @@ void lvc_destroy(lvc_handle* h) {
     cudaFree(h->d_elut); cudaFree(h->d_out_depth); cudaFree(h->d_out_ad); cudaFree(h->d_out_lik);
     cudaFree(h->d_cand_count);
     for (DevBuf* b : {&h->b_pos, &h->b_flag, &h->b_mapq, &h->b_keep, &h->b_coff, &h->b_cig, &h->b_soff, &h->b_seq,
-                      &h->b_qual, &h->b_defer, &h->g_order_ptrs, &h->g_order_keys, &h->g_cand, &h->g_pow, &h->g_ed})
+                      &h->b_qual, &h->g_order_ptrs, &h->g_order_keys, &h->g_cand, &h->g_pow, &h->g_ed})
         cudaFree(b->p);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -376,7 +375,7 @@ static int launch_deposit(lvc_handle* h, const BatchView& bv, int replay) {
     const int impl = h->impl == 0 ? 4 : h->impl;
     if (impl == 1 || replay || h->qprim == 255 || h->lut[h->qprim] == kNoPlane) {
         { KernelTimer t(h, 1);
-          k_deposit_general<<<(n + 127) / 128, 128, 0, h->stream>>>(bv, tv, dp, nullptr, n); }
+          k_deposit_general<<<(n + 127) / 128, 128, 0, h->stream>>>(bv, tv, dp, n); }
         h->launches++;
     } else {
         TileParams tp = make_tile_params(n, h->sm_count);
@@ -884,3 +883,5 @@ uint64_t lvc_launch_count(lvc_handle* h) { return h ? h->launches : 0; }
 uint64_t lvc_h2d_payload_bytes(lvc_handle* h) { return h ? h->h2d_payload_bytes : 0; }
 
 }  // extern "C"
+
+#include "ingest.cpp.inc"

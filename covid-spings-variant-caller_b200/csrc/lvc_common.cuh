@@ -11,7 +11,7 @@ constexpr int kMaxKeys = 1024;          // 4 allele groups x 256 qualities
 constexpr uint32_t kFlagFilter = 0x4u | 0x100u | 0x200u | 0x400u;   // UNMAP|SECONDARY|QCFAIL|DUP
 
 // status words written by the deposit kernels
-enum { ST_UNMAPPED = 0, ST_RANGE_ERR = 1, ST_DEFERRED = 2, ST_CHUNK_CTR = 3, ST_WORDS = 8 };
+enum { ST_UNMAPPED = 0, ST_RANGE_ERR = 1, ST_WORDS = 8 };
 
 // BAM nibble -> (group<<2 | slot).  A,C,G,T (1,2,4,8) are group 0 slots 0..3; the other 12 codes fill
 // groups 1..3 in ascending nibble order.  Packed 4 bits per nibble, nibble 0 in the low digit.

@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("LVC_LIB_PATH") or os.path.join(_HERE, "liblvc_b200.so
 
 LVC_OK = 0
 ERRORS = {-1: "LVC_EINVAL", -2: "LVC_ECUDA", -3: "LVC_ENOMEM", -4: "LVC_EUNSORTED", -5: "LVC_ERANGE",
-          -6: "LVC_ENODEVICE", -7: "LVC_EAGAIN"}
+          -6: "LVC_ENODEVICE", -7: "LVC_EAGAIN", -8: "LVC_EIO"}
 GENO_EMIT_ALL = 1
 MAX_DEPTH_DEFAULT = 8000
 
@@ -59,6 +59,12 @@ SIGNATURES = [
     ("lvc_sync", C.c_int, [_H]),
     ("lvc_admit", C.c_int, [C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                             C.c_void_p]),
+    ("lvc_read_alignments", C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_char_p,
+                                      C.c_int]),
+    ("lvc_reads_batch", C.c_int, [C.c_void_p, C.POINTER(Batch)]),
+    ("lvc_reads_info", C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int),
+                                 C.POINTER(C.c_int)]),
+    ("lvc_reads_free", None, [C.c_void_p]),
     ("lvc_push_batch", C.c_int, [_H, C.POINTER(Batch)]),
     ("lvc_push_batch_device", C.c_int, [_H, C.POINTER(Batch)]),
     ("lvc_set_impl", C.c_int, [_H, C.c_int]),
@@ -137,6 +143,69 @@ def admit(pos: np.ndarray, flag: np.ndarray, mapq: np.ndarray, cigar_off: np.nda
     if rc != LVC_OK:
         raise LvcError(rc, "lvc_admit failed")
     return keep
+
+
+class NativeReads:
+    """Alignments of one contig read and packed by the native ingest (lvc_read_alignments)."""
+
+    def __init__(self, path: str, contig: Optional[str], min_mapq: int, max_depth: int = MAX_DEPTH_DEFAULT,
+                 n_threads: int = 0):
+        self.lib = load_library()
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)                      # pysam raises OSError for a missing file too
+        r = C.c_void_p()
+        err = C.create_string_buffer(512)
+        rc = self.lib.lvc_read_alignments(path.encode(), (contig or "").encode(), int(min_mapq), int(max_depth),
+                                          int(n_threads), C.byref(r), err, 512)
+        if rc != LVC_OK:
+            msg = err.value.decode()
+            if "invalid contig" in msg or "not coordinate sorted" in msg:
+                raise ValueError(msg)
+            from .packing import UnsupportedInput
+            if rc == -1:
+                raise UnsupportedInput(msg)
+            raise LvcError(rc, msg)
+        self.r = r
+        self.batch = Batch()
+        self.lib.lvc_reads_batch(self.r, C.byref(self.batch))
+        self.batch._keepalive = self
+        name = C.create_string_buffer(256)
+        ln, nc, pinned = C.c_int64(0), C.c_int(0), C.c_int(0)
+        self.lib.lvc_reads_info(self.r, name, 256, C.byref(ln), C.byref(nc), C.byref(pinned))
+        self.contig, self.contig_len, self.pinned = name.value.decode(), ln.value, bool(pinned.value)
+
+    @property
+    def n_reads(self) -> int:
+        return int(self.batch.n_reads)
+
+    def as_readbatch(self):
+        """numpy views (no copy) in the layout of packing.ReadBatch; valid while this object lives"""
+        from .packing import ReadBatch
+        b = self.batch
+        n = b.n_reads
+
+        def view(ptr, dtype, count):
+            if count == 0:
+                return np.zeros(0, dtype=dtype)
+            buf = (C.c_uint8 * (count * np.dtype(dtype).itemsize)).from_address(ptr)
+            return np.frombuffer(buf, dtype=dtype, count=count)
+        rb = ReadBatch(view(b.pos, np.int32, n), view(b.flag, np.uint16, n), view(b.mapq, np.uint8, n),
+                       view(b.keep, np.uint8, n), view(b.cigar_off, np.uint32, n + 1),
+                       view(b.cigar, np.uint32, max(int(b.n_cigar_ops), 1)), view(b.seq_off, np.uint64, n + 1),
+                       view(b.seq4, np.uint8, int(b.n_qual_bytes) // 2 + 64), view(b.qual, np.uint8, int(b.n_qual_bytes) + 64))
+        rb._keepalive = self
+        return rb
+
+    def close(self):
+        if getattr(self, "r", None):
+            self.lib.lvc_reads_free(self.r)
+            self.r = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Handle:

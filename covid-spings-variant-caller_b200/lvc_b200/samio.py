@@ -205,9 +205,17 @@ def read_bam(path: str, contig: Optional[str], min_mapq: int,
     return contigs, packing.finalize_batch(pos, flag, mapq, coff, cigar, soff, seq4, qual, min_mapq, max_depth)
 
 
+def read_alignments_native(path: str, contig: Optional[str], min_mapq: int,
+                           max_depth: int = packing.capi.MAX_DEPTH_DEFAULT, n_threads: int = 0):
+    """BAM or SAM through the library's native ingest (multi-threaded BGZF inflate, page-locked output).
+    Returns a capi.NativeReads; `.batch` goes straight to Handle.push_batch, `.as_readbatch()` gives numpy views."""
+    return packing.capi.NativeReads(path, contig, min_mapq, max_depth, n_threads)
+
+
 def read_alignments(path: str, contig: Optional[str], min_mapq: int,
                     max_depth: int = packing.capi.MAX_DEPTH_DEFAULT):
-    """Dispatch on the file content: BGZF magic -> BAM, otherwise SAM text."""
+    """Pure-Python reader (kept as an independent cross-check of the native ingest).
+    Dispatch on the file content: BGZF magic -> BAM, otherwise SAM text."""
     with open(path, "rb") as fh:
         magic = fh.read(4)
     if magic[:2] == b"\x1f\x8b":
@@ -247,6 +255,58 @@ def write_bam(path: str, contigs: List[Tuple[str, int]], reads, header_text: Opt
             cdata = comp.compress(chunk) + comp.flush()
             bsize = len(cdata) + 25
             fh.write(b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", bsize))
+            fh.write(cdata)
+            fh.write(struct.pack("<II", zlib.crc32(chunk) & 0xFFFFFFFF, len(chunk)))
+        fh.write(_BGZF_EOF)
+
+
+def write_bam_batch(path: str, contig: Tuple[str, int], batch, level: int = 1):
+    """Write a packed ReadBatch as a BGZF BAM without a per-read Python loop (ingest benchmarks and
+    large fixtures).  Every read gets the 2-byte name "r"; mates are written unpaired-position (-1)."""
+    n = batch.n_reads
+    ncig = np.diff(batch.cigar_off[:n + 1]).astype(np.int64)
+    lq = np.diff(batch.seq_off[:n + 1].astype(np.int64))
+    lq_true = packing.query_lengths(batch.cigar_off, batch.cigar)[:n].astype(np.int64)
+    sbytes = (lq_true + 1) // 2
+    rec_len = 32 + 2 + 4 * ncig + sbytes + lq_true
+    offs = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(rec_len + 4, out=offs[1:])
+    out = np.zeros(int(offs[-1]), dtype=np.uint8)
+    core = np.zeros(n, dtype=np.dtype([("bs", "<i4"), ("ref", "<i4"), ("pos", "<i4"), ("lname", "u1"), ("mapq", "u1"),
+                                       ("bin", "<u2"), ("ncig", "<u2"), ("flag", "<u2"), ("lseq", "<i4"),
+                                       ("nref", "<i4"), ("npos", "<i4"), ("tlen", "<i4"), ("name", "S2")]))
+    core["bs"], core["pos"], core["lname"], core["mapq"] = rec_len, batch.pos[:n], 2, batch.mapq[:n]
+    core["bin"], core["ncig"], core["flag"], core["lseq"] = 4680, ncig, batch.flag[:n], lq_true
+    core["nref"], core["npos"], core["name"] = -1, -1, b"r"
+    hdr = core.view(np.uint8).reshape(n, 38)
+    out[(offs[:n, None] + np.arange(38)[None, :]).ravel()] = hdr.ravel()
+
+    def scatter(dst0, src0, lens, src):
+        tot = int(lens.sum())
+        if not tot:
+            return
+        starts = np.zeros(n, dtype=np.int64)
+        np.cumsum(lens[:-1], out=starts[1:])
+        within = np.arange(tot, dtype=np.int64) - np.repeat(starts, lens)
+        out[np.repeat(dst0, lens) + within] = src[np.repeat(src0, lens) + within]
+
+    cig8 = np.ascontiguousarray(batch.cigar).view(np.uint8)
+    scatter(offs[:n] + 38, batch.cigar_off[:n].astype(np.int64) * 4, 4 * ncig, cig8)
+    so = batch.seq_off[:n].astype(np.int64)
+    scatter(offs[:n] + 38 + 4 * ncig, so // 2, sbytes, batch.seq4)
+    scatter(offs[:n] + 38 + 4 * ncig + sbytes, so, lq_true, batch.qual)
+    _ = lq
+    name, length = contig
+    header_text = f"@HD\tVN:1.6\tSO:coordinate\n@SQ\tSN:{name}\tLN:{length}\n"
+    head = (b"BAM\x01" + struct.pack("<i", len(header_text)) + header_text.encode() + struct.pack("<i", 1) +
+            struct.pack("<i", len(name) + 1) + name.encode() + b"\x00" + struct.pack("<i", length))
+    body = head + out.tobytes()
+    with open(path, "wb") as fh:
+        for i in range(0, len(body), 0xFF00):
+            chunk = body[i:i + 0xFF00]
+            comp = zlib.compressobj(level, zlib.DEFLATED, -15)
+            cdata = comp.compress(chunk) + comp.flush()
+            fh.write(b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", len(cdata) + 25))
             fh.write(cdata)
             fh.write(struct.pack("<II", zlib.crc32(chunk) & 0xFFFFFFFF, len(chunk)))
         fh.write(_BGZF_EOF)

@@ -111,8 +111,10 @@ class LiveVariantCaller:
         packs them and deposits them into the device tables."""
         with self._lock:
             self._open_contig(referenceIndex)
-            _contigs, batch = samio.read_alignments(inputBam, self._contig, int(self.minMappingQuality), self.maxDepth)
-            self.process_batch(batch)
+            reads = samio.read_alignments_native(inputBam, self._contig, int(self.minMappingQuality), self.maxDepth)
+            if reads.n_reads:
+                self._handle.push_batch(reads.batch)
+            reads.close()
 
     def process_batch(self, batch: ReadBatch):
         """Deposit one packed, coordinate-sorted batch (the fast entry point for live batches)."""

@@ -28,6 +28,7 @@ extern "C" {
 #define LVC_EUNSORTED (-4)  /* reads not coordinate sorted (htslib errors out too)   */
 #define LVC_ERANGE (-5)     /* a read extends past the reference / ordinal space exhausted      */
 #define LVC_ENODEVICE (-6)  /* no CUDA device: there is NO CPU fallback                          */
+#define LVC_EIO (-8)        /* file cannot be opened / read                                     */
 #define LVC_EAGAIN (-7)     /* async pushes met a new (allele group, quality) key: redo synchronously */
 
 #define LVC_MAX_DEPTH_DEFAULT 8000 /* pysam pileup() default max_depth [EXT], SURVEY B1/B4 */
@@ -106,6 +107,19 @@ int lvc_sync(lvc_handle* h);
 int lvc_admit(uint32_t n_reads, const int32_t* pos, const uint16_t* flag, const uint8_t* mapq,
               const uint32_t* cigar_off, const uint32_t* cigar, int min_mapping_quality, int max_depth,
               uint8_t* keep_out);
+
+/* ---- native host ingest (no GPU needed): BAM (BGZF, multi-threaded inflate) or SAM text -> packed batch ----
+ * Replaces pysam.AlignmentFile(inputBam, 'rb') + the region iterator (live_variant_caller.py:55-60) and, for SAM
+ * input, pysam.sort's order (client_server/vc_queue.py:34).  Reads of `contig` (NULL / "" = first @SQ) are packed
+ * into page-locked arrays when a CUDA device is present (lvc_push_batch then reads the payload in place), the keep
+ * mask (lvc_admit + the ACGT-only hint) is filled in.  Records the path cannot reproduce (missing qualities,
+ * overlapping proper pairs, CG-tag CIGARs) are refused with LVC_EINVAL and a message in errbuf. */
+typedef struct lvc_reads lvc_reads;
+int lvc_read_alignments(const char* path, const char* contig, int min_mapping_quality, int max_depth, int n_threads,
+                        lvc_reads** out, char* errbuf, int errlen);
+int lvc_reads_batch(const lvc_reads* r, lvc_batch* batch_out);   /* pointers stay valid until lvc_reads_free */
+int lvc_reads_info(const lvc_reads* r, char* contig_name, int name_cap, int64_t* contig_len, int* n_contigs, int* pinned);
+void lvc_reads_free(lvc_reads* r);
 
 /* ---- deposit: process_bam / process_pileup_column / process_svn (live_variant_caller.py:54-103) ----
  * Walks every kept read's CIGAR on the device and adds its bases/qualities to the persistent

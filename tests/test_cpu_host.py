@@ -168,3 +168,44 @@ def test_vcf_text_layout():
     assert lines[0] == "##fileformat=VCFv4.2" and lines[-3].startswith("#CHROM")
     assert lines[-2] == "NC_045512.2\t10\t.\tA\tT\t0.001\t.\tDP=70;AD=5;GL=0;PL=0;SCORE=0"
     assert lines[-1] == "NC_045512.2\t10\t.\tA\tG\t0.000316228\t.\tDP=70;AD=60;GL=-35.0082;PL=350;SCORE=99"
+
+
+def test_native_ingest_matches_python_readers(lib, golden_synth, tmp_path):
+    """lvc_read_alignments (C++: BGZF inflate, SAM parse + samtools-order sort, packing, admission, ACGT hint)
+    against the independent pure-Python readers, on the reference's fixture and on a generated BAM"""
+    from lvc_b200 import samio, packing
+    sam = os.path.join(GOLD, "testfile.sam")
+    cases = [(sam, None, 0), (sam, "NC_045512.2", 20)]
+    # a BAM with every CIGAR op, filtered reads, odd lengths, N bases
+    g = golden_synth["mixed_small"]
+    reads = synth_small.rows_to_reads(g["reads"])
+    bam = str(tmp_path / "m.bam")
+    samio.write_bam(bam, [("chrS", len(g["ref"]))], [(r.flag, r.pos, r.mapq, r.cigar, r.seq, r.qual, r.name) for r in reads])
+    cases += [(bam, "chrS", 0), (bam, None, 20)]
+    # an unsorted SAM: both readers sort like samtools
+    rows = g["reads"][::-1]
+    usam = tmp_path / "u.sam"
+    usam.write_text("@SQ\tSN:chrS\tLN:%d\n" % len(g["ref"]) +
+                    "".join(f"{n}\t{f}\tchrS\t{p + 1}\t{m}\t{c}\t*\t0\t0\t{s}\t{q}\n" for n, f, p, m, c, s, q in rows))
+    cases.append((str(usam), None, 0))
+    for path, contig, mq in cases:
+        _, pyb = samio.read_alignments(path, contig, mq)
+        nat = samio.read_alignments_native(path, contig, mq, n_threads=3)
+        nb = nat.as_readbatch()
+        assert nat.n_reads == pyb.n_reads, path
+        for f in ("pos", "flag", "mapq", "keep", "cigar_off", "seq_off"):
+            assert getattr(nb, f).tolist() == getattr(pyb, f).tolist(), (path, f)
+        assert nb.cigar[:nb.n_cigar].tolist() == pyb.cigar[:pyb.n_cigar].tolist()
+        assert nb.qual[:nb.n_qual].tolist() == pyb.qual[:pyb.n_qual].tolist()
+        assert nb.seq4[:nb.n_qual // 2].tolist() == pyb.seq4[:pyb.n_qual // 2].tolist()
+        nat.close()
+    with pytest.raises(ValueError):
+        samio.read_alignments_native(bam, "chrNope", 0)
+    with pytest.raises(OSError):
+        samio.read_alignments_native(str(tmp_path / "missing.bam"), None, 0)
+    ov = tmp_path / "ov.sam"
+    ov.write_text("@SQ\tSN:c\tLN:1000\n"
+                  "a\t99\tc\t11\t60\t50M\t=\t41\t80\t" + "A" * 50 + "\t" + "I" * 50 + "\n"
+                  "a\t147\tc\t41\t60\t50M\t=\t11\t-80\t" + "A" * 50 + "\t" + "I" * 50 + "\n")
+    with pytest.raises(packing.UnsupportedInput):
+        samio.read_alignments_native(str(ov), None, 0)
