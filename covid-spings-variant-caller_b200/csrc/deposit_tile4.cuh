@@ -16,7 +16,11 @@
 namespace lvc {
 
 constexpr int kTile4CtasPerSM = 4;
-constexpr int kTaskRuns = 64;                    // runs per task (4 passes of 16 runs; 4-bit counters hold <= 4)
+#ifndef LVC_TASK_RUNS
+#define LVC_TASK_RUNS 128
+#endif
+constexpr int kTaskRuns = LVC_TASK_RUNS;         // runs per task (passes of 16 runs; the 4-bit counters hold <= 15 passes)
+static_assert(kTaskRuns % 32 == 0 && kTaskRuns <= 224, "4-bit counters: at most 15 units per lane");
 constexpr uint32_t kKeyBasesPerWin = kTileReads * 160u;              // bases per staged window (stride)
 constexpr uint32_t kKeyCapBases = kKeyBasesPerWin + kMaxReadBytes;   // + one longest tileable read
 
@@ -36,7 +40,8 @@ struct Tile4Smem {
     static constexpr uint32_t slab_pre_off = slab_a_off + kMaxSlabs * 4;       // u32 [kMaxSlabs+1]
     static constexpr uint32_t slab_n_off = slab_pre_off + (kMaxSlabs + 1) * 4; // u32 [kMaxSlabs]
     static constexpr uint32_t misc_off = (slab_n_off + kMaxSlabs * 4 + 15) & ~15u;
-    static constexpr uint32_t total = misc_off + 256;
+    static constexpr uint32_t pk_off = misc_off + 256;                         // uint2 [kMaxRuns]: what the pass loop reads
+    static constexpr uint32_t total = pk_off + kMaxRuns * 8;
 };
 constexpr size_t kTile4SmemBytes = Tile4Smem::total;
 static_assert((kTile4SmemBytes + 1024) * kTile4CtasPerSM <= 227 * 1024, "the intended CTAs per SM must fit");
@@ -56,6 +61,19 @@ __device__ __forceinline__ PassUnit4 pass_load4(uint32_t k_smem, int32_t ka, int
     u.k1 = __funnelshift_r(x1, x2, sh);
     return u;
 }
+// PRMT in its default mode: selector nibbles with bit 3 set replicate the SIGN of the selected byte over the
+// result byte (0xFF / 0x00).  (__byte_perm masks that bit off, hence the inline PTX.)
+__device__ __forceinline__ uint32_t prmt_sign(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+// (a & c) | (b & ~c) in one LOP3
+__device__ __forceinline__ uint32_t bitsel(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
 // byte flags (0x80 per byte) of 4 bases -> nibble mask (0xF per passing base) in bits 0..15
 __device__ __forceinline__ uint32_t flags_to_nibbles(uint32_t f80) {
     const uint32_t m = f80 >> 7;                                   // bits 0, 8, 16, 24
@@ -63,9 +81,12 @@ __device__ __forceinline__ uint32_t flags_to_nibbles(uint32_t f80) {
     return ((x | (x >> 8)) & 0x1111u) * 15u;                       // nibbles 0..3
 }
 
+// kernel parameters stay in the constant bank even where their address is taken (the warp-per-read helper takes
+// the views by reference): without this every thread copies them to local memory first
+#define LVC_GC const __grid_constant__
 template <bool GE_ALL>
 __global__ void __launch_bounds__(kTileThreads, kTile4CtasPerSM)
-k_deposit_tile4(BatchView b, TableView tv, DepositParams dp, TileParams tp) {
+k_deposit_tile4(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp, LVC_GC TileParams tp) {
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t sbase = smem_u32(smem);
     uint32_t* s_tab = reinterpret_cast<uint32_t*>(smem + Tile4Smem::tab_off);
@@ -80,6 +101,7 @@ k_deposit_tile4(BatchView b, TableView tv, DepositParams dp, TileParams tp) {
     uint32_t* s_slab_pre = reinterpret_cast<uint32_t*>(smem + Tile4Smem::slab_pre_off);
     uint32_t* s_slab_n = reinterpret_cast<uint32_t*>(smem + Tile4Smem::slab_n_off);
     uint32_t* s_misc = reinterpret_cast<uint32_t*>(smem + Tile4Smem::misc_off);
+    uint2* s_pk = reinterpret_cast<uint2*>(smem + Tile4Smem::pk_off);
     // s_misc: [0,1] mbarrier  [2] task counter  [3] n_items  [4] window max end column (long reads only)  [6] deferred reads
     //         [5] run table end (overflow only)
     //         [8..11] min read byte, max read end byte, max reference span, max end column   [32..39] runs per warp
@@ -142,7 +164,17 @@ k_deposit_tile4(BatchView b, TableView tv, DepositParams dp, TileParams tp) {
         uint32_t nr = 0, nd = 0, rspan = 0;
         bool defer = false;
         const uint32_t i = chunk0 + tid;
-        if (read_passes_filter(hd.flag, hd.mapq, hd.keep, dp.min_mq)) {
+        const bool rpass = read_passes_filter(hd.flag, hd.mapq, hd.keep, dp.min_mq);
+        // warp-uniform shortcut: every read of the warp that passes the filter is one match op (150M): no CIGAR walk
+        const uint32_t l0 = hd.cg0 >> 4;
+        const bool one_m = hd.nc == 1 && op_is_match(hd.cg0 & 15u) && (hd.keep & 2u) && (hd.so1 - hd.so) <= kMaxReadBytes &&
+                           l0 >= 1u && l0 <= 65535u;
+        if (__all_sync(0xFFFFFFFFu, !rpass || one_m)) {
+            if (rpass) {
+                if (hd.pos < 0 || (int64_t)hd.pos + l0 > tv.G) atomicAdd(&tv.status[ST_RANGE_ERR], 1u);
+                else { nr = 1; run_pos[0] = hd.pos; run_len[0] = l0; run_q[0] = 0; rspan = l0; }
+            }
+        } else if (rpass) {
             bool tileable = hd.nc <= (uint32_t)kMaxCigarTile && hd.nc > 0 && (hd.so1 - hd.so) <= kMaxReadBytes &&
                             (hd.keep & 2u);
             uint32_t lq = 0;
@@ -271,6 +303,8 @@ k_deposit_tile4(BatchView b, TableView tv, DepositParams dp, TileParams tp) {
                         s_len[idx] = (uint16_t)run_len[k];
                         s_rd[idx] = (uint16_t)(run_pos[k] - hd.pos);
                         s_rix[idx] = (uint16_t)((win << 8) | (uint32_t)tid);
+                        // (start column, key offset inside the read's window | length << 16): one 8-byte load per unit
+                        s_pk[idx] = make_uint2((uint32_t)run_pos[k], ((off + run_q[k] - win * kWinStride) & 0xFFFFu) | (run_len[k] << 16));
                     }
                 }
             }
@@ -327,29 +361,32 @@ k_deposit_tile4(BatchView b, TableView tv, DepositParams dp, TileParams tp) {
                             const uint32_t gg = half ? gB : g;
                             const uint4 q = half ? qB : qA;
                             const uint2 sraw = half ? sB : sA;
-                            const uint32_t qw[4] = {q.x, q.y, q.z, q.w};
                             // base nibbles in little-endian nibble order (base k at bits 4k)
-                            const uint32_t s0 = ((sraw.x & 0x0F0F0F0Fu) << 4) | ((sraw.x >> 4) & 0x0F0F0F0Fu);
-                            const uint32_t s1 = ((sraw.y & 0x0F0F0F0Fu) << 4) | ((sraw.y >> 4) & 0x0F0F0F0Fu);
-                            uint32_t e80[4], oth = 0;
-#pragma unroll
-                            for (int w = 0; w < 4; ++w) {
-                                e80[w] = bytes_eq80(qw[w], qprim4);
-                                const uint32_t g80 = GE_ALL ? 0x80808080u : bytes_ge80(qw[w], ge_add4);
-                                oth |= g80 & ~e80[w];
-                            }
-                            // byte flags of 8 bases -> nibble mask: gather the even / odd bases' flag bytes (PRMT),
-                            // widen each flag to its nibble with a multiply (fma pipe)
-                            const uint32_t ev0 = __byte_perm(e80[0], e80[1], 0x6420), od0 = __byte_perm(e80[0], e80[1], 0x7531);
-                            const uint32_t ev1 = __byte_perm(e80[2], e80[3], 0x6420), od1 = __byte_perm(e80[2], e80[3], 0x7531);
-                            const uint32_t k0 = s0 & (((ev0 >> 7) * 0x0Fu) | ((od0 >> 7) * 0xF0u));
-                            const uint32_t k1 = s1 & (((ev1 >> 7) * 0x0Fu) | ((od1 >> 7) * 0xF0u));
-                            asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(k_smem + 8u * gg), "r"(k0), "r"(k1) : "memory");
-                            if (oth) {
-                                // rare: a passing quality other than the primary one -> deposit the base individually
+                            const uint32_t s0 = bitsel(sraw.x >> 4, sraw.x << 4, 0x0F0F0F0Fu);
+                            const uint32_t s1 = bitsel(sraw.y >> 4, sraw.y << 4, 0x0F0F0F0Fu);
+                            // Qualities below 128 (every real file): no carries between bytes, so per word
+                            //   bit 7 of (q ^ qprim) + 0x7F = "differs from the primary quality"
+                            //   bit 7 of  q + (0x80 - minBQ) = "passes the base-quality threshold"
+                            const uint32_t t0 = (q.x ^ qprim4) + 0x7F7F7F7Fu, t1 = (q.y ^ qprim4) + 0x7F7F7F7Fu;
+                            const uint32_t t2 = (q.z ^ qprim4) + 0x7F7F7F7Fu, t3 = (q.w ^ qprim4) + 0x7F7F7F7Fu;
+                            uint32_t cold = q.x | q.y | q.z | q.w;                       // a byte >= 128: exact path
+                            if (GE_ALL) cold |= t0 | t1 | t2 | t3;
+                            else cold |= (t0 & (q.x + ge_add4)) | (t1 & (q.y + ge_add4)) | (t2 & (q.z + ge_add4)) |
+                                         (t3 & (q.w + ge_add4));                          // passing, not primary
+                            // "differs" flags of the even / odd bases gathered and widened to bytes (PRMT sign mode)
+                            uint32_t k0 = s0 & ~bitsel(prmt_sign(t0, t1, 0xECA8u), prmt_sign(t0, t1, 0xFDB9u), 0x0F0F0F0Fu);
+                            uint32_t k1 = s1 & ~bitsel(prmt_sign(t2, t3, 0xECA8u), prmt_sign(t2, t3, 0xFDB9u), 0x0F0F0F0Fu);
+                            if (cold & 0x80808080u) {
+                                // rare: exact flags; a passing quality other than the primary one is deposited individually
+                                k0 = 0; k1 = 0;
 #pragma unroll 1
                                 for (int w = 0; w < 4; ++w) {
-                                    uint32_t m80 = (GE_ALL ? 0x80808080u : bytes_ge80(qw[w], ge_add4)) & ~e80[w];
+                                    const uint32_t qv = w == 0 ? q.x : (w == 1 ? q.y : (w == 2 ? q.z : q.w));
+                                    const uint32_t e80 = bytes_eq80(qv, qprim4);
+                                    const uint32_t sx = ((w < 2) ? s0 : s1) >> (16 * (w & 1));     // these 4 bases' nibbles
+                                    const uint32_t kw = sx & flags_to_nibbles(e80);
+                                    if (w < 2) k0 |= kw << (16 * (w & 1)); else k1 |= kw << (16 * (w & 1));
+                                    uint32_t m80 = (GE_ALL ? 0x80808080u : bytes_ge80(qv, ge_add4)) & ~e80;
                                     while (m80) {
                                         const int bb = (__ffs(m80) - 1) >> 3;
                                         m80 &= ~(0x80u << (8 * bb));
@@ -358,16 +395,14 @@ k_deposit_tile4(BatchView b, TableView tv, DepositParams dp, TileParams tp) {
                                         while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if (s_qo[m] <= x_rel) lo = m + 1; else hi = m; }
                                         if (lo > a0) {
                                             const uint32_t r = lo - 1, d = x_rel - s_qo[r];
-                                            if (d < (uint32_t)s_len[r]) {
-                                                const uint32_t sx = (w < 2) ? s0 : s1;
-                                                const uint32_t nib = (sx >> (16 * (w & 1) + 4 * bb)) & 15u;
-                                                deposit_base(tv, dp, (int64_t)s_pos[r] + d, nib, (qw[w] >> (8 * bb)) & 255u,
-                                                             chunk_ord + (s_rix[r] & 255u));
-                                            }
+                                            if (d < (uint32_t)s_len[r])
+                                                deposit_base(tv, dp, (int64_t)s_pos[r] + d, (sx >> (4 * bb)) & 15u,
+                                                             (qv >> (8 * bb)) & 255u, chunk_ord + (s_rix[r] & 255u));
                                         }
                                     }
                                 }
                             }
+                            asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(k_smem + 8u * gg), "r"(k0), "r"(k1) : "memory");
                         }
                     }
                 }
@@ -424,6 +459,17 @@ k_deposit_tile4(BatchView b, TableView tv, DepositParams dp, TileParams tp) {
                         const uint32_t rb = min(s_slab_a[k] + s_slab_n[k], ra + (uint32_t)kTaskRuns);
                         const int32_t col_lane = wc0 + k * kSlabCols + 16 * w2;
                         uint32_t acc4[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};    // [key word][allele]: 8 columns x 4-bit counters (<= 4)
+                        const uint32_t pk_smem = sbase + Tile4Smem::pk_off;
+                        // one unit = 16 columns of one run.  A run that misses this lane's columns (or a slot past the end
+                        // of the group) becomes a unit of length 0, which the edge mask below empties: no other branch.
+                        auto unit_load = [&](uint32_t r) {
+                            uint32_t px = (uint32_t)col_lane, py = 0;
+                            if (r < rb) asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(px), "=r"(py) : "r"(pk_smem + 8u * r));
+                            int32_t j = col_lane - (int32_t)px, len = (int32_t)(py >> 16);
+                            const bool on = j > -16 && j < len;
+                            j = on ? j : 0; len = on ? len : 0;
+                            return pass_load4(k_smem, (int32_t)(py & 0xFFFFu) + j, j, len);
+                        };
                         auto consume = [&](const PassUnit4& u) {
                             uint32_t k0 = u.k, k1 = u.k1;
                             if (u.j < 0 || u.j + 16 > u.len) {
@@ -439,17 +485,9 @@ k_deposit_tile4(BatchView b, TableView tv, DepositParams dp, TileParams tp) {
                         };
 #pragma unroll 1
                         for (uint32_t r = ra + sread; r < rb; r += 32) {
-                            const uint32_t r2 = r + 16;
-                            const int32_t jA = col_lane - s_pos[r], lenA = (int32_t)s_len[r];
-                            const bool onA = jA > -16 && jA < lenA;
-                            int32_t jB = 0, lenB = 0;
-                            bool onB = false;
-                            if (r2 < rb) { jB = col_lane - s_pos[r2]; lenB = (int32_t)s_len[r2]; onB = jB > -16 && jB < lenB; }
-                            PassUnit4 uA, uB;
-                            if (onA) uA = pass_load4(k_smem, (int32_t)(s_qo[r] - w_rel) + jA, jA, lenA);
-                            if (onB) uB = pass_load4(k_smem, (int32_t)(s_qo[r2] - w_rel) + jB, jB, lenB);
-                            if (onA) consume(uA);
-                            if (onB) consume(uB);
+                            const PassUnit4 uA = unit_load(r), uB = unit_load(r + 16);
+                            consume(uA);
+                            consume(uB);
                         }
                         // widen to 8-bit fields: v[word][parity][allele]; parity 0 = even columns of the word
                         uint32_t v16[16];

@@ -373,7 +373,8 @@ static int launch_deposit(lvc_handle* h, const BatchView& bv, int replay) {
     const uint32_t n = bv.n_reads;
     if (n == 0) return LVC_OK;
     const int impl = h->impl == 0 ? 4 : h->impl;
-    if (impl == 1 || replay || h->qprim == 255 || h->lut[h->qprim] == kNoPlane) {
+    // the tiled kernels' byte arithmetic assumes a primary quality and a threshold below 128
+    if (impl == 1 || replay || h->qprim >= 128 || h->min_bq > 128 || h->lut[h->qprim] == kNoPlane) {
         { KernelTimer t(h, 1);
           k_deposit_general<<<(n + 127) / 128, 128, 0, h->stream>>>(bv, tv, dp, n); }
         h->launches++;
