@@ -15,7 +15,10 @@
 
 namespace lvc {
 
-constexpr int kTile4CtasPerSM = 4;
+#ifndef LVC_CTAS_PER_SM
+#define LVC_CTAS_PER_SM 5
+#endif
+constexpr int kTile4CtasPerSM = LVC_CTAS_PER_SM;
 #ifndef LVC_TASK_RUNS
 #define LVC_TASK_RUNS 128
 #endif
@@ -107,6 +110,9 @@ k_deposit_tile4(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
     //         [8..11] min read byte, max read end byte, max reference span, max end column   [32..39] runs per warp
     const uint32_t k_smem = sbase + Tile4Smem::key_off + kSlack;      // staged keys start here
 
+    // let a kernel launched with programmatic stream serialization (the genotype pass) become resident while this
+    // grid drains; it still waits for this grid's completion before reading
+    asm volatile("griddepcontrol.launch_dependents;");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t qprim4 = tp.qprim * 0x01010101u;
     const int mbq = dp.min_bq < 1 ? 1 : (dp.min_bq > 128 ? 128 : dp.min_bq);
@@ -125,7 +131,8 @@ k_deposit_tile4(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
     }
     for (int k = tid; k < kTabCols * 4; k += kTileThreads) s_tab[k] = 0;
     hdr_load2(b, hd, dp.min_mq);       // CIGAR ops, only for reads that pass the read-level filter
-    __syncthreads();
+    // a chunk in which no read passes the read-level filter (everything dropped by the depth cap) ends here
+    if (!__syncthreads_or(read_passes_filter(hd.flag, hd.mapq, hd.keep, dp.min_mq))) return;
     // byte extent of the reads that pass the read-level filter (a superset of what will be deposited):
     // known before the CIGARs arrive, so the bulk copy overlaps classification
     const uint32_t so_rel = hd.so - (uint32_t)so0, so1_rel = hd.so1 - (uint32_t)so0;
@@ -347,63 +354,67 @@ k_deposit_tile4(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
                     const uint32_t chunk_ord = dp.ord_base + chunk0;
                     const uint4* gq = reinterpret_cast<const uint4*>(b.qual + qbeg);
                     const uint2* gs = reinterpret_cast<const uint2*>(b.seq4 + (qbeg >> 1));
-                    for (uint32_t g = tid; g < n_grp; g += 2 * kTileThreads) {
-                        const uint32_t gB = g + kTileThreads;
-                        const bool hasB = gB < n_grp;
-                        const uint4 qA = gq[g];
-                        const uint2 sA = gs[g];
-                        uint4 qB = make_uint4(0, 0, 0, 0);
-                        uint2 sB = make_uint2(0, 0);
-                        if (hasB) { qB = gq[gB]; sB = gs[gB]; }
-#pragma unroll
-                        for (int half = 0; half < 2; ++half) {
-                            if (half && !hasB) break;
-                            const uint32_t gg = half ? gB : g;
-                            const uint4 q = half ? qB : qA;
-                            const uint2 sraw = half ? sB : sA;
-                            // base nibbles in little-endian nibble order (base k at bits 4k)
-                            const uint32_t s0 = bitsel(sraw.x >> 4, sraw.x << 4, 0x0F0F0F0Fu);
-                            const uint32_t s1 = bitsel(sraw.y >> 4, sraw.y << 4, 0x0F0F0F0Fu);
-                            // Qualities below 128 (every real file): no carries between bytes, so per word
-                            //   bit 7 of (q ^ qprim) + 0x7F = "differs from the primary quality"
-                            //   bit 7 of  q + (0x80 - minBQ) = "passes the base-quality threshold"
-                            const uint32_t t0 = (q.x ^ qprim4) + 0x7F7F7F7Fu, t1 = (q.y ^ qprim4) + 0x7F7F7F7Fu;
-                            const uint32_t t2 = (q.z ^ qprim4) + 0x7F7F7F7Fu, t3 = (q.w ^ qprim4) + 0x7F7F7F7Fu;
-                            uint32_t cold = q.x | q.y | q.z | q.w;                       // a byte >= 128: exact path
-                            if (GE_ALL) cold |= t0 | t1 | t2 | t3;
-                            else cold |= (t0 & (q.x + ge_add4)) | (t1 & (q.y + ge_add4)) | (t2 & (q.z + ge_add4)) |
-                                         (t3 & (q.w + ge_add4));                          // passing, not primary
-                            // "differs" flags of the even / odd bases gathered and widened to bytes (PRMT sign mode)
-                            uint32_t k0 = s0 & ~bitsel(prmt_sign(t0, t1, 0xECA8u), prmt_sign(t0, t1, 0xFDB9u), 0x0F0F0F0Fu);
-                            uint32_t k1 = s1 & ~bitsel(prmt_sign(t2, t3, 0xECA8u), prmt_sign(t2, t3, 0xFDB9u), 0x0F0F0F0Fu);
-                            if (cold & 0x80808080u) {
-                                // rare: exact flags; a passing quality other than the primary one is deposited individually
-                                k0 = 0; k1 = 0;
+                    // one group = 16 bases: 16 quality bytes + 8 sequence bytes -> 16 keys
+                    auto stage_group = [&](uint32_t gg, const uint4& q, const uint2& sraw) {
+                        // base nibbles in little-endian nibble order (base k at bits 4k)
+                        const uint32_t s0 = bitsel(sraw.x >> 4, sraw.x << 4, 0x0F0F0F0Fu);
+                        const uint32_t s1 = bitsel(sraw.y >> 4, sraw.y << 4, 0x0F0F0F0Fu);
+                        // Qualities below 128 (every real file): no carries between bytes, so per word
+                        //   bit 7 of (q ^ qprim) + 0x7F = "differs from the primary quality"
+                        //   bit 7 of  q + (0x80 - minBQ) = "passes the base-quality threshold"
+                        const uint32_t t0 = (q.x ^ qprim4) + 0x7F7F7F7Fu, t1 = (q.y ^ qprim4) + 0x7F7F7F7Fu;
+                        const uint32_t t2 = (q.z ^ qprim4) + 0x7F7F7F7Fu, t3 = (q.w ^ qprim4) + 0x7F7F7F7Fu;
+                        uint32_t cold = q.x | q.y | q.z | q.w;                       // a byte >= 128: exact path
+                        if (GE_ALL) cold |= t0 | t1 | t2 | t3;
+                        else cold |= (t0 & (q.x + ge_add4)) | (t1 & (q.y + ge_add4)) | (t2 & (q.z + ge_add4)) |
+                                     (t3 & (q.w + ge_add4));                          // passing, not primary
+                        // "differs" flags of the even / odd bases gathered and widened to bytes (PRMT sign mode)
+                        uint32_t k0 = s0 & ~bitsel(prmt_sign(t0, t1, 0xECA8u), prmt_sign(t0, t1, 0xFDB9u), 0x0F0F0F0Fu);
+                        uint32_t k1 = s1 & ~bitsel(prmt_sign(t2, t3, 0xECA8u), prmt_sign(t2, t3, 0xFDB9u), 0x0F0F0F0Fu);
+                        if (cold & 0x80808080u) {
+                            // rare: exact flags; a passing quality other than the primary one is deposited individually
+                            k0 = 0; k1 = 0;
 #pragma unroll 1
-                                for (int w = 0; w < 4; ++w) {
-                                    const uint32_t qv = w == 0 ? q.x : (w == 1 ? q.y : (w == 2 ? q.z : q.w));
-                                    const uint32_t e80 = bytes_eq80(qv, qprim4);
-                                    const uint32_t sx = ((w < 2) ? s0 : s1) >> (16 * (w & 1));     // these 4 bases' nibbles
-                                    const uint32_t kw = sx & flags_to_nibbles(e80);
-                                    if (w < 2) k0 |= kw << (16 * (w & 1)); else k1 |= kw << (16 * (w & 1));
-                                    uint32_t m80 = (GE_ALL ? 0x80808080u : bytes_ge80(qv, ge_add4)) & ~e80;
-                                    while (m80) {
-                                        const int bb = (__ffs(m80) - 1) >> 3;
-                                        m80 &= ~(0x80u << (8 * bb));
-                                        const uint32_t x_rel = w_rel + 16u * gg + 4u * (uint32_t)w + (uint32_t)bb;
-                                        uint32_t lo = a0, hi = a1;             // last run with s_qo <= x_rel
-                                        while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if (s_qo[m] <= x_rel) lo = m + 1; else hi = m; }
-                                        if (lo > a0) {
-                                            const uint32_t r = lo - 1, d = x_rel - s_qo[r];
-                                            if (d < (uint32_t)s_len[r])
-                                                deposit_base(tv, dp, (int64_t)s_pos[r] + d, (sx >> (4 * bb)) & 15u,
-                                                             (qv >> (8 * bb)) & 255u, chunk_ord + (s_rix[r] & 255u));
-                                        }
+                            for (int w = 0; w < 4; ++w) {
+                                const uint32_t qv = w == 0 ? q.x : (w == 1 ? q.y : (w == 2 ? q.z : q.w));
+                                const uint32_t e80 = bytes_eq80(qv, qprim4);
+                                const uint32_t sx = ((w < 2) ? s0 : s1) >> (16 * (w & 1));     // these 4 bases' nibbles
+                                const uint32_t kw = sx & flags_to_nibbles(e80);
+                                if (w < 2) k0 |= kw << (16 * (w & 1)); else k1 |= kw << (16 * (w & 1));
+                                uint32_t m80 = (GE_ALL ? 0x80808080u : bytes_ge80(qv, ge_add4)) & ~e80;
+                                while (m80) {
+                                    const int bb = (__ffs(m80) - 1) >> 3;
+                                    m80 &= ~(0x80u << (8 * bb));
+                                    const uint32_t x_rel = w_rel + 16u * gg + 4u * (uint32_t)w + (uint32_t)bb;
+                                    uint32_t lo = a0, hi = a1;             // last run with s_qo <= x_rel
+                                    while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if (s_qo[m] <= x_rel) lo = m + 1; else hi = m; }
+                                    if (lo > a0) {
+                                        const uint32_t r = lo - 1, d = x_rel - s_qo[r];
+                                        if (d < (uint32_t)s_len[r])
+                                            deposit_base(tv, dp, (int64_t)s_pos[r] + d, (sx >> (4 * bb)) & 15u,
+                                                         (qv >> (8 * bb)) & 255u, chunk_ord + (s_rix[r] & 255u));
                                     }
                                 }
                             }
-                            asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(k_smem + 8u * gg), "r"(k0), "r"(k1) : "memory");
                         }
+                        asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(k_smem + 8u * gg), "r"(k0), "r"(k1) : "memory");
+                    };
+                    // software pipeline: the loads of the next two groups are in flight while these two are reduced
+                    uint32_t g = tid;
+                    uint4 qA = make_uint4(0, 0, 0, 0), qB = make_uint4(0, 0, 0, 0);
+                    uint2 sA = make_uint2(0, 0), sB = make_uint2(0, 0);
+                    if (g < n_grp) { qA = gq[g]; sA = gs[g]; }
+                    if (g + kTileThreads < n_grp) { qB = gq[g + kTileThreads]; sB = gs[g + kTileThreads]; }
+                    while (g < n_grp) {
+                        const uint32_t gn = g + 2 * kTileThreads;
+                        uint4 nqA = make_uint4(0, 0, 0, 0), nqB = make_uint4(0, 0, 0, 0);
+                        uint2 nsA = make_uint2(0, 0), nsB = make_uint2(0, 0);
+                        if (gn < n_grp) { nqA = gq[gn]; nsA = gs[gn]; }
+                        if (gn + kTileThreads < n_grp) { nqB = gq[gn + kTileThreads]; nsB = gs[gn + kTileThreads]; }
+                        stage_group(g, qA, sA);
+                        if (g + kTileThreads < n_grp) stage_group(g + kTileThreads, qB, sB);
+                        qA = nqA; sA = nsA; qB = nqB; sB = nsB;
+                        g = gn;
                     }
                 }
 
@@ -541,14 +552,29 @@ k_deposit_tile4(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
                     uint32_t* first0 = tv.first[0];
                     const uint32_t ord_lo = chunk_ord0 + (s_rix[a0] & 255u);
                     const int ncols = min(kTabCols, cmax - wc0);
-                    for (int e = tid; e < ncols * 4; e += kTileThreads) {
-                        const uint32_t v = s_tab[e];
-                        if (v) {
-                            s_tab[e] = 0;
-                            const int64_t cell = (int64_t)wc0 * 4 + e;
-                            atomicAdd(&plane[cell], v);
-                            if (first0[cell] > ord_lo) s_items[atomicAdd(&s_misc[3], 1u)] = (uint16_t)e;
+                    {
+                        // 4 table cells per thread; the 4 first-seen loads are issued together (one memory latency, not 4)
+                        static_assert(kTabCols * 4 == 4 * kTileThreads, "flush: 4 cells per thread");
+                        uint32_t fv[4], ff[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int e = tid + k * kTileThreads;
+                            fv[k] = e < ncols * 4 ? s_tab[e] : 0u;
                         }
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int e = tid + k * kTileThreads;
+                            ff[k] = 0;
+                            if (fv[k]) {
+                                s_tab[e] = 0;
+                                const int64_t cell = (int64_t)wc0 * 4 + e;
+                                atomicAdd(&plane[cell], fv[k]);
+                                ff[k] = first0[cell];
+                            }
+                        }
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (fv[k] && ff[k] > ord_lo) s_items[atomicAdd(&s_misc[3], 1u)] = (uint16_t)(tid + k * kTileThreads);
                     }
                     __syncthreads();                                       // barrier E: table flushed, items known
                     const uint32_t n_items = s_misc[3];

@@ -75,7 +75,8 @@ struct GenoParams {
     uint32_t cand_cap;
 };
 
-constexpr int kGenoThreads = 256;            // 64 positions x 4 allele slots
+constexpr int kGenoThreads = 128;            // 32 positions x 4 allele slots
+constexpr int kGenoBatch = 8;                // plane counts requested together
 constexpr int kGenoPowBits = 32;
 
 // Power tables, built once per (plane set, phred table) and cached on the device: for every plane the 32
@@ -107,15 +108,23 @@ __device__ __forceinline__ XF xf_shfl_xor(XF v, int lanemask) {
     return r;
 }
 
-// x^n from the table of x^(2^k): one extended multiply per set bit of n
+// x^n from the table of x^(2^k): one multiply per set bit of n.  The table entries are normalised
+// (mantissa in [0.5, 1)), so a chain of <= 32 products stays far inside the normal fp64 range: the mantissas are
+// multiplied as they are and the product is re-normalised ONCE (scaling by a power of two is exact, so the bits
+// equal those of a chain normalised after every step).
 __device__ __forceinline__ XF xf_pow_tab(const XF* __restrict__ tab, uint32_t n) {
-    XF r = xf_one();
+    double m = 1.0;
+    long long x = 0;
     while (n) {
         const int k = __ffs(n) - 1;
         n &= n - 1;
-        r = xf_mul(r, tab[k]);
+        const XF t = tab[k];
+        m *= t.m;
+        x += t.x;
     }
-    return r;
+    int e;
+    m = frexp(m, &e);
+    return XF{m, x + e};
 }
 
 // One thread per (position, allele slot); the 4 slots of a position sit in 4 adjacent lanes and are
@@ -128,8 +137,12 @@ __global__ void __launch_bounds__(kGenoThreads) k_genotype(GenoParams gp, const 
                                                            const uint32_t* const* __restrict__ first,
                                                            uint32_t* __restrict__ out_depth, uint32_t* __restrict__ out_ad,
                                                            double* __restrict__ out_lik, lvc_candidate* __restrict__ cand,
-                                                           uint32_t* __restrict__ cand_count) {
+                                                           uint32_t* __restrict__ cand_count,
+                                                           uint32_t* __restrict__ cand_count_next) {
     const int tid = threadIdx.x;
+    // everything below reads tables written by the deposit kernel launched before this one
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (blockIdx.x == 0 && tid == 0) *cand_count_next = 0;
     const int slot = tid & 3;
     const int64_t p = gp.p0 + (int64_t)blockIdx.x * (kGenoThreads / 4) + (tid >> 2);
     const bool live = p < gp.p1;
@@ -141,13 +154,22 @@ __global__ void __launch_bounds__(kGenoThreads) k_genotype(GenoParams gp, const 
 
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
-        for (int k = gp.grp_begin[g]; k < gp.grp_begin[g + 1]; ++k) {
-            const uint32_t n = plane_ptrs[k][pc * 4 + slot];
-            if (n) {
-                st[g].ad += n;
-                st[g].es += (double)n * ed_tab[k];
-                st[g].pe = xf_mul(st[g].pe, xf_pow_tab(pow_tab + (size_t)(2 * k) * kGenoPowBits, n));
-                st[g].p1 = xf_mul(st[g].p1, xf_pow_tab(pow_tab + (size_t)(2 * k + 1) * kGenoPowBits, n));
+        // counts of up to kGenoBatch planes are requested together (one memory latency per batch, not per plane)
+        for (int k0 = gp.grp_begin[g]; k0 < gp.grp_begin[g + 1]; k0 += kGenoBatch) {
+            uint32_t cnt[kGenoBatch];
+#pragma unroll
+            for (int j = 0; j < kGenoBatch; ++j)
+                cnt[j] = k0 + j < gp.grp_begin[g + 1] ? __ldcg(&plane_ptrs[k0 + j][pc * 4 + slot]) : 0u;
+#pragma unroll
+            for (int j = 0; j < kGenoBatch; ++j) {
+                const uint32_t n = cnt[j];
+                if (n) {
+                    const int k = k0 + j;
+                    st[g].ad += n;
+                    st[g].es += (double)n * ed_tab[k];
+                    st[g].pe = xf_mul(st[g].pe, xf_pow_tab(pow_tab + (size_t)(2 * k) * kGenoPowBits, n));
+                    st[g].p1 = xf_mul(st[g].p1, xf_pow_tab(pow_tab + (size_t)(2 * k + 1) * kGenoPowBits, n));
+                }
             }
         }
     }

@@ -66,7 +66,8 @@ struct lvc_handle {
     uint32_t* d_out_depth = nullptr;
     uint32_t* d_out_ad = nullptr;
     double* d_out_lik = nullptr;
-    uint32_t* d_cand_count = nullptr;
+    uint32_t* d_cand_count = nullptr;           // [2]: the genotype kernel counts in one and clears the other for the next call
+    int cand_slot = 0;
     uint32_t cand_cap = 0;
     uint32_t last_cand_count = 0;
     int64_t geno_p0 = 0, geno_p1 = -1;       // genotype position range (p1 < 0: whole contig)
@@ -214,8 +215,8 @@ int lvc_create(lvc_handle** out, int device, int64_t ref_len, const uint8_t* ref
         CU(cudaMalloc(&h->d_out_depth, G * sizeof(uint32_t)));
         CU(cudaMalloc(&h->d_out_ad, G * 4 * sizeof(uint32_t)));
         CU(cudaMalloc(&h->d_out_lik, G * 4 * sizeof(double)));
-        CU(cudaMalloc(&h->d_cand_count, sizeof(uint32_t)));
-        CU(cudaMemsetAsync(h->d_cand_count, 0, sizeof(uint32_t), h->stream));
+        CU(cudaMalloc(&h->d_cand_count, 2 * sizeof(uint32_t)));
+        CU(cudaMemsetAsync(h->d_cand_count, 0, 2 * sizeof(uint32_t), h->stream));
         CU(cudaFuncSetAttribute(k_deposit_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
         CU(cudaFuncSetAttribute(k_deposit_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
         CU(cudaFuncSetAttribute(k_deposit_tile4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTile4SmemBytes));
@@ -672,7 +673,6 @@ static int genotype_enqueue(lvc_handle* h, int64_t min_total_depth, int64_t min_
                                                                h->d_elut + 256, (XF*)h->g_pow.p, (double*)h->g_ed.p);
         h->launches++;
     }
-    CU(cudaMemsetAsync(h->d_cand_count, 0, sizeof(uint32_t), h->stream));
     GenoParams gp;
     gp.G = h->G; gp.p0 = h->geno_p0; gp.p1 = h->geno_p1 < 0 ? h->G : h->geno_p1; gp.min_total_depth = min_total_depth; gp.min_allele_depth = min_allele_depth;
     gp.min_ratio = min_ratio; gp.flags = flags; gp.n_planes = np; gp.cand_cap = h->cand_cap;
@@ -681,12 +681,23 @@ static int genotype_enqueue(lvc_handle* h, int64_t min_total_depth, int64_t min_
     const unsigned blocks = (unsigned)((gp.p1 - gp.p0 + (threads / 4) - 1) / (threads / 4));
     if (gp.p1 <= gp.p0) { h->last_cand_count = 0; h->geno_pending = false; return LVC_OK; }
     {
+        // Launched with programmatic stream serialization: its blocks may become resident while the deposit kernel
+        // drains (that kernel signals launch_dependents at its start); k_genotype waits for the deposit kernel's
+        // completion (griddepcontrol.wait) before it reads a table.  No memset sits between the two launches: the
+        // candidate counter alternates between two words, each call clearing the other one.
         KernelTimer t(h, 2);
-        k_genotype<<<blocks, threads, 0, h->stream>>>(gp, (const uint32_t* const*)h->g_order_ptrs.p,
-                                                     (const XF*)h->g_pow.p, (const double*)h->g_ed.p,
-                                                     h->d_dels, h->d_ref, (const uint32_t* const*)h->d_first_arr,
-                                                        h->d_out_depth, h->d_out_ad, h->d_out_lik,
-                                                        (lvc_candidate*)h->g_cand.p, h->d_cand_count);
+        h->cand_slot ^= 1;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = 0; cfg.stream = h->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        CU(cudaLaunchKernelEx(&cfg, k_genotype, gp, (const uint32_t* const*)h->g_order_ptrs.p, (const XF*)h->g_pow.p,
+                              (const double*)h->g_ed.p, (const uint32_t*)h->d_dels, (const uint8_t*)h->d_ref,
+                              (const uint32_t* const*)h->d_first_arr, h->d_out_depth, h->d_out_ad, h->d_out_lik,
+                              (lvc_candidate*)h->g_cand.p, h->d_cand_count + h->cand_slot,
+                              h->d_cand_count + (h->cand_slot ^ 1)));
     }
     h->launches++;
     CU(cudaGetLastError());
@@ -695,7 +706,7 @@ static int genotype_enqueue(lvc_handle* h, int64_t min_total_depth, int64_t min_
 }
 
 static int genotype_read_count(lvc_handle* h) {
-    CU(cudaMemcpyAsync(h->h_status, h->d_cand_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(h->h_status, h->d_cand_count + h->cand_slot, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     h->last_cand_count = h->h_status[0];
     h->geno_pending = false;
