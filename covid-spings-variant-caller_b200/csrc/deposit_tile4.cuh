@@ -133,6 +133,9 @@ k_deposit_tile4(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
     hdr_load2(b, hd, dp.min_mq);       // CIGAR ops, only for reads that pass the read-level filter
     // a chunk in which no read passes the read-level filter (everything dropped by the depth cap) ends here
     if (!__syncthreads_or(read_passes_filter(hd.flag, hd.mapq, hd.keep, dp.min_mq))) return;
+    // Up to here only the batch was read.  The tables may still be in use by the previous kernel of the stream (this
+    // kernel is launched with programmatic stream serialization): wait for it before the first table access.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     // byte extent of the reads that pass the read-level filter (a superset of what will be deposited):
     // known before the CIGARs arrive, so the bulk copy overlaps classification
     const uint32_t so_rel = hd.so - (uint32_t)so0, so1_rel = hd.so1 - (uint32_t)so0;

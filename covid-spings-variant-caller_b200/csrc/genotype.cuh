@@ -142,6 +142,7 @@ __global__ void __launch_bounds__(kGenoThreads) k_genotype(GenoParams gp, const 
     const int tid = threadIdx.x;
     // everything below reads tables written by the deposit kernel launched before this one
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;");        // the next deposit kernel may start reading its batch
     if (blockIdx.x == 0 && tid == 0) *cand_count_next = 0;
     const int slot = tid & 3;
     const int64_t p = gp.p0 + (int64_t)blockIdx.x * (kGenoThreads / 4) + (tid >> 2);

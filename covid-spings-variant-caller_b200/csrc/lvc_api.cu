@@ -385,10 +385,17 @@ static int launch_deposit(lvc_handle* h, const BatchView& bv, int replay) {
         tp.prim_plane = h->lut[h->qprim];
         { KernelTimer t(h, 0);
           if (impl == 4) {
-              if (h->min_bq <= 0)
-                  k_deposit_tile4<true><<<tp.grid, kTileThreads, kTile4SmemBytes, h->stream>>>(bv, tv, dp, tp);
-              else
-                  k_deposit_tile4<false><<<tp.grid, kTileThreads, kTile4SmemBytes, h->stream>>>(bv, tv, dp, tp);
+              // programmatic stream serialization: the chunk headers are read (and dead chunks retire) while the
+              // previous kernel of the stream drains; the kernel waits for it before its first table access
+              cudaLaunchConfig_t cfg = {};
+              cfg.gridDim = dim3(tp.grid); cfg.blockDim = dim3(kTileThreads); cfg.dynamicSmemBytes = kTile4SmemBytes;
+              cfg.stream = h->stream;
+              cudaLaunchAttribute at[1];
+              at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+              at[0].val.programmaticStreamSerializationAllowed = 1;
+              cfg.attrs = at; cfg.numAttrs = 1;
+              if (h->min_bq <= 0) CU(cudaLaunchKernelEx(&cfg, k_deposit_tile4<true>, bv, tv, dp, tp));
+              else CU(cudaLaunchKernelEx(&cfg, k_deposit_tile4<false>, bv, tv, dp, tp));
           } else if (h->min_bq <= 0)
               k_deposit_tile<true><<<tp.grid, kTileThreads, kTileSmemBytes, h->stream>>>(bv, tv, dp, tp);
           else
