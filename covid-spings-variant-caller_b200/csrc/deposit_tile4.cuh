@@ -170,7 +170,7 @@ k_deposit_tile4(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
         int32_t run_pos[kMaxRunsPerRead] = {0, 0, 0};
         uint32_t run_len[kMaxRunsPerRead] = {0, 0, 0}, run_q[kMaxRunsPerRead] = {0, 0, 0};
         int32_t del_pos[kMaxDelsPerRead] = {0, 0};
-        uint32_t del_len[kMaxDelsPerRead] = {0, 0};
+        uint32_t del_len[kMaxDelsPerRead] = {0, 0}, del_q[kMaxDelsPerRead] = {0, 0};
         uint32_t nr = 0, nd = 0, rspan = 0;
         bool defer = false;
         const uint32_t i = chunk0 + tid;
@@ -217,14 +217,15 @@ k_deposit_tile4(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
                         prev_match = false;
                         if (op == 2 || op == 3) {
                             any_ref = true;
-                            // kept iff the NEXT query base passes the quality rule (0 if past the end)
-                            const uint32_t q = qi < lq ? (uint32_t)b.qual[b.seq_off[i] + qi] : 0u;
-                            if ((int)q >= dp.min_bq) {
-                                if (nd == (uint32_t)kMaxDelsPerRead) tileable = false;
-                                else {
-                                    if (nd == 0) { del_pos[0] = r; del_len[0] = l; } else { del_pos[1] = r; del_len[1] = l; }
-                                    ++nd;
-                                }
+                            // kept iff the NEXT query base passes the quality rule (0 if past the end).  The quality
+                            // is only requested here; it is tested where the entries are deposited, after the barrier,
+                            // so its latency does not hold up the chunk
+                            if (nd == (uint32_t)kMaxDelsPerRead) tileable = false;
+                            else {
+                                const uint32_t q = qi < lq ? (uint32_t)b.qual[so0 + so_rel + qi] : 0u;
+                                if (nd == 0) { del_pos[0] = r; del_len[0] = l; del_q[0] = q; }
+                                else { del_pos[1] = r; del_len[1] = l; del_q[1] = q; }
+                                ++nd;
                             }
                             r += (int32_t)l;
                         } else if (op == 1 || op == 4) qi += l;
@@ -296,7 +297,7 @@ k_deposit_tile4(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
             if (active && lane == __ffs(me) - 1) atomicAdd(&tv.covdiff[hd.pos + rspan], -(int32_t)__popc(me));
 #pragma unroll
             for (int k = 0; k < kMaxDelsPerRead; ++k)
-                if ((uint32_t)k < nd)
+                if ((uint32_t)k < nd && (int)del_q[k] >= dp.min_bq)
                     for (uint32_t j = 0; j < del_len[k]; ++j) atomicAdd(&tv.dels[del_pos[k] + j], 1u);
         }
         if (n_runs) {
@@ -349,6 +350,40 @@ k_deposit_tile4(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
                     __syncthreads();
                     cmax = (int32_t)s_misc[4];
                 }
+                // Task table of one column window: per 32-column slab the candidate run range (binary search over the
+                // sorted read start of each run) and the exclusive scan of the task counts.  One warp does it.  For the
+                // first column window that happens while the warp's first payload loads are in flight.
+                auto slab_setup = [&](int32_t wc0) {
+                    const int nslab = min(kMaxSlabs, (cmax - wc0 + kSlabCols - 1) / kSlabCols);
+                    uint32_t cnt = 0, first_run = 0;
+                    if (lane < nslab) {
+                        const int32_t s_lo = wc0 + lane * kSlabCols, s_hi = s_lo + kSlabCols;
+                        uint32_t lo = a0, hi = a1;               // first run whose read starts at or after s_hi
+                        while (lo < hi) {
+                            const uint32_t m = (lo + hi) >> 1;
+                            if (s_pos[m] - (int32_t)s_rd[m] < s_hi) lo = m + 1; else hi = m;
+                        }
+                        const uint32_t bnd = lo;
+                        const int64_t thr = (int64_t)s_lo - (int64_t)maxspan;   // first run whose read starts after thr
+                        lo = a0; hi = bnd;
+                        while (lo < hi) {
+                            const uint32_t m = (lo + hi) >> 1;
+                            if ((int64_t)(s_pos[m] - (int32_t)s_rd[m]) <= thr) lo = m + 1; else hi = m;
+                        }
+                        first_run = lo;
+                        cnt = bnd - lo;
+                    }
+                    const uint32_t groups = (cnt + kTaskRuns - 1) / kTaskRuns;
+                    uint32_t incl = groups;
+#pragma unroll
+                    for (int d = 1; d < kMaxSlabs; d <<= 1) {
+                        const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                        if (lane >= d) incl += up;
+                    }
+                    if (lane < nslab) { s_slab_a[lane] = first_run; s_slab_n[lane] = cnt; s_slab_pre[lane] = incl - groups; }
+                    if (lane == nslab - 1) s_slab_pre[nslab] = incl;
+                    if (lane == 0) s_misc[2] = 0;
+                };
                 // ---- stage this window as KEYS: coalesced 16-byte loads, 16 bases per step, written in place once
                 if (a1 > a0) {
                     const uint64_t qend_all = so0 + max_rel;
@@ -408,6 +443,7 @@ k_deposit_tile4(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
                     uint2 sA = make_uint2(0, 0), sB = make_uint2(0, 0);
                     if (g < n_grp) { qA = gq[g]; sA = gs[g]; }
                     if (g + kTileThreads < n_grp) { qB = gq[g + kTileThreads]; sB = gs[g + kTileThreads]; }
+                    if (warp == 0 && cmin < cmax) slab_setup(cmin);
                     while (g < n_grp) {
                         const uint32_t gn = g + 2 * kTileThreads;
                         uint4 nqA = make_uint4(0, 0, 0, 0), nqB = make_uint4(0, 0, 0, 0);
@@ -424,43 +460,12 @@ k_deposit_tile4(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
                 // ---- column windows of kTabCols (one for amplicon / deep shotgun chunks)
                 for (int32_t wc0 = cmin; wc0 < cmax; wc0 += kTabCols) {
                     const int nslab = min(kMaxSlabs, (cmax - wc0 + kSlabCols - 1) / kSlabCols);
-                    // per-slab candidate run range by binary search over the (sorted) read start of each run;
-                    // warp 0 does the searches and the exclusive scan of the task counts
-                    if (warp == 0) {
-                        uint32_t cnt = 0, first_run = 0;
-                        if (lane < nslab) {
-                            const int32_t s_lo = wc0 + lane * kSlabCols, s_hi = s_lo + kSlabCols;
-                            uint32_t lo = a0, hi = a1;               // first run whose read starts at or after s_hi
-                            while (lo < hi) {
-                                const uint32_t m = (lo + hi) >> 1;
-                                if (s_pos[m] - (int32_t)s_rd[m] < s_hi) lo = m + 1; else hi = m;
-                            }
-                            const uint32_t bnd = lo;
-                            const int64_t thr = (int64_t)s_lo - (int64_t)maxspan;   // first run whose read starts after thr
-                            lo = a0; hi = bnd;
-                            while (lo < hi) {
-                                const uint32_t m = (lo + hi) >> 1;
-                                if ((int64_t)(s_pos[m] - (int32_t)s_rd[m]) <= thr) lo = m + 1; else hi = m;
-                            }
-                            first_run = lo;
-                            cnt = bnd - lo;
-                        }
-                        const uint32_t groups = (cnt + kTaskRuns - 1) / kTaskRuns;
-                        uint32_t incl = groups;
-#pragma unroll
-                        for (int d = 1; d < kMaxSlabs; d <<= 1) {
-                            const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-                            if (lane >= d) incl += up;
-                        }
-                        if (lane < nslab) { s_slab_a[lane] = first_run; s_slab_n[lane] = cnt; s_slab_pre[lane] = incl - groups; }
-                        if (lane == nslab - 1) s_slab_pre[nslab] = incl;
-                        if (lane == 0) s_misc[2] = 0;
-                    }
+                    if (warp == 0 && wc0 != cmin) slab_setup(wc0);
                     __syncthreads();                                       // barrier C
                     const uint32_t n_tasks = s_slab_pre[nslab];
 
-                    // ---- tasks: (slab, group of 64 runs); lane = 16 columns of one run per unit (2 lanes per run,
-                    //      16 runs per pass, 4 passes): per-task overhead is paid once per 2048 bases
+                    // ---- tasks: (slab, group of kTaskRuns runs); lane = 16 columns of one run per unit (2 lanes per run,
+                    //      16 runs per pass): the per-task overhead is paid once per 4096 bases
                     const int w2 = lane & 1, sread = lane >> 1;
                     for (;;) {
                         uint32_t t = 0;
