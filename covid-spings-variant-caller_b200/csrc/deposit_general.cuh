@@ -27,8 +27,8 @@ __device__ __forceinline__ void deposit_base(const TableView& tv, const DepositP
     }
     const int64_t cell = r * 4 + (gs & 3u);
     atomicAdd(&tv.planes[pl][cell], 1u);
-    uint32_t* f = tv.first[gs >> 2];
-    if (f[cell] > ord) atomicMin(&f[cell], ord);
+    // first-seen ordinal: an unconditional reduction (fire and forget) instead of a load the warp would wait for
+    atomicMin(&tv.first[gs >> 2][cell], ord);
 }
 
 // Walk one read (one thread).
@@ -85,22 +85,30 @@ __device__ __forceinline__ void deposit_read_general(const BatchView& b, const T
     }
 }
 
-// The same walk with one WARP per read: the lanes stride over the bases of each match op (coalesced loads,
-// 32 reductions in flight) while the CIGAR walk itself is warp-uniform.  Used by the tiled kernel for the
-// reads it cannot take.
-__device__ __noinline__ void deposit_read_warp(const BatchView& b, const TableView& tv, const DepositParams& dp,
-                                               uint32_t i, uint32_t lane) {
+// The same walk with one WARP per read.  The CIGAR is read cooperatively: lane k holds op k of a group of 32 ops, the
+// reference / query offsets of every op come from a warp scan, and the ops that deposit something (match runs,
+// deletions, skips) are visited by broadcasting them from their lane -- no dependent global load per op.  Inside a
+// match run the lanes stride over the bases (coalesced loads, 32 reductions in flight).
+__device__ __forceinline__ void deposit_read_warp_impl(const BatchView& b, const TableView& tv, const DepositParams& dp,
+                                                       uint32_t i, uint32_t lane) {
     if (!read_passes_filter(b.flag[i], b.mapq[i], b.keep[i], dp.min_mq)) return;
     const uint32_t c0 = b.cigar_off[i], c1 = b.cigar_off[i + 1];
+    const int64_t pos = b.pos[i];
+    const uint64_t qb = b.seq_off[i];
+    // totals: reference length and l_qseq
     int64_t rlen = 0;
     uint32_t lq = 0;
-    for (uint32_t k = c0; k < c1; ++k) {
-        const uint32_t c = b.cigar[k], op = c & 15u, len = c >> 4;
-        if (op_consumes_ref(op)) rlen += len;
-        if (op_consumes_query(op)) lq += len;
+    uint32_t cg_first = 0;                                   // the first group's ops stay in registers
+    for (uint32_t g0 = c0; g0 < c1; g0 += 32) {
+        const uint32_t c = g0 + lane < c1 ? b.cigar[g0 + lane] : 0u;    // padding: a match of length 0
+        if (g0 == c0) cg_first = c;
+        const uint32_t op = c & 15u, len = c >> 4;
+        const uint32_t rl = op_consumes_ref(op) ? len : 0u, ql = op_consumes_query(op) ? len : 0u;
+        // per-op lengths are < 2^28: 32 of them fit 64 bits exactly; sum in two halves to stay in 32-bit reductions
+        rlen += (int64_t)__reduce_add_sync(0xFFFFFFFFu, rl & 0xFFFFu) + ((int64_t)__reduce_add_sync(0xFFFFFFFFu, rl >> 16) << 16);
+        lq += __reduce_add_sync(0xFFFFFFFFu, ql);
     }
-    if (rlen == 0) return;
-    const int64_t pos = b.pos[i];
+    if (rlen == 0) return;   // no M/D/N/=/X op: htslib asserts on such records; skipped
     if (pos < 0 || pos + rlen > tv.G) {
         if (lane == 0) atomicAdd(&tv.status[ST_RANGE_ERR], 1u);
         return;
@@ -109,38 +117,86 @@ __device__ __noinline__ void deposit_read_warp(const BatchView& b, const TableVi
         atomicAdd(&tv.covdiff[pos], 1);
         atomicAdd(&tv.covdiff[pos + rlen], -1);
     }
-    const uint64_t qb = b.seq_off[i];
     const uint8_t* qual = b.qual + qb;
     const uint8_t* seq = b.seq4 + (qb >> 1);
+    // request the read's whole payload now (one line per lane): the per-run loads below then hit L1 instead of
+    // paying a DRAM latency per run
+    for (uint32_t off = lane * 128u; off < lq; off += 32u * 128u) {
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(qual + off));
+        if (off < (lq + 1) / 2) asm volatile("prefetch.global.L1 [%0];" ::"l"(seq + off));
+    }
     const uint32_t ord = dp.ord_base + i;
-    int64_t r = pos;
-    uint32_t qi = 0;
-    for (uint32_t k = c0; k < c1; ++k) {
-        const uint32_t c = b.cigar[k], op = c & 15u, len = c >> 4;
-        if (op_is_match(op)) {
-            for (uint32_t j = lane; j < len; j += 32) {
-                const uint32_t q = qual[qi + j];
-                if ((int)q < dp.min_bq) continue;
-                const uint32_t byte = seq[(qi + j) >> 1];
-                const uint32_t nib = ((qi + j) & 1u) ? (byte & 15u) : (byte >> 4);
-                deposit_base(tv, dp, r + j, nib, q, ord);
-            }
-            qi += len; r += len;
-        } else if (op == 2 || op == 3) {
-            const uint32_t q = (qi < lq) ? (uint32_t)qual[qi] : 0u;
-            if (!dp.replay && (int)q >= dp.min_bq)
-                for (uint32_t j = lane; j < len; j += 32) atomicAdd(&tv.dels[r + j], 1u);
-            r += len;
-        } else if (op == 1 || op == 4) {
-            qi += len;
+    int64_t r_base = pos;
+    uint32_t q_base = 0;
+    for (uint32_t g0 = c0; g0 < c1; g0 += 32) {
+        const uint32_t c = g0 == c0 ? cg_first : (g0 + lane < c1 ? b.cigar[g0 + lane] : 0u);
+        const uint32_t op = c & 15u, len = c >> 4;
+        const uint32_t rl = op_consumes_ref(op) ? len : 0u, ql = op_consumes_query(op) ? len : 0u;
+        // exclusive prefix of the reference / query lengths inside the group (ref offsets in 64 bits)
+        uint64_t r_in = rl;
+        uint32_t q_in = ql;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint64_t ur = __shfl_up_sync(0xFFFFFFFFu, r_in, d);
+            const uint32_t uq = __shfl_up_sync(0xFFFFFFFFu, q_in, d);
+            if ((int)lane >= d) { r_in += ur; q_in += uq; }
         }
+        const uint64_t r_off = r_in - rl;
+        const uint32_t q_off = q_in - ql;
+        // ops with something to deposit
+        uint32_t work = __ballot_sync(0xFFFFFFFFu, len != 0 && (op_is_match(op) || op == 2 || op == 3));
+        while (work) {
+            const int k = __ffs(work) - 1;
+            work &= work - 1;
+            const uint32_t ck = __shfl_sync(0xFFFFFFFFu, c, k);
+            const int64_t r = r_base + (int64_t)__shfl_sync(0xFFFFFFFFu, r_off, k);
+            const uint32_t qi = q_base + __shfl_sync(0xFFFFFFFFu, q_off, k);
+            const uint32_t opk = ck & 15u, lenk = ck >> 4;
+            if (op_is_match(opk)) {
+                for (uint32_t j = lane; j < lenk; j += 32) {
+                    const uint32_t q = qual[qi + j];
+                    if ((int)q < dp.min_bq) continue;
+                    const uint32_t byte = seq[(qi + j) >> 1];
+                    const uint32_t nib = ((qi + j) & 1u) ? (byte & 15u) : (byte >> 4);
+                    deposit_base(tv, dp, r + j, nib, q, ord);
+                }
+            } else if (!dp.replay) {
+                // deletion / ref-skip entries are kept iff the NEXT query base passes the quality rule
+                // (pysam pileup_base_qual_skip on qpos = y; 0 if qpos >= l_qseq) -- SURVEY B3
+                const uint32_t q = (qi < lq) ? (uint32_t)qual[qi] : 0u;
+                if ((int)q >= dp.min_bq)
+                    for (uint32_t j = lane; j < lenk; j += 32) atomicAdd(&tv.dels[r + j], 1u);
+            }
+        }
+        r_base += (int64_t)__shfl_sync(0xFFFFFFFFu, r_in, 31);
+        q_base += __shfl_sync(0xFFFFFFFFu, q_in, 31);
     }
 }
 
+// out of line: what the tiled kernels call for the few reads they hand over
+__device__ __noinline__ void deposit_read_warp(const BatchView& b, const TableView& tv, const DepositParams& dp,
+                                               uint32_t i, uint32_t lane) {
+    deposit_read_warp_impl(b, tv, dp, i, lane);
+}
+
 // one thread per read of the batch
-__global__ void __launch_bounds__(128) k_deposit_general(BatchView b, TableView tv, DepositParams dp, uint32_t n) {
+__global__ void __launch_bounds__(128) k_deposit_general(const __grid_constant__ BatchView b,
+                                                         const __grid_constant__ TableView tv,
+                                                         const __grid_constant__ DepositParams dp, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) deposit_read_general(b, tv, dp, i);
+}
+
+// one WARP per read of the batch: long reads with many CIGAR ops and a wide quality alphabet (ONT), where neither a
+// primary quality nor a short run table exists.  Every read of the batch is in flight at once.
+constexpr int kWarpKernelThreads = 256;
+__global__ void __launch_bounds__(kWarpKernelThreads) k_deposit_warp(const __grid_constant__ BatchView b,
+                                                                     const __grid_constant__ TableView tv,
+                                                                     const __grid_constant__ DepositParams dp, uint32_t n) {
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");     // the tables may still be read by the previous kernel
+    const uint32_t i = blockIdx.x * (kWarpKernelThreads / 32) + (threadIdx.x >> 5);
+    if (i < n) deposit_read_warp_impl(b, tv, dp, i, threadIdx.x & 31u);
 }
 
 }  // namespace lvc

@@ -173,7 +173,6 @@ k_deposit_tile4(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
         uint32_t del_len[kMaxDelsPerRead] = {0, 0}, del_q[kMaxDelsPerRead] = {0, 0};
         uint32_t nr = 0, nd = 0, rspan = 0;
         bool defer = false;
-        const uint32_t i = chunk0 + tid;
         const bool rpass = read_passes_filter(hd.flag, hd.mapq, hd.keep, dp.min_mq);
         // warp-uniform shortcut: every read of the warp that passes the filter is one match op (150M): no CIGAR walk
         const uint32_t l0 = hd.cg0 >> 4;

@@ -5,62 +5,58 @@
 // (done on the host with the host libm).
 //
 // The reference multiplies per-read error probabilities sequentially in fp64 and lets the product
-// underflow to exactly 0.0.  Here each allele's products are evaluated from the integer quality
-// histogram as  prod_q e[q]^n  by square-and-multiply in an extended-range representation
-// (mantissa in [0.5,1) + 64-bit binary exponent), so nothing underflows early; the final value is
-// rounded to fp64 ONCE (ldexp), giving 0.0 exactly where the true product is below 2^-1075 and a
-// correctly rounded denormal inside the denormal band (where the reference itself is order
-// dependent).  e[q] / 1-e[q] come from the host (math.pow) -- never pow() on the device.
+// underflow to exactly 0.0.  Here every product  prod_q e[q]^n[q]  is evaluated from the integer quality
+// histogram in the log2 domain with double-double arithmetic:  S = sum_q n[q] * log2(e[q]),  the logarithms
+// being double-double constants computed on the host in 80-bit arithmetic from the SAME e[q] / 1-e[q] doubles
+// the reference uses (math.pow; never pow() on the device).  S carries ~100 bits, so 2^S is good to ~1e-15
+// relative whatever the depth; it is split into an integer exponent and a fraction in [0,1), and the result
+// is rounded to fp64 ONCE (ldexp): exactly 0.0 where the true product is below 2^-1075, a correctly rounded
+// denormal inside the denormal band (where the reference itself is order dependent).  One fused
+// multiply-add chain per (plane, allele): no data-dependent loop, no divergence.
 #pragma once
 #include "lvc_common.cuh"
 
 namespace lvc {
 
-struct XF {            // value = m * 2^x ; m == 0 means exactly zero
-    double m;
-    long long x;
+struct DD {            // value = h + l, |l| <= ulp(h)/2
+    double h, l;
 };
 
-__device__ __forceinline__ XF xf_one() { return XF{0.5, 1}; }
+__device__ __forceinline__ DD dd_zero() { return DD{0.0, 0.0}; }
 
-__device__ __forceinline__ XF xf_from_double(double v) {
-    if (v == 0.0) return XF{0.0, 0};
-    int e;
-    double m = frexp(v, &e);
-    return XF{m, (long long)e};
+// s += n * (ch + cl)        (n < 2^32 exactly representable)
+__device__ __forceinline__ void dd_fma_acc(DD& s, double n, double ch, double cl) {
+    const double p = n * ch;
+    const double pe = fma(n, ch, -p) + n * cl;            // exact error of the product + the low part
+    const double t = s.h + p;
+    const double bp = t - s.h;
+    const double se = (s.h - (t - bp)) + (p - bp);         // exact error of the sum
+    s.h = t;
+    s.l += se + pe;
 }
 
-__device__ __forceinline__ XF xf_mul(XF a, XF b) {
-    XF r;
-    r.m = a.m * b.m;            // in [0.25, 1) or 0
-    r.x = a.x + b.x;
-    if (r.m < 0.5 && r.m != 0.0) { r.m *= 2.0; r.x -= 1; }
-    return r;
+__device__ __forceinline__ DD dd_add(DD a, DD b) {
+    const double t = a.h + b.h;
+    const double bp = t - a.h;
+    const double se = (a.h - (t - bp)) + (b.h - bp);
+    const double lo = se + a.l + b.l;
+    const double h = t + lo;
+    return DD{h, lo - (h - t)};
 }
 
-__device__ __forceinline__ XF xf_div(XF a, XF b) {   // b.m != 0
-    XF r;
-    r.m = a.m / b.m;            // in (0.5, 2)
-    r.x = a.x - b.x;
-    if (r.m >= 1.0) { r.m *= 0.5; r.x += 1; }
-    return r;
+__device__ __forceinline__ DD dd_sub(DD a, DD b) { return dd_add(a, DD{-b.h, -b.l}); }
+
+__device__ __forceinline__ DD dd_shfl_xor(DD v, int lanemask) {
+    return DD{__shfl_xor_sync(0xFFFFFFFFu, v.h, lanemask), __shfl_xor_sync(0xFFFFFFFFu, v.l, lanemask)};
 }
 
-__device__ __forceinline__ XF xf_pow(XF b, uint32_t n) {
-    XF r = xf_one();
-    while (n) {
-        if (n & 1u) r = xf_mul(r, b);
-        n >>= 1;
-        if (n) b = xf_mul(b, b);
-    }
-    return r;
-}
-
-__device__ __forceinline__ double xf_to_double(XF a) {
-    if (a.m == 0.0) return 0.0;
-    if (a.x < -1200) return 0.0;
-    if (a.x > 1100) return a.m * 8.98846567431158e307 * 4.0;   // +inf (cannot happen: all factors <= 1)
-    return ldexp(a.m, (int)a.x);                                // single rounding, gradual underflow
+// 2^(h + l) rounded once to fp64 (gradual underflow; 0.0 below the denormal range)
+__device__ __forceinline__ double dd_exp2(DD s) {
+    const double t = s.h + s.l;
+    if (!(t > -1200.0)) return 0.0;
+    const double i = floor(s.h);
+    const double f = (s.h - i) + s.l;                      // in [0, 1] up to the low part
+    return ldexp(exp2(f), (int)i);
 }
 
 struct GenoParams {
@@ -75,63 +71,28 @@ struct GenoParams {
     uint32_t cand_cap;
 };
 
-constexpr int kGenoThreads = 128;            // 32 positions x 4 allele slots
+constexpr int kGenoThreads = 128;            // 32 positions x 4 allele slots (LPP = 1)
 constexpr int kGenoBatch = 8;                // plane counts requested together
-constexpr int kGenoPowBits = 32;
-
-// Power tables, built once per (plane set, phred table) and cached on the device: for every plane the 32
-// repeated squarings e^(2^k) and (1-e)^(2^k) in extended range.  Layout: [plane][e | 1-e][32].
-__global__ void k_pow_tables(int n_planes, const uint16_t* __restrict__ plane_keys, const double* __restrict__ e_lut,
-                             const double* __restrict__ om_lut, XF* __restrict__ pow_tab, double* __restrict__ ed) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= 2 * n_planes) return;
-    const int k = t >> 1;
-    const bool is_om = t & 1;
-    const uint32_t q = plane_keys[k] & 255u;
-    XF v = xf_from_double(is_om ? om_lut[q] : e_lut[q]);
-    XF* dst = pow_tab + (size_t)t * kGenoPowBits;
-    for (int i = 0; i < kGenoPowBits; ++i) { dst[i] = v; v = xf_mul(v, v); }
-    if (!is_om) ed[k] = e_lut[q];
-}
 
 struct AlleleStat {
-    XF pe;       // prod e
-    XF p1;       // prod (1-e)
+    DD pe;       // log2 prod e
+    DD p1;       // log2 prod (1-e)
     double es;   // sum e
     uint32_t ad;
 };
 
-__device__ __forceinline__ XF xf_shfl_xor(XF v, int lanemask) {
-    XF r;
-    r.m = __shfl_xor_sync(0xFFFFFFFFu, v.m, lanemask);
-    r.x = __shfl_xor_sync(0xFFFFFFFFu, v.x, lanemask);
-    return r;
-}
+// per-plane constants, built on the host: log2(e), log2(1-e) as double-doubles and e itself
+struct PlaneConst {
+    double le_h, le_l, lo_h, lo_l, e;
+};
 
-// x^n from the table of x^(2^k): one multiply per set bit of n.  The table entries are normalised
-// (mantissa in [0.5, 1)), so a chain of <= 32 products stays far inside the normal fp64 range: the mantissas are
-// multiplied as they are and the product is re-normalised ONCE (scaling by a power of two is exact, so the bits
-// equal those of a chain normalised after every step).
-__device__ __forceinline__ XF xf_pow_tab(const XF* __restrict__ tab, uint32_t n) {
-    double m = 1.0;
-    long long x = 0;
-    while (n) {
-        const int k = __ffs(n) - 1;
-        n &= n - 1;
-        const XF t = tab[k];
-        m *= t.m;
-        x += t.x;
-    }
-    int e;
-    m = frexp(m, &e);
-    return XF{m, x + e};
-}
-
-// One thread per (position, allele slot); the 4 slots of a position sit in 4 adjacent lanes and are
-// combined with shuffles.  Alleles of the rare groups 1..3 are handled by the same lanes in turn.
+// LPP lanes per (position, allele slot); the 4 slots of a position sit in 4 adjacent lanes and are combined with
+// shuffles.  With LPP > 1 (wide quality alphabets: ONT) lane `sub` of a slot takes the planes k = sub (mod LPP) and the
+// partial products are multiplied together by a shuffle tree first.  Alleles of the rare groups 1..3 are handled by
+// the same lanes in turn.
+template <int LPP>
 __global__ void __launch_bounds__(kGenoThreads) k_genotype(GenoParams gp, const uint32_t* const* __restrict__ plane_ptrs,
-                                                           const XF* __restrict__ pow_tab,
-                                                           const double* __restrict__ ed_tab,
+                                                           const PlaneConst* __restrict__ pconst,
                                                            const uint32_t* __restrict__ dels,
                                                            const uint8_t* __restrict__ ref,
                                                            const uint32_t* const* __restrict__ first,
@@ -145,47 +106,57 @@ __global__ void __launch_bounds__(kGenoThreads) k_genotype(GenoParams gp, const 
     asm volatile("griddepcontrol.launch_dependents;");        // the next deposit kernel may start reading its batch
     if (blockIdx.x == 0 && tid == 0) *cand_count_next = 0;
     const int slot = tid & 3;
-    const int64_t p = gp.p0 + (int64_t)blockIdx.x * (kGenoThreads / 4) + (tid >> 2);
+    const int sub = (tid >> 2) & (LPP - 1);
+    const int64_t p = gp.p0 + (int64_t)blockIdx.x * (kGenoThreads / (4 * LPP)) + (tid / (4 * LPP));
     const bool live = p < gp.p1;
     const int64_t pc = live ? p : gp.p1 - 1;         // clamp: every lane takes part in the shuffles
 
     AlleleStat st[4];
 #pragma unroll
-    for (int g = 0; g < 4; ++g) { st[g].pe = xf_one(); st[g].p1 = xf_one(); st[g].es = 0.0; st[g].ad = 0; }
+    for (int g = 0; g < 4; ++g) { st[g].pe = dd_zero(); st[g].p1 = dd_zero(); st[g].es = 0.0; st[g].ad = 0; }
 
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
         // counts of up to kGenoBatch planes are requested together (one memory latency per batch, not per plane)
-        for (int k0 = gp.grp_begin[g]; k0 < gp.grp_begin[g + 1]; k0 += kGenoBatch) {
+        for (int k0 = gp.grp_begin[g] + sub; k0 < gp.grp_begin[g + 1]; k0 += kGenoBatch * LPP) {
             uint32_t cnt[kGenoBatch];
 #pragma unroll
             for (int j = 0; j < kGenoBatch; ++j)
-                cnt[j] = k0 + j < gp.grp_begin[g + 1] ? __ldcg(&plane_ptrs[k0 + j][pc * 4 + slot]) : 0u;
+                cnt[j] = k0 + j * LPP < gp.grp_begin[g + 1] ? __ldcg(&plane_ptrs[k0 + j * LPP][pc * 4 + slot]) : 0u;
 #pragma unroll
             for (int j = 0; j < kGenoBatch; ++j) {
                 const uint32_t n = cnt[j];
                 if (n) {
-                    const int k = k0 + j;
+                    const PlaneConst pcn = pconst[k0 + j * LPP];
+                    const double nd = (double)n;
                     st[g].ad += n;
-                    st[g].es += (double)n * ed_tab[k];
-                    st[g].pe = xf_mul(st[g].pe, xf_pow_tab(pow_tab + (size_t)(2 * k) * kGenoPowBits, n));
-                    st[g].p1 = xf_mul(st[g].p1, xf_pow_tab(pow_tab + (size_t)(2 * k + 1) * kGenoPowBits, n));
+                    st[g].es += nd * pcn.e;
+                    dd_fma_acc(st[g].pe, nd, pcn.le_h, pcn.le_l);
+                    dd_fma_acc(st[g].p1, nd, pcn.lo_h, pcn.lo_l);
                 }
             }
         }
+        if (LPP > 1 && gp.grp_begin[g + 1] > gp.grp_begin[g]) {
+            // partial sums of the LPP lanes of this (position, slot): lanes differ in bits 2.. of the lane index
+#pragma unroll
+            for (int d = 4; d < 4 * LPP; d <<= 1) {
+                st[g].pe = dd_add(st[g].pe, dd_shfl_xor(st[g].pe, d));
+                st[g].p1 = dd_add(st[g].p1, dd_shfl_xor(st[g].p1, d));
+                st[g].es += __shfl_xor_sync(0xFFFFFFFFu, st[g].es, d);
+                st[g].ad += __shfl_xor_sync(0xFFFFFFFFu, st[g].ad, d);
+            }
+        }
     }
-    // ---- combine the (up to 16) alleles of the position
+    // ---- combine the (up to 16) alleles of the position: log2 of the product of e over ALL of them
     const bool has_other = gp.grp_begin[4] > gp.grp_begin[1];
-    XF own = st[0].ad ? st[0].pe : xf_one();                  // product of e over this lane's alleles
+    DD own = st[0].pe;
     uint32_t own_ad = st[0].ad;
     if (has_other) {
 #pragma unroll
-        for (int g = 1; g < 4; ++g) { if (st[g].ad) own = xf_mul(own, st[g].pe); own_ad += st[g].ad; }
+        for (int g = 1; g < 4; ++g) { own = dd_add(own, st[g].pe); own_ad += st[g].ad; }
     }
-    const XF v1 = xf_shfl_xor(own, 1);
-    const XF pair = xf_mul(own, v1);
-    const XF opp = xf_shfl_xor(pair, 2);
-    const XF others_lanes = xf_mul(v1, opp);                  // product over the other three lanes
+    DD tot = dd_add(own, dd_shfl_xor(own, 1));
+    tot = dd_add(tot, dd_shfl_xor(tot, 2));
     uint32_t dsum = own_ad + __shfl_xor_sync(0xFFFFFFFFu, own_ad, 1);
     dsum += __shfl_xor_sync(0xFFFFFFFFu, dsum, 2);
     const uint64_t depth = (uint64_t)dels[pc] + dsum;
@@ -196,20 +167,14 @@ __global__ void __launch_bounds__(kGenoThreads) k_genotype(GenoParams gp, const 
     for (int g = 0; g < 4; ++g) {
         L[g] = 0.0;
         if ((g == 0 || has_other) && st[g].ad) {
-            XF others = others_lanes;
-            if (has_other) {
-#pragma unroll
-                for (int h = 0; h < 4; ++h)
-                    if (h != g && st[h].ad) others = xf_mul(others, st[h].pe);
-            }
-            L[g] = xf_to_double(xf_mul(st[g].p1, others));
+            L[g] = dd_exp2(dd_add(st[g].p1, dd_sub(tot, st[g].pe)));
             Ssum += L[g];
         }
     }
     Ssum += __shfl_xor_sync(0xFFFFFFFFu, Ssum, 1);
     Ssum += __shfl_xor_sync(0xFFFFFFFFu, Ssum, 2);
     const double S = Ssum == 0.0 ? 1.0 : Ssum;                                   // live_variant_caller.py:146
-    if (!live) return;
+    if (!live || sub != 0) return;
     const uint32_t depth32 = (uint32_t)(depth > 0xFFFFFFFFull ? 0xFFFFFFFFull : depth);
     if (slot == 0) out_depth[p] = depth32;
     out_ad[p * 4 + slot] = st[0].ad;

@@ -61,7 +61,8 @@ struct lvc_handle {
     DevBuf b_pos, b_flag, b_mapq, b_keep, b_coff, b_cig, b_soff, b_seq, b_qual;
 
     // genotype
-    DevBuf g_order_ptrs, g_order_keys, g_cand, g_pow, g_ed;
+    DevBuf g_order_ptrs, g_order_keys, g_cand, g_pconst;
+    std::vector<PlaneConst> pconst_host;     // staging of the per-plane constants (kept alive for the async copy)
     double* d_elut = nullptr;                // [512] e, 1-e
     uint32_t* d_out_depth = nullptr;
     uint32_t* d_out_ad = nullptr;
@@ -249,7 +250,7 @@ void lvc_destroy(lvc_handle* h) {
     cudaFree(h->d_elut); cudaFree(h->d_out_depth); cudaFree(h->d_out_ad); cudaFree(h->d_out_lik);
     cudaFree(h->d_cand_count);
     for (DevBuf* b : {&h->b_pos, &h->b_flag, &h->b_mapq, &h->b_keep, &h->b_coff, &h->b_cig, &h->b_soff, &h->b_seq,
-                      &h->b_qual, &h->g_order_ptrs, &h->g_order_keys, &h->g_cand, &h->g_pow, &h->g_ed})
+                      &h->b_qual, &h->g_order_ptrs, &h->g_order_keys, &h->g_cand, &h->g_pconst})
         cudaFree(b->p);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -273,7 +274,7 @@ int lvc_sync(lvc_handle* h) {
 }
 
 int lvc_set_impl(lvc_handle* h, int impl) {
-    if (!h || impl < 0 || impl > 4 || impl == 3) return LVC_EINVAL;
+    if (!h || impl < 0 || impl > 4) return LVC_EINVAL;
     h->impl = impl;
     return LVC_OK;
 }
@@ -363,7 +364,7 @@ int lvc_admit(uint32_t n, const int32_t* pos, const uint16_t* flag, const uint8_
 // ------------------------------------------------------------------------------------------------
 // deposit
 // ------------------------------------------------------------------------------------------------
-static int launch_deposit(lvc_handle* h, const BatchView& bv, int replay) {
+static int launch_deposit(lvc_handle* h, const BatchView& bv, int replay, uint64_t n_cigar_ops) {
     TableView tv = table_view(h);
     DepositParams dp;
     dp.min_bq = h->min_bq;
@@ -373,9 +374,24 @@ static int launch_deposit(lvc_handle* h, const BatchView& bv, int replay) {
     dp.replay_keys = h->d_replay;
     const uint32_t n = bv.n_reads;
     if (n == 0) return LVC_OK;
-    const int impl = h->impl == 0 ? 4 : h->impl;
+    // auto: batches of long reads (many CIGAR ops per read: ONT) take the warp-per-read kernel, short-read batches
+    // the tiled kernel
+    const bool long_reads = n_cigar_ops > 4ull * n;
+    const int impl = h->impl == 0 ? (long_reads ? 3 : 4) : h->impl;
     // the tiled kernels' byte arithmetic assumes a primary quality and a threshold below 128
-    if (impl == 1 || replay || h->qprim >= 128 || h->min_bq > 128 || h->lut[h->qprim] == kNoPlane) {
+    const bool tile_ok = h->qprim < 128 && h->min_bq <= 128 && h->lut[h->qprim] != kNoPlane;
+    if (impl == 3 || ((replay || !tile_ok) && impl != 1 && long_reads)) {
+        { KernelTimer t(h, 1);
+          cudaLaunchConfig_t cfg = {};
+          const unsigned wpb = kWarpKernelThreads / 32;
+          cfg.gridDim = dim3((n + wpb - 1) / wpb); cfg.blockDim = dim3(kWarpKernelThreads); cfg.stream = h->stream;
+          cudaLaunchAttribute at[1];
+          at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+          at[0].val.programmaticStreamSerializationAllowed = 1;
+          cfg.attrs = at; cfg.numAttrs = 1;
+          CU(cudaLaunchKernelEx(&cfg, k_deposit_warp, bv, tv, dp, n)); }
+        h->launches++;
+    } else if (impl == 1 || replay || !tile_ok) {
         { KernelTimer t(h, 1);
           k_deposit_general<<<(n + 127) / 128, 128, 0, h->stream>>>(bv, tv, dp, n); }
         h->launches++;
@@ -406,11 +422,11 @@ static int launch_deposit(lvc_handle* h, const BatchView& bv, int replay) {
     return LVC_OK;
 }
 
-static int deposit_with_replay(lvc_handle* h, const BatchView& bv) {
+static int deposit_with_replay(lvc_handle* h, const BatchView& bv, uint64_t n_cigar_ops) {
     if ((uint64_t)h->ordinal + bv.n_reads >= 0xFFFFFFFFull)
         return fail(h, LVC_ERANGE, "first-seen ordinal space (2^32-1 reads per handle) exhausted");
     CU(cudaMemsetAsync(h->d_status, 0, ST_WORDS * sizeof(uint32_t), h->stream));
-    int rc = launch_deposit(h, bv, 0);
+    int rc = launch_deposit(h, bv, 0, n_cigar_ops);
     if (rc) return rc;
     CU(cudaMemcpyAsync(h->h_status, h->d_status, ST_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaMemcpyAsync(h->h_status + ST_WORDS, h->d_newkeys, 32 * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
@@ -430,7 +446,7 @@ static int deposit_with_replay(lvc_handle* h, const BatchView& bv) {
         CU(cudaMemcpyAsync(h->d_replay, h->d_newkeys, 32 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, h->stream));
         CU(cudaMemsetAsync(h->d_newkeys, 0, 32 * sizeof(uint32_t), h->stream));
         CU(cudaMemsetAsync(h->d_status, 0, ST_WORDS * sizeof(uint32_t), h->stream));
-        rc = launch_deposit(h, bv, 1);
+        rc = launch_deposit(h, bv, 1, n_cigar_ops);
         if (rc) return rc;
         CU(cudaStreamSynchronize(h->stream));
     }
@@ -555,7 +571,7 @@ int lvc_push_batch(lvc_handle* h, const lvc_batch* b) {
     bv.cigar_off = (const uint32_t*)h->b_coff.p; bv.cigar = (const uint32_t*)h->b_cig.p;
     bv.seq_off = (const uint64_t*)h->b_soff.p; bv.seq4 = dev_seq;
     bv.qual = dev_qual;
-    return deposit_with_replay(h, bv);
+    return deposit_with_replay(h, bv, b->n_cigar_ops);
 }
 
 int lvc_push_batch_device(lvc_handle* h, const lvc_batch* b) {
@@ -569,7 +585,7 @@ int lvc_push_batch_device(lvc_handle* h, const lvc_batch* b) {
     bv.cigar_off = b->cigar_off; bv.cigar = b->cigar; bv.seq_off = b->seq_off; bv.seq4 = b->seq4; bv.qual = b->qual;
     rc = premap_device(h, b);
     if (rc) return rc;
-    return deposit_with_replay(h, bv);
+    return deposit_with_replay(h, bv, b->n_cigar_ops);
 }
 
 int lvc_push_batch_device_async(lvc_handle* h, const lvc_batch* b) {
@@ -583,7 +599,7 @@ int lvc_push_batch_device_async(lvc_handle* h, const lvc_batch* b) {
     bv.n_reads = b->n_reads;
     bv.pos = b->pos; bv.flag = b->flag; bv.mapq = b->mapq; bv.keep = b->keep;
     bv.cigar_off = b->cigar_off; bv.cigar = b->cigar; bv.seq_off = b->seq_off; bv.seq4 = b->seq4; bv.qual = b->qual;
-    rc = launch_deposit(h, bv, 0);
+    rc = launch_deposit(h, bv, 0, b->n_cigar_ops);
     if (rc) return rc;
     h->ordinal += b->n_reads;
     return LVC_OK;
@@ -667,25 +683,41 @@ static int genotype_enqueue(lvc_handle* h, int64_t min_total_depth, int64_t min_
         memcmp(h->lut_host + 256, om_lut, 256 * sizeof(double)) != 0) {
         memcpy(h->lut_host, e_lut, 256 * sizeof(double));
         memcpy(h->lut_host + 256, om_lut, 256 * sizeof(double));
-        CU(cudaMemcpyAsync(h->d_elut, h->lut_host, 512 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
         h->lut_valid = true;
         tables_stale = true;
     }
     if (tables_stale && np > 0) {
-        rc = ensure(h, h->g_pow, (size_t)np * 2 * kGenoPowBits * sizeof(XF));
+        // per plane: log2(e[q]) and log2(1 - e[q]) as double-doubles, from the caller's doubles in 80-bit arithmetic.
+        // A zero probability (1 - e at q = 0) becomes a huge finite negative logarithm: its products vanish.
+        rc = ensure(h, h->g_pconst, (size_t)np * sizeof(PlaneConst));
         if (rc) return rc;
-        rc = ensure(h, h->g_ed, (size_t)np * sizeof(double));
-        if (rc) return rc;
-        k_pow_tables<<<(2 * np + 63) / 64, 64, 0, h->stream>>>(np, (const uint16_t*)h->g_order_keys.p, h->d_elut,
-                                                               h->d_elut + 256, (XF*)h->g_pow.p, (double*)h->g_ed.p);
-        h->launches++;
+        CU(cudaStreamSynchronize(h->stream));                 // the staging vector may still feed an earlier copy
+        h->pconst_host.resize((size_t)np);
+        auto split = [](double v, double& hi, double& lo) {
+            if (!(v > 0.0)) { hi = -1e290; lo = 0.0; return; }
+            const long double l = log2l((long double)v);
+            hi = (double)l;
+            lo = (double)(l - (long double)hi);
+        };
+        for (int k = 0; k < np; ++k) {
+            const uint32_t q = keys[(size_t)k] & 255u;
+            PlaneConst& pc = h->pconst_host[(size_t)k];
+            split(e_lut[q], pc.le_h, pc.le_l);
+            split(om_lut[q], pc.lo_h, pc.lo_l);
+            pc.e = e_lut[q];
+        }
+        CU(cudaMemcpyAsync(h->g_pconst.p, h->pconst_host.data(), (size_t)np * sizeof(PlaneConst), cudaMemcpyHostToDevice,
+                           h->stream));
     }
     GenoParams gp;
     gp.G = h->G; gp.p0 = h->geno_p0; gp.p1 = h->geno_p1 < 0 ? h->G : h->geno_p1; gp.min_total_depth = min_total_depth; gp.min_allele_depth = min_allele_depth;
     gp.min_ratio = min_ratio; gp.flags = flags; gp.n_planes = np; gp.cand_cap = h->cand_cap;
     for (int g = 0; g < 5; ++g) gp.grp_begin[g] = grp_begin[g];
     const int threads = kGenoThreads;
-    const unsigned blocks = (unsigned)((gp.p1 - gp.p0 + (threads / 4) - 1) / (threads / 4));
+    // wide quality alphabets (ONT: dozens of planes) on a short contig: 8 lanes share the planes of one (position, slot)
+    const int lpp = (grp_begin[1] - grp_begin[0] >= 16 && gp.p1 - gp.p0 <= (1 << 22)) ? 8 : 1;
+    const int ppb = threads / (4 * lpp);                      // positions per block
+    const unsigned blocks = (unsigned)((gp.p1 - gp.p0 + ppb - 1) / ppb);
     if (gp.p1 <= gp.p0) { h->last_cand_count = 0; h->geno_pending = false; return LVC_OK; }
     {
         // Launched with programmatic stream serialization: its blocks may become resident while the deposit kernel
@@ -700,8 +732,9 @@ static int genotype_enqueue(lvc_handle* h, int64_t min_total_depth, int64_t min_
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        CU(cudaLaunchKernelEx(&cfg, k_genotype, gp, (const uint32_t* const*)h->g_order_ptrs.p, (const XF*)h->g_pow.p,
-                              (const double*)h->g_ed.p, (const uint32_t*)h->d_dels, (const uint8_t*)h->d_ref,
+        auto kern = lpp == 8 ? k_genotype<8> : k_genotype<1>;
+        CU(cudaLaunchKernelEx(&cfg, kern, gp, (const uint32_t* const*)h->g_order_ptrs.p,
+                              (const PlaneConst*)h->g_pconst.p, (const uint32_t*)h->d_dels, (const uint8_t*)h->d_ref,
                               (const uint32_t* const*)h->d_first_arr, h->d_out_depth, h->d_out_ad, h->d_out_lik,
                               (lvc_candidate*)h->g_cand.p, h->d_cand_count + h->cand_slot,
                               h->d_cand_count + (h->cand_slot ^ 1)));

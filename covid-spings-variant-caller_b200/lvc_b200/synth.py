@@ -68,15 +68,19 @@ def _illumina_block(rng, refc: np.ndarray, pos: np.ndarray, read_len: int, snv_p
     # planted SNVs: a read carries the ALT with probability AF at each planted position it covers
     if len(snv_pos):
         lo, hi = int(pos.min()), int(pos.max()) + L + 4
+        sorted_pos = bool((np.diff(pos) >= 0).all())
         for k in np.nonzero((snv_pos >= lo) & (snv_pos < hi))[0]:
-            hit = (ridx == snv_pos[k]) & ~ins_mask
+            # only reads starting in [snv - L - 3, snv] can cover it (pos is sorted: two binary searches)
+            r0, r1 = (int(np.searchsorted(pos, snv_pos[k] - L - 4, "left")), int(np.searchsorted(pos, snv_pos[k], "right"))) \
+                if sorted_pos else (0, n)
+            hit = (ridx[r0:r1] == snv_pos[k]) & ~ins_mask[r0:r1]
             rows = np.nonzero(hit.any(axis=1))[0]
             if len(rows) == 0:
                 continue
             carry = rng.random(len(rows)) < snv_af[k]
             rr = rows[carry]
             cc = hit[rr].argmax(axis=1)
-            base[rr, cc] = snv_alt[k]
+            base[r0 + rr, cc] = snv_alt[k]
     base[ins_mask] = rng.integers(0, 4, int(ins_mask.sum()))
     # sequencing errors drawn from the base quality
     err = rng.random((n, L)) < np.power(10.0, qual.astype(np.float64) / -10.0)
@@ -223,3 +227,71 @@ def ont_batch(seed: int, ref: str, depth: float = 1000.0, ref_span: int = 400, m
         q = np.clip(np.round(np.exp(rng.normal(2.85, 0.55, len(seq)))), 2, 90).astype(np.uint8)
         rows.append((16 if strand[i] else 0, int(pos[i]), 60, ops, "".join(letters[b] for b in seq), q))
     return packing.pack_reads(rows, min_mapq, max_depth)
+
+
+def ont_batch_fast(seed: int, ref: str, depth: float = 1000.0, ref_span: int = 400, min_mapq: int = 20,
+                   max_depth: int = 8000, n_runs: int = 10) -> ReadBatch:
+    """Vectorised SURVEY 8d config-3 batch (same model as ont_batch, fixed op count): every read is
+    S, M, (I|D, M) x 9, S = 21 CIGAR ops, reference span `ref_span`, 50-70 bp soft clips, indels of 1-3 bp,
+    3 % substitutions, qualities round(exp(N(2.85, 0.55))) clipped to 2..90, flag 0/16, mapq 60."""
+    G = len(ref)
+    refc = _reference_codes(ref)
+    rng = np.random.default_rng(seed)
+    n = int(round(G * depth / ref_span))
+    pos = np.sort(rng.integers(0, G - ref_span - 40, n)).astype(np.int64)
+    strand = rng.random(n) < 0.5
+    order = np.lexsort((strand, pos))
+    pos, strand = pos[order], strand[order]
+    n_gap = n_runs - 1
+    is_del = rng.random((n, n_gap)) < 0.5
+    glen = rng.integers(1, 4, (n, n_gap)).astype(np.int64)
+    m_total = ref_span - np.where(is_del, glen, 0).sum(axis=1)                 # reference bases in match runs
+    # n_runs positive run lengths summing to m_total: sorted distinct cut points
+    cuts = np.sort(rng.random((n, n_gap)), axis=1)
+    edges = np.concatenate([np.zeros((n, 1)), cuts, np.ones((n, 1))], axis=1)
+    runs = np.floor(np.diff(edges, axis=1) * (m_total - n_runs)[:, None]).astype(np.int64) + 1
+    runs[:, -1] += m_total - runs.sum(axis=1)
+    clipl, clipr = rng.integers(50, 71, n).astype(np.int64), rng.integers(50, 71, n).astype(np.int64)
+    n_ops = 2 * n_runs + 1
+    op = np.zeros((n, n_ops), dtype=np.int64)
+    ln = np.zeros((n, n_ops), dtype=np.int64)
+    op[:, 0], ln[:, 0], op[:, -1], ln[:, -1] = 4, clipl, 4, clipr
+    op[:, 1:-1:2], ln[:, 1:-1:2] = 0, runs
+    op[:, 2:-1:2], ln[:, 2:-1:2] = np.where(is_del, 2, 1), glen
+    cigar = ((ln << 4) | op).astype(np.uint32).ravel()
+    coff = (np.arange(n + 1, dtype=np.int64) * n_ops).astype(np.uint32)
+    # per-op reference start and query length
+    consumes_ref = (op == 0) | (op == 2)
+    consumes_q = op != 2
+    ref_start = pos[:, None] + np.cumsum(np.where(consumes_ref, ln, 0), axis=1) - np.where(consumes_ref, ln, 0)
+    qlen_op = np.where(consumes_q, ln, 0)
+    lq = qlen_op.sum(axis=1)
+    lqp = lq + (lq & 1)                                                         # reads start at even offsets
+    soff = np.concatenate([[0], np.cumsum(lqp)]).astype(np.uint64)
+    # expand to bases
+    tot = int(lq.sum())
+    flat_q = qlen_op.ravel()
+    op_of_base = np.repeat(np.arange(n * n_ops, dtype=np.int64), flat_q)
+    starts = np.cumsum(flat_q) - flat_q
+    within = np.arange(tot, dtype=np.int64) - starts[op_of_base]
+    is_m = op.ravel()[op_of_base] == 0
+    base = rng.integers(0, 4, tot).astype(np.uint8)
+    rp = ref_start.ravel()[op_of_base] + within
+    mb = refc[np.where(is_m, rp, 0)]
+    err = rng.random(tot) < 0.03
+    mb = np.where(err, (mb + rng.integers(1, 4, tot)) & 3, mb).astype(np.uint8)
+    base = np.where(is_m, mb, base)
+    qual_b = np.clip(np.round(np.exp(rng.normal(2.85, 0.55, tot))), 2, 90).astype(np.uint8)
+    # scatter to padded per-read layout
+    read_of_base = np.repeat(np.arange(n, dtype=np.int64), lq)
+    rstart = np.cumsum(lq) - lq
+    dst = soff[:-1].astype(np.int64)[read_of_base] + (np.arange(tot, dtype=np.int64) - rstart[read_of_base])
+    nq = int(soff[-1])
+    nib = np.zeros(nq, dtype=np.uint8)
+    nib[dst] = _NIB[base]
+    qual = np.zeros(nq, dtype=np.uint8)
+    qual[dst] = qual_b
+    seq4 = ((nib[0::2] << 4) | nib[1::2]).astype(np.uint8)
+    flag = np.where(strand, 16, 0).astype(np.uint16)
+    return packing.finalize_batch(pos.astype(np.int32), flag, np.full(n, 60, np.uint8), coff, cigar, soff, seq4, qual,
+                                  min_mapq, max_depth, acgt_only=np.ones(n, dtype=bool))

@@ -123,9 +123,10 @@ void lvc_reads_free(lvc_reads* r);
 
 /* ---- deposit: process_bam / process_pileup_column / process_svn (live_variant_caller.py:54-103) ----
  * Walks every kept read's CIGAR on the device and adds its bases/qualities to the persistent
- * per-position tables.  Accumulates across calls (live batches).  `impl`: 0 = auto (= 4), 1 = general
- * kernel only, 2 = tiled kernel staging the raw payload with TMA, 4 = tiled kernel staging 4-bit keys (both use the
- * general path for what they cannot take). */
+ * per-position tables.  Accumulates across calls (live batches).  `impl`: 0 = auto (4 for short-read batches, 3 for
+ * batches averaging more than 4 CIGAR ops per read), 1 = general kernel only (one thread per read), 2 = tiled kernel
+ * staging the raw payload with TMA, 3 = one warp per read (long reads, wide quality alphabets), 4 = tiled kernel
+ * staging 4-bit keys (the tiled kernels use the warp path for the reads they cannot take). */
 int lvc_push_batch(lvc_handle* h, const lvc_batch* host_batch);
 int lvc_push_batch_device(lvc_handle* h, const lvc_batch* device_batch);
 int lvc_set_impl(lvc_handle* h, int impl);
