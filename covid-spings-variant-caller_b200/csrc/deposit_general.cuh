@@ -95,27 +95,27 @@ __device__ __forceinline__ void deposit_read_warp_impl(const BatchView& b, const
     const uint32_t c0 = b.cigar_off[i], c1 = b.cigar_off[i + 1];
     const int64_t pos = b.pos[i];
     const uint64_t qb = b.seq_off[i];
-    // totals: reference length and l_qseq
-    int64_t rlen = 0;
-    uint32_t lq = 0;
-    uint32_t cg_first = 0;                                   // the first group's ops stay in registers
+    // group 0 of the ops (all of them for reads with <= 32 ops) stays in registers
+    const uint32_t cg_first = c0 + lane < c1 ? b.cigar[c0 + lane] : 0u;       // padding: a match of length 0
+    // totals: reference length and l_qseq.  Per-op lengths are < 2^28, so 32 of them cannot wrap 64 bits; a read
+    // whose reference span does not fit 31 bits cannot lie inside any contig and is reported as out of range.
+    uint64_t rlen = 0, lq64 = 0;
     for (uint32_t g0 = c0; g0 < c1; g0 += 32) {
-        const uint32_t c = g0 + lane < c1 ? b.cigar[g0 + lane] : 0u;    // padding: a match of length 0
-        if (g0 == c0) cg_first = c;
+        const uint32_t c = g0 == c0 ? cg_first : (g0 + lane < c1 ? b.cigar[g0 + lane] : 0u);
         const uint32_t op = c & 15u, len = c >> 4;
         const uint32_t rl = op_consumes_ref(op) ? len : 0u, ql = op_consumes_query(op) ? len : 0u;
-        // per-op lengths are < 2^28: 32 of them fit 64 bits exactly; sum in two halves to stay in 32-bit reductions
-        rlen += (int64_t)__reduce_add_sync(0xFFFFFFFFu, rl & 0xFFFFu) + ((int64_t)__reduce_add_sync(0xFFFFFFFFu, rl >> 16) << 16);
-        lq += __reduce_add_sync(0xFFFFFFFFu, ql);
+        rlen += (uint64_t)__reduce_add_sync(0xFFFFFFFFu, rl >> 8) * 256u + __reduce_add_sync(0xFFFFFFFFu, rl & 255u);
+        lq64 += (uint64_t)__reduce_add_sync(0xFFFFFFFFu, ql >> 8) * 256u + __reduce_add_sync(0xFFFFFFFFu, ql & 255u);
     }
     if (rlen == 0) return;   // no M/D/N/=/X op: htslib asserts on such records; skipped
-    if (pos < 0 || pos + rlen > tv.G) {
+    if (pos < 0 || rlen > 0x7FFFFFFFull || lq64 > 0xFFFFFFFFull || pos + (int64_t)rlen > tv.G) {
         if (lane == 0) atomicAdd(&tv.status[ST_RANGE_ERR], 1u);
         return;
     }
+    const uint32_t lq = (uint32_t)lq64;
     if (!dp.replay && lane == 0) {
         atomicAdd(&tv.covdiff[pos], 1);
-        atomicAdd(&tv.covdiff[pos + rlen], -1);
+        atomicAdd(&tv.covdiff[pos + (int64_t)rlen], -1);
     }
     const uint8_t* qual = b.qual + qb;
     const uint8_t* seq = b.seq4 + (qb >> 1);
@@ -126,31 +126,28 @@ __device__ __forceinline__ void deposit_read_warp_impl(const BatchView& b, const
         if (off < (lq + 1) / 2) asm volatile("prefetch.global.L1 [%0];" ::"l"(seq + off));
     }
     const uint32_t ord = dp.ord_base + i;
-    int64_t r_base = pos;
-    uint32_t q_base = 0;
+    uint32_t r_base = 0, q_base = 0;                         // offsets from pos / from the first query base
     for (uint32_t g0 = c0; g0 < c1; g0 += 32) {
         const uint32_t c = g0 == c0 ? cg_first : (g0 + lane < c1 ? b.cigar[g0 + lane] : 0u);
         const uint32_t op = c & 15u, len = c >> 4;
         const uint32_t rl = op_consumes_ref(op) ? len : 0u, ql = op_consumes_query(op) ? len : 0u;
-        // exclusive prefix of the reference / query lengths inside the group (ref offsets in 64 bits)
-        uint64_t r_in = rl;
-        uint32_t q_in = ql;
+        // inclusive prefix of the reference / query lengths inside the group
+        uint32_t r_in = rl, q_in = ql;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const uint64_t ur = __shfl_up_sync(0xFFFFFFFFu, r_in, d);
+            const uint32_t ur = __shfl_up_sync(0xFFFFFFFFu, r_in, d);
             const uint32_t uq = __shfl_up_sync(0xFFFFFFFFu, q_in, d);
             if ((int)lane >= d) { r_in += ur; q_in += uq; }
         }
-        const uint64_t r_off = r_in - rl;
-        const uint32_t q_off = q_in - ql;
+        const uint32_t r_off = r_base + r_in - rl, q_off = q_base + q_in - ql;
         // ops with something to deposit
         uint32_t work = __ballot_sync(0xFFFFFFFFu, len != 0 && (op_is_match(op) || op == 2 || op == 3));
         while (work) {
             const int k = __ffs(work) - 1;
             work &= work - 1;
             const uint32_t ck = __shfl_sync(0xFFFFFFFFu, c, k);
-            const int64_t r = r_base + (int64_t)__shfl_sync(0xFFFFFFFFu, r_off, k);
-            const uint32_t qi = q_base + __shfl_sync(0xFFFFFFFFu, q_off, k);
+            const int64_t r = pos + (int64_t)__shfl_sync(0xFFFFFFFFu, r_off, k);
+            const uint32_t qi = __shfl_sync(0xFFFFFFFFu, q_off, k);
             const uint32_t opk = ck & 15u, lenk = ck >> 4;
             if (op_is_match(opk)) {
                 for (uint32_t j = lane; j < lenk; j += 32) {
@@ -168,7 +165,7 @@ __device__ __forceinline__ void deposit_read_warp_impl(const BatchView& b, const
                     for (uint32_t j = lane; j < lenk; j += 32) atomicAdd(&tv.dels[r + j], 1u);
             }
         }
-        r_base += (int64_t)__shfl_sync(0xFFFFFFFFu, r_in, 31);
+        r_base += __shfl_sync(0xFFFFFFFFu, r_in, 31);
         q_base += __shfl_sync(0xFFFFFFFFu, q_in, 31);
     }
 }
