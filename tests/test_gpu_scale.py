@@ -110,8 +110,19 @@ def test_live_batches_ont(lib):
     ref = synth.random_reference(6000, 3)
     batches = [synth.ont_batch(100 + k, ref, depth=40.0) for k in range(3)]
     th = dict(minBQ=13, minMQ=20, minDP=10, minAD=3, ratio=0.05)
-    for impl in (1, 2, 4):
+    for impl in (0, 1, 2, 3, 4):          # 0 = auto: picks the warp-per-read kernel for these batches
         check_against_c_oracle(ref, batches, th, impl)
+
+
+def test_config3_sized_ont_batches(lib):
+    """SURVEY 8d config 3 at full batch size (74,758 reads, ~21 CIGAR ops each, qualities 2..90): two live batches
+    through the warp-per-read kernel and the 8-lane genotype pass, against the C oracle"""
+    from lvc_b200 import synth
+    ref = synth.random_reference(29903, 20260199)
+    batches = [synth.ont_batch_fast(20260200 + k, ref) for k in range(2)]
+    assert batches[0].n_reads == 74758 and batches[0].n_cigar == 21 * 74758
+    check_against_c_oracle(ref, batches, dict(minBQ=30, minMQ=20, minDP=10, minAD=5, ratio=0.10), 0)
+    check_against_c_oracle(ref, batches[:1], dict(minBQ=7, minMQ=20, minDP=10, minAD=5, ratio=0.02), 0)
 
 
 def test_full_size_config2_properties(lib):
