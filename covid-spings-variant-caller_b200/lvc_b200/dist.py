@@ -156,6 +156,145 @@ def process_batch_sharded(caller, batch: ReadBatch, group=None) -> int:
     return n
 
 
+# ------------------------------------------------------------------------------------------------
+# halo-only exchange (the refinement of the full-table reduce)
+# ------------------------------------------------------------------------------------------------
+def ref_lengths(batch: ReadBatch) -> np.ndarray:
+    """reference span per read = sum of the M/D/N/=/X op lengths"""
+    n = batch.n_reads
+    if n == 0:
+        return np.zeros(0, dtype=np.int64)
+    nc = int(batch.cigar_off[n])
+    ops = batch.cigar[:nc] & 15
+    w = np.where((ops == 0) | (ops == 2) | (ops == 3) | (ops == 7) | (ops == 8), (batch.cigar[:nc] >> 4).astype(np.int64), 0)
+    csum = np.concatenate([[0], np.cumsum(w)])
+    co = batch.cigar_off[:n + 1].astype(np.int64)
+    return csum[co[1:]] - csum[co[:-1]]
+
+
+def touched_ranges(batch: ReadBatch, shards: Sequence[Tuple[int, int]]) -> List[Tuple[int, int]]:
+    """[lo, hi) columns each rank's chunk of reads can deposit into (a superset: filtered reads count too).
+    Every rank computes the same list from the batch metadata, so the exchange plan needs no communication."""
+    end = batch.pos[:batch.n_reads].astype(np.int64) + ref_lengths(batch)
+    out = []
+    for a, b in shards:
+        out.append((int(batch.pos[a]), int(end[a:b].max())) if b > a else (0, 0))
+    return out
+
+
+def halo_plan(G: int, world_size: int, touched: Sequence[Tuple[int, int]]) -> Dict[Tuple[int, int], Tuple[int, int]]:
+    """(src, dst) -> [lo, hi): the columns rank `src` deposited into that rank `dst` owns (position_slice)."""
+    plan = {}
+    for src, (lo, hi) in enumerate(touched):
+        if hi <= lo:
+            continue
+        for dst in range(world_size):
+            if dst == src:
+                continue
+            p0, p1 = position_slice(G, world_size, dst)
+            a, b = max(lo, p0), min(hi, p1)
+            if b > a:
+                plan[(src, dst)] = (a, b)
+    return plan
+
+
+def _width(name: str) -> int:
+    return 1 if name in ("dels", "covdiff") else 4
+
+
+def _segment(name: str, a: int, b: int, G: int) -> Tuple[int, int]:
+    """element range of table `name` for the columns [a, b).  The coverage difference array has G + 1 entries;
+    entry i belongs to the owner of column min(i, G - 1)."""
+    if name == "covdiff":
+        return a, b + 1 if b == G else b
+    w = _width(name)
+    return a * w, b * w
+
+
+def halo_exchange(tables: Dict[str, "object"], G: int, touched: Sequence[Tuple[int, int]], group=None) -> int:
+    """Position-ownership exchange: rank r owns the columns position_slice(G, world, r) and keeps the history of
+    those only.  After a rank deposited its chunk of reads, whatever it deposited into columns owned by another
+    rank (normally a halo of one read span next to its own slice) is SENT to the owner (one message per pair),
+    added there (unsigned MIN for the first-seen tables) and cleared locally.  Works on CPU tensors with gloo (tests)
+    and on CUDA tensors with NCCL P2P over NVLink (production).  Returns the bytes this rank sent.
+
+    The touched range is widened by one column so that the end marker of the coverage difference array (written
+    at column end + 1) travels with it; cumulative coverage of a slice needs the prefix of the lower ranks' slices."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return 0
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    plan = halo_plan(G, world, [(lo, min(hi + 1, G)) if hi > lo else (0, 0) for lo, hi in touched])
+    names = sorted(tables)
+    bias = None
+    ops, recvs, sends = [], [], []
+    for (src, dst), (a, b) in sorted(plan.items()):
+        segs = [_segment(nm, a, b, G) for nm in names]
+        if src == rank:
+            buf = torch.cat([tables[nm][x:y] for nm, (x, y) in zip(names, segs)])
+            sends.append((buf, segs))
+            ops.append(dist.P2POp(dist.isend, buf, dst, group))
+        elif dst == rank:
+            ref_t = tables[names[0]]
+            buf = torch.empty(sum(y - x for x, y in segs), dtype=torch.int32, device=ref_t.device)
+            recvs.append((buf, segs))
+            ops.append(dist.P2POp(dist.irecv, buf, src, group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    sent = 0
+    for buf, segs in recvs:
+        off = 0
+        for nm, (x, y) in zip(names, segs):
+            part = buf[off:off + (y - x)]
+            off += y - x
+            t = tables[nm]
+            if nm.startswith("first"):
+                if bias is None:
+                    bias = torch.tensor(_BIAS, dtype=torch.int32, device=t.device)
+                t[x:y] = torch.minimum(t[x:y] ^ bias, part ^ bias) ^ bias
+            else:
+                t[x:y] += part
+    for buf, segs in sends:
+        sent += buf.numel() * 4
+        for nm, (x, y) in zip(names, segs):
+            tables[nm][x:y] = -1 if nm.startswith("first") else 0
+    return sent
+
+
+def process_batch_halo(caller, batch: ReadBatch, group=None) -> int:
+    """One sample, read-chunk sharding with POSITION OWNERSHIP (halo-only refinement): every rank deposits
+    its contiguous chunk of the coordinate-sorted batch, then sends only the columns it touched outside its own
+    slice of positions to their owners.  Each rank's tables hold the full history of ITS slice (and zeros elsewhere),
+    which is the slice it genotypes.  Use either this or process_batch_sharded on a caller, not both.
+    Returns the bytes this rank sent."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    h = caller._handle
+    base = h.ordinal
+    shards = shard_reads(batch, world)
+    a, b = shards[rank]
+    h.ordinal = base + a                      # first-seen ordinals are global read indices
+    if b > a:
+        h.push_batch(batch.slice(a, b).as_capi())
+    h.ordinal = base + batch.n_reads
+    sent = 0
+    if world > 1:
+        h.sync()
+        for k in key_union([int(k) for k in h.plane_keys()], group):
+            h.ensure_plane(k)
+        tabs = device_tables(h)
+        torch.cuda.synchronize()
+        sent = halo_exchange(tabs, h.G, touched_ranges(batch, shards), group)
+        torch.cuda.synchronize()
+    p0, p1 = position_slice(h.G, world, rank)
+    h.set_genotype_range(p0, p1)
+    return sent
+
+
 def gather_variants(caller, group=None) -> List[dict]:
     """records of every rank's position slice, merged in position order on every rank"""
     import torch.distributed as dist

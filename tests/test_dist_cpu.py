@@ -99,3 +99,84 @@ def test_shard_reads_balanced_and_contiguous(lib, golden_synth):
     sl = b.slice(5, 40)
     assert sl.n_reads == 35 and sl.pos.tolist() == b.pos[5:40].tolist()
     assert sl.qual[:sl.n_qual].tolist() == b.qual[int(b.seq_off[5]):int(b.seq_off[40])].tolist()
+
+
+def _halo_worker(rank, world, port, rows, ref, q):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (root, os.path.join(root, "covid-spings-variant-caller_b200"), os.path.join(root, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch
+    import torch.distributed as dist
+    from lvc_b200 import packing, dist as ldist
+    from oracle.c_oracle import COracle
+    from helpers import rows_to_tuples as r2t
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    G = len(ref)
+    tabs = {"plane_ad": torch.zeros(G * 16, dtype=torch.int32), "dels": torch.zeros(G, dtype=torch.int32),
+            "covdiff": torch.zeros(G + 1, dtype=torch.int32), "first0": torch.full((G * 16,), -1, dtype=torch.int32)}
+    ldist_width = ldist._width
+    ldist._width = lambda name: 16 if name in ("plane_ad", "first0") else ldist_width(name)   # 16 alleles per column here
+    sent = 0
+    ordinal = 0
+    for k in range(3):                                        # three live batches: history stays with the owner
+        sel = list(range(k, len(rows), 3))
+        batch = packing.pack_reads(r2t([rows[i] for i in sel]), 0)
+        shards = ldist.shard_reads(batch, world)
+        a, b = shards[rank]
+        co = COracle(ref, 13, 0, max_depth=10 ** 9)
+        co.st.ordinal = ordinal + a
+        co.process(_apply_keep(batch.slice(a, b)))
+        ordinal += batch.n_reads
+        # this batch's deposits of this rank, added to the local tables (first-seen: unsigned min)
+        tabs["plane_ad"] += torch.from_numpy(co.ad.astype(np.int32).reshape(-1).copy())
+        tabs["dels"] += torch.from_numpy((co.depth.astype(np.int64) - co.ad.sum(axis=1)).astype(np.int32))
+        tabs["covdiff"] += torch.from_numpy(np.diff(np.concatenate([[0], co.cov.astype(np.int64), [0]])).astype(np.int32))
+        f = torch.from_numpy(co.first.astype(np.uint32).view(np.int32).reshape(-1).copy())
+        bias = torch.tensor(-2 ** 31, dtype=torch.int32)
+        tabs["first0"] = torch.minimum(tabs["first0"] ^ bias, f ^ bias) ^ bias
+        sent += ldist.halo_exchange(tabs, G, ldist.touched_ranges(batch, shards))
+    q.put((rank, ldist.position_slice(G, world, rank), {k: v.numpy().copy() for k, v in tabs.items()}, sent))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_halo_exchange_leaves_every_owner_with_the_full_history_of_its_slice(lib, golden_synth, world):
+    import torch.multiprocessing as mp
+    from lvc_b200 import packing
+    from oracle.c_oracle import COracle
+    g = golden_synth["amplicon_like"]
+    rows, ref = g["reads"], g["ref"]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_halo_worker, args=(r, world, port, rows, ref, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    co = COracle(ref, 13, 0)
+    for k in range(3):
+        co.process(packing.pack_reads(rows_to_tuples([rows[i] for i in range(k, len(rows), 3)]), 0))
+    G = len(ref)
+    want_cd = np.diff(np.concatenate([[0], co.cov.astype(np.int64), [0]])).astype(np.int32)
+    total_cd = np.zeros(G + 1, dtype=np.int64)
+    full_bytes = (16 + 1 + 16) * 4 * G
+    for rank, (p0, p1), tabs, sent in got:
+        ad = tabs["plane_ad"].reshape(-1, 16)
+        assert np.array_equal(ad[p0:p1], co.ad.astype(np.int32)[p0:p1])
+        assert not ad[:p0].any() and not ad[p1:].any()                  # nothing but the owned slice is kept
+        dels = (co.depth.astype(np.int64) - co.ad.sum(axis=1)).astype(np.int32)
+        assert np.array_equal(tabs["dels"][p0:p1], dels[p0:p1])
+        first = tabs["first0"].view(np.uint32).reshape(-1, 16)
+        assert np.array_equal(first[p0:p1], co.first[p0:p1])
+        assert (first[:p0] == 0xFFFFFFFF).all() and (first[p1:] == 0xFFFFFFFF).all()
+        total_cd += tabs["covdiff"]
+        hi = p1 + 1 if p1 == G else p1
+        assert not tabs["covdiff"][:p0].any() and not tabs["covdiff"][hi:].any()
+        assert sent < full_bytes                                        # a halo, not the table
+    assert np.array_equal(total_cd, want_cd)

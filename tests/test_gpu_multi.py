@@ -19,7 +19,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, rows, ref, q):
+def _worker(rank, world, port, rows, ref, q, mode="full"):
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     for p in (root, os.path.join(root, "covid-spings-variant-caller_b200"), os.path.join(root, "tests")):
@@ -42,10 +42,24 @@ def _worker(rank, world, port, rows, ref, q):
     for k in range(3):                                   # three live batches
         sel = list(range(k, len(rows), 3))
         batch = packing.pack_reads(r2t([rows[i] for i in sel]), th["minMQ"])
-        ldist.process_batch_sharded(lvc, batch)
+        if mode == "halo":
+            sent = ldist.process_batch_halo(lvc, batch)
+            assert sent < 4 * 4 * len(ref) * len(lvc._handle.plane_keys())      # a halo, not the tables
+        else:
+            ldist.process_batch_sharded(lvc, batch)
         out.append(ldist.gather_variants(lvc))
     lvc._handle.set_genotype_range(0, -1)
-    mem = memory_tables(lvc.memory)
+    if mode == "halo":
+        # every rank keeps the history of its own slice of positions only
+        p0, p1 = ldist.position_slice(len(ref), world, rank)
+        lvc._candidates()                                  # genotype pass over all positions: fills the dense outputs
+        depth, ad, _lik = lvc._handle.copy_dense()
+        mem = (p0, p1, depth[p0:p1].tolist(), ad[p0:p1].tolist(), bool(ad[:p0].any() or ad[p1:].any()))
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mem)
+        mem = gathered
+    else:
+        mem = memory_tables(lvc.memory)
     if rank == 0:
         q.put((out, mem))
     dist.barrier()
@@ -83,4 +97,42 @@ def test_two_ranks_equal_one(lib, golden_synth, tmp_path):
         one.process_batch(packing.pack_reads(rows_to_tuples([rows[i] for i in sel]), th["minMQ"]))
         assert_variants_equal(out[k], one.prepare_variants(), f"batch {k}")
     assert mem == memory_tables(one.memory)
+    one.close()
+
+
+def test_two_ranks_halo_exchange_equal_one(lib, golden_synth, tmp_path):
+    """position ownership + halo-only exchange (NCCL send/recv): records of every live batch and the per-slice
+    tables must equal the single-GPU run"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from lvc_b200 import packing
+    from variant_caller.live_variant_caller import LiveVariantCaller
+    g = golden_synth["amplicon_like"]
+    rows, ref = g["reads"], g["ref"]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, rows, ref, q, "halo")) for r in range(2)]
+    for p in procs:
+        p.start()
+    out, slices = q.get(timeout=300)
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    fa = str(tmp_path / "c.fasta")
+    with open(fa, "w") as fh:
+        fh.write(">c\n" + ref + "\n")
+    th = dict(minBQ=13, minMQ=0, minDP=3, minAD=2, ratio=0.05)
+    one = LiveVariantCaller(fa, th["minBQ"], th["minMQ"], th["minDP"], th["minAD"], th["ratio"], 1, device=0)
+    for k in range(3):
+        sel = list(range(k, len(rows), 3))
+        one.process_batch(packing.pack_reads(rows_to_tuples([rows[i] for i in sel]), th["minMQ"]))
+        assert_variants_equal(out[k], one.prepare_variants(), f"batch {k}")
+    one._candidates()
+    depth, ad, _ = one._handle.copy_dense()
+    for p0, p1, d, a, outside in slices:
+        assert d == depth[p0:p1].tolist() and a == ad[p0:p1].tolist()
+        assert not outside
     one.close()
