@@ -45,6 +45,7 @@ def main():
     ap.add_argument("--batches", type=int, default=100)
     ap.add_argument("--ref-len", type=int, default=1_000_000)
     ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--segments", type=int, default=1, help="config 5: genome = segments x ref-len (5 x 1 Mb = SURVEY's 5 Mb)")
     ap.add_argument("--min-bq", type=int, default=THRESH["minBQ"])
     a = ap.parse_args()
     import torch
@@ -106,7 +107,34 @@ def main():
                "kernel_avg_ms": kt}
     else:
         t0 = time.time()
-        ref, batch = synth.shotgun_sample(ref_len=a.ref_len, n_snvs=max(10, a.ref_len // 10000))[:2]
+        if a.segments <= 1:
+            ref, batch = synth.shotgun_sample(ref_len=a.ref_len, n_snvs=max(10, a.ref_len // 10000))[:2]
+        else:
+            # a genome of `segments` x ref_len: independently seeded segments, positions shifted, concatenated (the
+            # result is coordinate sorted; depth 1,000x never reaches the admission cap, finalize_batch recomputes it)
+            from lvc_b200 import packing
+            parts, refs = [], []
+            for k in range(a.segments):
+                r_k, b_k = synth.shotgun_sample(seed=20260400 + 7 * k, ref_len=a.ref_len,
+                                                n_snvs=max(10, a.ref_len // 10000))[:2]
+                refs.append(r_k); parts.append(b_k)
+            n_tot = sum(b.n_reads for b in parts)
+            pos = np.concatenate([b.pos[:b.n_reads].astype(np.int64) + k * a.ref_len for k, b in enumerate(parts)])
+            coff = np.zeros(n_tot + 1, dtype=np.uint32); soff = np.zeros(n_tot + 1, dtype=np.uint64)
+            i0 = c0 = q0 = 0
+            for b in parts:
+                n = b.n_reads
+                coff[i0 + 1:i0 + n + 1] = b.cigar_off[1:n + 1].astype(np.uint32) + np.uint32(c0)
+                soff[i0 + 1:i0 + n + 1] = b.seq_off[1:n + 1] + np.uint64(q0)
+                i0 += n; c0 += b.n_cigar; q0 += b.n_qual
+            batch = packing.finalize_batch(
+                pos.astype(np.int32), np.concatenate([b.flag[:b.n_reads] for b in parts]),
+                np.concatenate([b.mapq[:b.n_reads] for b in parts]), coff,
+                np.concatenate([b.cigar[:b.n_cigar] for b in parts]), soff,
+                np.concatenate([b.seq4[:b.n_qual // 2] for b in parts]),
+                np.concatenate([b.qual[:b.n_qual] for b in parts]), THRESH["minMQ"], acgt_only=np.ones(n_tot, dtype=bool))
+            ref = "".join(refs)
+            del parts
         gen_s = time.time() - t0
         h = capi.Handle(ref.encode("latin-1"), a.min_bq, THRESH["minMQ"], device=0, stream=stream.cuda_stream)
         db, keep = to_device(torch, capi, batch, dev)
