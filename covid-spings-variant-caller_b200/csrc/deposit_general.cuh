@@ -27,8 +27,11 @@ __device__ __forceinline__ void deposit_base(const TableView& tv, const DepositP
     }
     const int64_t cell = r * 4 + (gs & 3u);
     atomicAdd(&tv.planes[pl][cell], 1u);
-    // first-seen ordinal: an unconditional reduction (fire and forget) instead of a load the warp would wait for
-    atomicMin(&tv.first[gs >> 2][cell], ord);
+    // first-seen ordinal.  Every quality plane of a group shares ONE first-seen cell per (column, allele): at depth d
+    // an unconditional RED.MIN would put d same-address atomics per batch on it (they serialise in L2), so test first;
+    // after the first reads of a column the test fails and nothing is written
+    uint32_t* f = tv.first[gs >> 2] + cell;
+    if (__ldcg(f) > ord) atomicMin(f, ord);
 }
 
 // Walk one read (one thread).
@@ -89,15 +92,27 @@ __device__ __forceinline__ void deposit_read_general(const BatchView& b, const T
 // reference / query offsets of every op come from a warp scan, and the ops that deposit something (match runs,
 // deletions, skips) are visited by broadcasting them from their lane -- no dependent global load per op.  Inside a
 // match run the lanes stride over the bases (coalesced loads, 32 reductions in flight).
-// COMPACT: the quality test and the deposit are separated.  Lanes test one base each and append the passing ones to a
-// 64-entry ring in shared memory (`ring`, 64 x {column offset u32, query index u32, quality u8} per warp); whenever 32
-// entries are waiting they are deposited with every lane busy.  With a threshold that most bases fail (ONT at minBQ
-// 30: 85 %) the ~40-instruction deposit sequence runs once per 32 PASSING bases instead of once per 32 bases.
+// COMPACT (the warp-per-read kernel): the quality test and the deposit are separated.  Per group of 32 ops the lanes
+// test the group's query bases FOUR AT A TIME (aligned 32-bit words of the quality array, byte-parallel compare) and
+// append the passing ones, packed as (query index | quality << 24), to a 256-entry ring in shared memory; 32 entries
+// at a time are then resolved to their op with a shuffle binary search over the group's query offsets (entries in
+// soft clips and insertions are dropped there) and deposited with every lane busy.  With a threshold that most
+// bases fail (ONT at minBQ 30: 85 %) the ~70-instruction resolve-and-deposit sequence runs once per 32 PASSING
+// bases, and the test costs ~1/4 instruction per base.
+constexpr uint32_t kRingEntries = 256;
 struct WarpRing {
-    uint32_t rr[64];
-    uint32_t qx[64];
-    uint8_t q[64];
+    uint32_t e[kRingEntries];
 };
+
+// 0x80 in every byte of w that is >= min_bq (any min_bq)
+__device__ __forceinline__ uint32_t ge_flags4(uint32_t w, int min_bq) {
+    if (min_bq <= 0) return 0x80808080u;
+    if (min_bq <= 128) return (((w & 0x7F7F7F7Fu) + (uint32_t)(0x80 - min_bq) * 0x01010101u) | w) & 0x80808080u;
+    uint32_t f = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) f |= (int)((w >> (8 * k)) & 255u) >= min_bq ? (0x80u << (8 * k)) : 0u;
+    return f;
+}
 
 template <bool COMPACT>
 __device__ __forceinline__ void deposit_read_warp_impl(const BatchView& b, const TableView& tv, const DepositParams& dp,
@@ -138,6 +153,7 @@ __device__ __forceinline__ void deposit_read_warp_impl(const BatchView& b, const
     }
     const uint32_t ord = dp.ord_base + i;
     uint32_t ring_head = 0, ring_n = 0;
+    const bool wide = COMPACT && lq < (1u << 24);           // ring entries carry 24-bit query indices
     uint32_t r_base = 0, q_base = 0;                         // offsets from pos / from the first query base
     for (uint32_t g0 = c0; g0 < c1; g0 += 32) {
         const uint32_t c = g0 == c0 ? cg_first : (g0 + lane < c1 ? b.cigar[g0 + lane] : 0u);
@@ -153,7 +169,8 @@ __device__ __forceinline__ void deposit_read_warp_impl(const BatchView& b, const
         }
         const uint32_t r_off = r_base + r_in - rl, q_off = q_base + q_in - ql;
         // ops with something to deposit
-        uint32_t work = __ballot_sync(0xFFFFFFFFu, len != 0 && (op_is_match(op) || op == 2 || op == 3));
+        // (with the word-parallel test below, match runs are not visited one by one)
+        uint32_t work = __ballot_sync(0xFFFFFFFFu, len != 0 && ((!wide && op_is_match(op)) || op == 2 || op == 3));
         while (work) {
             const int k = __ffs(work) - 1;
             work &= work - 1;
@@ -162,39 +179,13 @@ __device__ __forceinline__ void deposit_read_warp_impl(const BatchView& b, const
             const uint32_t qi = __shfl_sync(0xFFFFFFFFu, q_off, k);
             const uint32_t opk = ck & 15u, lenk = ck >> 4;
             if (op_is_match(opk)) {
-                if (COMPACT) {
-                    const uint32_t r_rel = (uint32_t)(r - pos);
-                    for (uint32_t j0 = 0; j0 < lenk; j0 += 32) {
-                        const uint32_t j = j0 + lane;
-                        uint32_t q = 0;
-                        if (j < lenk) q = qual[qi + j];
-                        const bool pass = j < lenk && (int)q >= dp.min_bq;
-                        const uint32_t m = __ballot_sync(0xFFFFFFFFu, pass);
-                        if (m == 0) continue;
-                        if (pass) {
-                            const uint32_t slot = (ring_head + ring_n + __popc(m & ((1u << lane) - 1u))) & 63u;
-                            ring->rr[slot] = r_rel + j; ring->qx[slot] = qi + j; ring->q[slot] = (uint8_t)q;
-                        }
-                        ring_n += __popc(m);
-                        if (ring_n >= 32) {
-                            __syncwarp();
-                            const uint32_t e = (ring_head + lane) & 63u;
-                            const uint32_t qx = ring->qx[e];
-                            const uint32_t byte = seq[qx >> 1];
-                            deposit_base(tv, dp, pos + ring->rr[e], (qx & 1u) ? (byte & 15u) : (byte >> 4), ring->q[e], ord);
-                            ring_head = (ring_head + 32) & 63u;
-                            ring_n -= 32;
-                            __syncwarp();
-                        }
-                    }
-                } else {
-                    for (uint32_t j = lane; j < lenk; j += 32) {
-                        const uint32_t q = qual[qi + j];
-                        if ((int)q < dp.min_bq) continue;
-                        const uint32_t byte = seq[(qi + j) >> 1];
-                        const uint32_t nib = ((qi + j) & 1u) ? (byte & 15u) : (byte >> 4);
-                        deposit_base(tv, dp, r + j, nib, q, ord);
-                    }
+                if (wide) continue;                          // handled below for the whole group at once
+                for (uint32_t j = lane; j < lenk; j += 32) {
+                    const uint32_t q = qual[qi + j];
+                    if ((int)q < dp.min_bq) continue;
+                    const uint32_t byte = seq[(qi + j) >> 1];
+                    const uint32_t nib = ((qi + j) & 1u) ? (byte & 15u) : (byte >> 4);
+                    deposit_base(tv, dp, r + j, nib, q, ord);
                 }
             } else if (!dp.replay) {
                 // deletion / ref-skip entries are kept iff the NEXT query base passes the quality rule
@@ -204,18 +195,69 @@ __device__ __forceinline__ void deposit_read_warp_impl(const BatchView& b, const
                     for (uint32_t j = lane; j < lenk; j += 32) atomicAdd(&tv.dels[r + j], 1u);
             }
         }
-        r_base += __shfl_sync(0xFFFFFFFFu, r_in, 31);
-        q_base += __shfl_sync(0xFFFFFFFFu, q_in, 31);
-    }
-    if (COMPACT) {                                           // what is left in the ring (< 32 entries)
-        __syncwarp();
-        if (lane < ring_n) {
-            const uint32_t e = (ring_head + lane) & 63u;
-            const uint32_t qx = ring->qx[e];
-            const uint32_t byte = seq[qx >> 1];
-            deposit_base(tv, dp, pos + ring->rr[e], (qx & 1u) ? (byte & 15u) : (byte >> 4), ring->q[e], ord);
+        const uint32_t r_tot = __shfl_sync(0xFFFFFFFFu, r_in, 31), q_tot = __shfl_sync(0xFFFFFFFFu, q_in, 31);
+        if (wide && __any_sync(0xFFFFFFFFu, len != 0 && op_is_match(op))) {
+            // query offsets of the group's ops, padded with +inf, for the op lookup
+            const uint32_t q_key = g0 + lane < c1 ? q_off : 0xFFFFFFFFu;
+            // resolve and deposit the first `cnt` (<= 32) entries of the ring
+            auto flush = [&](uint32_t cnt) {
+                uint32_t x = 0, q = 0;
+                if (lane < cnt) { const uint32_t e = ring->e[(ring_head + lane) & (kRingEntries - 1)]; x = e & 0xFFFFFFu; q = e >> 24; }
+                else x = q_base;                              // idle lanes take part in the shuffles
+                uint32_t k = 0;                               // number of ops with q_off <= x  (>= 1)
+#pragma unroll
+                for (int st = 16; st >= 1; st >>= 1)
+                    if (__shfl_sync(0xFFFFFFFFu, q_key, (int)(k + st - 1)) <= x) k += st;
+                if (__shfl_sync(0xFFFFFFFFu, q_key, (int)k) <= x) ++k;
+                const int ko = (int)k - 1;
+                const uint32_t co = __shfl_sync(0xFFFFFFFFu, c, ko);
+                const uint32_t qo = __shfl_sync(0xFFFFFFFFu, q_off, ko), ro = __shfl_sync(0xFFFFFFFFu, r_off, ko);
+                if (lane < cnt && op_is_match(co & 15u)) {
+                    const uint32_t byte = seq[x >> 1];
+                    deposit_base(tv, dp, pos + (int64_t)ro + (x - qo), (x & 1u) ? (byte & 15u) : (byte >> 4), q, ord);
+                }
+                ring_head = (ring_head + cnt) & (kRingEntries - 1);
+                ring_n -= cnt;
+            };
+            // the group's query bases [q_base, q_base + q_tot) as aligned words of the quality array
+            const uint32_t mis = (uint32_t)(qb & 3u);                       // the read starts `mis` bytes into a word
+            const uint32_t* qw = reinterpret_cast<const uint32_t*>(b.qual + (qb - mis));
+            const uint32_t w_end = (mis + q_base + q_tot + 3u) >> 2;
+            const uint32_t lt = (1u << lane) - 1u;
+            for (uint32_t w0 = (mis + q_base) >> 2; w0 < w_end; w0 += 32) {
+                const uint32_t w = w0 + lane;
+                uint32_t f = 0, word = 0;
+                const int32_t x0 = (int32_t)(w << 2) - (int32_t)mis;          // query index of byte 0 (may be < q_base)
+                if (w < w_end) {
+                    word = qw[w];
+                    const int32_t lo = max((int32_t)q_base - x0, 0), hi = min((int32_t)(q_base + q_tot) - x0, 4);
+                    if (hi > lo) f = ge_flags4(word, dp.min_bq) & (0xFFFFFFFFu << (8 * lo)) & (0xFFFFFFFFu >> (8 * (4 - hi)));
+                }
+                // exclusive prefix of the per-lane counts (0..4) from three ballots
+                const uint32_t cnt = __popc(f);
+                const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, cnt & 1u), b1 = __ballot_sync(0xFFFFFFFFu, cnt & 2u),
+                               b2 = __ballot_sync(0xFFFFFFFFu, cnt & 4u);
+                const uint32_t total = __popc(b0) + 2u * __popc(b1) + 4u * __popc(b2);
+                if (total == 0) continue;
+                uint32_t slot = ring_head + ring_n + __popc(b0 & lt) + 2u * __popc(b1 & lt) + 4u * __popc(b2 & lt);
+                while (f) {
+                    const int bb = (__ffs(f) - 1) >> 3;
+                    f &= f - 1;
+                    ring->e[slot & (kRingEntries - 1)] = (uint32_t)(x0 + bb) | (((word >> (8 * bb)) & 255u) << 24);
+                    ++slot;
+                }
+                ring_n += total;
+                __syncwarp();
+                while (ring_n >= 32) flush(32);
+                __syncwarp();
+            }
+            // entries are resolved against THIS group's ops: nothing may stay in the ring
+            __syncwarp();
+            if (ring_n) flush(ring_n);
+            __syncwarp();
         }
-        __syncwarp();
+        r_base += r_tot;
+        q_base += q_tot;
     }
 }
 
