@@ -90,7 +90,7 @@ struct PlaneConst {
 // shuffles.  With LPP > 1 (wide quality alphabets: ONT) lane `sub` of a slot takes the planes k = sub (mod LPP) and the
 // partial products are multiplied together by a shuffle tree first.  Alleles of the rare groups 1..3 are handled by
 // the same lanes in turn.
-template <int LPP>
+template <int LPP, int NG>      // NG = 1: only the A/C/G/T group has planes (the usual case), 4: all groups
 __global__ void __launch_bounds__(kGenoThreads) k_genotype(GenoParams gp, const uint32_t* const* __restrict__ plane_ptrs,
                                                            const PlaneConst* __restrict__ pconst,
                                                            const uint32_t* __restrict__ dels,
@@ -111,12 +111,12 @@ __global__ void __launch_bounds__(kGenoThreads) k_genotype(GenoParams gp, const 
     const bool live = p < gp.p1;
     const int64_t pc = live ? p : gp.p1 - 1;         // clamp: every lane takes part in the shuffles
 
-    AlleleStat st[4];
+    AlleleStat st[NG];
 #pragma unroll
-    for (int g = 0; g < 4; ++g) { st[g].pe = dd_zero(); st[g].p1 = dd_zero(); st[g].es = 0.0; st[g].ad = 0; }
+    for (int g = 0; g < NG; ++g) { st[g].pe = dd_zero(); st[g].p1 = dd_zero(); st[g].es = 0.0; st[g].ad = 0; }
 
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
+    for (int g = 0; g < NG; ++g) {
         // counts of up to kGenoBatch planes are requested together (one memory latency per batch, not per plane)
         for (int k0 = gp.grp_begin[g] + sub; k0 < gp.grp_begin[g + 1]; k0 += kGenoBatch * LPP) {
             uint32_t cnt[kGenoBatch];
@@ -148,12 +148,12 @@ __global__ void __launch_bounds__(kGenoThreads) k_genotype(GenoParams gp, const 
         }
     }
     // ---- combine the (up to 16) alleles of the position: log2 of the product of e over ALL of them
-    const bool has_other = gp.grp_begin[4] > gp.grp_begin[1];
+    constexpr bool has_other = NG > 1;
     DD own = st[0].pe;
     uint32_t own_ad = st[0].ad;
     if (has_other) {
 #pragma unroll
-        for (int g = 1; g < 4; ++g) { own = dd_add(own, st[g].pe); own_ad += st[g].ad; }
+        for (int g = 1; g < NG; ++g) { own = dd_add(own, st[g].pe); own_ad += st[g].ad; }
     }
     DD tot = dd_add(own, dd_shfl_xor(own, 1));
     tot = dd_add(tot, dd_shfl_xor(tot, 2));
@@ -161,10 +161,10 @@ __global__ void __launch_bounds__(kGenoThreads) k_genotype(GenoParams gp, const 
     dsum += __shfl_xor_sync(0xFFFFFFFFu, dsum, 2);
     const uint64_t depth = (uint64_t)dels[pc] + dsum;
     // L(a) = prod(1-e | a) * prod over b != a of prod(e | b)      (utils.py:16-24)
-    double L[4];
+    double L[NG];
     double Ssum = 0.0;
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
+    for (int g = 0; g < NG; ++g) {
         L[g] = 0.0;
         if ((g == 0 || has_other) && st[g].ad) {
             L[g] = dd_exp2(dd_add(st[g].p1, dd_sub(tot, st[g].pe)));
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(kGenoThreads) k_genotype(GenoParams gp, const 
     const bool all = gp.flags & 1u;
     const double ddepth = (double)depth;
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
+    for (int g = 0; g < NG; ++g) {
         if (!((g == 0 || has_other) && st[g].ad)) continue;
         const uint32_t gs = (uint32_t)(g * 4 + slot);
         const uint32_t nib = gs_nibble(gs);

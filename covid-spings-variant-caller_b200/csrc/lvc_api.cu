@@ -732,7 +732,9 @@ static int genotype_enqueue(lvc_handle* h, int64_t min_total_depth, int64_t min_
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        auto kern = lpp == 8 ? k_genotype<8> : k_genotype<1>;
+        const bool other_groups = grp_begin[4] > grp_begin[1];
+        auto kern = lpp == 8 ? (other_groups ? k_genotype<8, 4> : k_genotype<8, 1>)
+                             : (other_groups ? k_genotype<1, 4> : k_genotype<1, 1>);
         CU(cudaLaunchKernelEx(&cfg, kern, gp, (const uint32_t* const*)h->g_order_ptrs.p,
                               (const PlaneConst*)h->g_pconst.p, (const uint32_t*)h->d_dels, (const uint8_t*)h->d_ref,
                               (const uint32_t* const*)h->d_first_arr, h->d_out_depth, h->d_out_ad, h->d_out_lik,
