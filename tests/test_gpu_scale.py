@@ -169,3 +169,16 @@ def test_pinned_host_buffers_are_read_in_place(lib):
     co.process(b)
     assert np.array_equal(tabs[1][0], co.ad.astype(np.uint64))
     assert np.array_equal(tabs[1][2][tabs[1][0] > 0], co.first[co.ad > 0])
+
+
+def test_long_reads_with_many_cigar_ops(lib):
+    """reads with 121 and 401 CIGAR ops (several groups of 32 ops in the warp-per-read kernel, ring flushes at every
+    group boundary), two live batches, every kernel selection, low and high base-quality thresholds"""
+    from lvc_b200 import synth
+    ref = synth.random_reference(12000, 77)
+    b1 = synth.ont_batch_fast(501, ref, depth=40.0, ref_span=2400, n_runs=60)
+    b2 = synth.ont_batch_fast(502, ref, depth=25.0, ref_span=6000, n_runs=200)
+    assert b1.n_cigar == 121 * b1.n_reads and b2.n_cigar == 401 * b2.n_reads
+    for impl in (0, 3, 4):
+        check_against_c_oracle(ref, [b1, b2], dict(minBQ=20, minMQ=20, minDP=5, minAD=2, ratio=0.05), impl)
+    check_against_c_oracle(ref, [b2, b1], dict(minBQ=0, minMQ=0, minDP=1, minAD=1, ratio=0.0), 0)
