@@ -438,7 +438,7 @@ k_deposit_tile4(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
                     };
                     // two groups per iteration, loaded then reduced.  (A software-pipelined version with the next two
                     // groups in flight costs 12 more live registers under the 48-register cap and measured 4 % slower:
-                    // with 5 CTAs per SM the load latency is covered by the other CTAs.)
+                    // with 5 CTAs per SM the load latency is covered by the other CTAs.  One group per iteration is 8 % slower.)
                     if (warp == 0 && cmin < cmax) slab_setup(cmin);
                     for (uint32_t g = tid; g < n_grp; g += 2 * kTileThreads) {
                         const bool hasB = g + kTileThreads < n_grp;
@@ -497,11 +497,12 @@ k_deposit_tile4(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
                             acc4[0][2] += (k0 >> 2) & 0x11111111u; acc4[1][2] += (k1 >> 2) & 0x11111111u;
                             acc4[0][3] += (k0 >> 3) & 0x11111111u; acc4[1][3] += (k1 >> 3) & 0x11111111u;
                         };
+                        // one unit per iteration: two in flight cost 8 more live registers under the 48-register cap and
+                        // measured 2 % slower
 #pragma unroll 1
-                        for (uint32_t r = ra + sread; r < rb; r += 32) {
-                            const PassUnit4 uA = unit_load(r), uB = unit_load(r + 16);
+                        for (uint32_t r = ra + sread; r < rb; r += 16) {
+                            const PassUnit4 uA = unit_load(r);
                             consume(uA);
-                            consume(uB);
                         }
                         // widen to 8-bit fields: v[word][parity][allele]; parity 0 = even columns of the word
                         uint32_t v16[16];
