@@ -123,15 +123,34 @@ __device__ __forceinline__ void deposit_read_warp_impl(const BatchView& b, const
     const uint64_t qb = b.seq_off[i];
     // group 0 of the ops (all of them for reads with <= 32 ops) stays in registers
     const uint32_t cg_first = c0 + lane < c1 ? b.cigar[c0 + lane] : 0u;       // padding: a match of length 0
-    // totals: reference length and l_qseq.  Per-op lengths are < 2^28, so 32 of them cannot wrap 64 bits; a read
+    // scan of group 0 (inclusive prefix of the reference / query lengths), needed below anyway
+    uint32_t r_in0, q_in0;
+    {
+        const uint32_t op = cg_first & 15u, len = cg_first >> 4;
+        r_in0 = op_consumes_ref(op) ? len : 0u;
+        q_in0 = op_consumes_query(op) ? len : 0u;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t ur = __shfl_up_sync(0xFFFFFFFFu, r_in0, d);
+            const uint32_t uq = __shfl_up_sync(0xFFFFFFFFu, q_in0, d);
+            if ((int)lane >= d) { r_in0 += ur; q_in0 += uq; }
+        }
+    }
+    // totals: reference length and l_qseq.  One group of ops whose lengths are all < 2^26 (any real read): the scan
+    // has them.  Otherwise sum group by group (per-op lengths are < 2^28, so 32 of them cannot wrap 64 bits).  A read
     // whose reference span does not fit 31 bits cannot lie inside any contig and is reported as out of range.
     uint64_t rlen = 0, lq64 = 0;
-    for (uint32_t g0 = c0; g0 < c1; g0 += 32) {
-        const uint32_t c = g0 == c0 ? cg_first : (g0 + lane < c1 ? b.cigar[g0 + lane] : 0u);
-        const uint32_t op = c & 15u, len = c >> 4;
-        const uint32_t rl = op_consumes_ref(op) ? len : 0u, ql = op_consumes_query(op) ? len : 0u;
-        rlen += (uint64_t)__reduce_add_sync(0xFFFFFFFFu, rl >> 8) * 256u + __reduce_add_sync(0xFFFFFFFFu, rl & 255u);
-        lq64 += (uint64_t)__reduce_add_sync(0xFFFFFFFFu, ql >> 8) * 256u + __reduce_add_sync(0xFFFFFFFFu, ql & 255u);
+    if (c1 - c0 <= 32u && !__any_sync(0xFFFFFFFFu, (cg_first >> 4) >= (1u << 26))) {
+        rlen = __shfl_sync(0xFFFFFFFFu, r_in0, 31);
+        lq64 = __shfl_sync(0xFFFFFFFFu, q_in0, 31);
+    } else {
+        for (uint32_t g0 = c0; g0 < c1; g0 += 32) {
+            const uint32_t c = g0 == c0 ? cg_first : (g0 + lane < c1 ? b.cigar[g0 + lane] : 0u);
+            const uint32_t op = c & 15u, len = c >> 4;
+            const uint32_t rl = op_consumes_ref(op) ? len : 0u, ql = op_consumes_query(op) ? len : 0u;
+            rlen += (uint64_t)__reduce_add_sync(0xFFFFFFFFu, rl >> 8) * 256u + __reduce_add_sync(0xFFFFFFFFu, rl & 255u);
+            lq64 += (uint64_t)__reduce_add_sync(0xFFFFFFFFu, ql >> 8) * 256u + __reduce_add_sync(0xFFFFFFFFu, ql & 255u);
+        }
     }
     if (rlen == 0) return;   // no M/D/N/=/X op: htslib asserts on such records; skipped
     if (pos < 0 || rlen > 0x7FFFFFFFull || lq64 > 0xFFFFFFFFull || pos + (int64_t)rlen > tv.G) {
@@ -160,17 +179,26 @@ __device__ __forceinline__ void deposit_read_warp_impl(const BatchView& b, const
         const uint32_t op = c & 15u, len = c >> 4;
         const uint32_t rl = op_consumes_ref(op) ? len : 0u, ql = op_consumes_query(op) ? len : 0u;
         // inclusive prefix of the reference / query lengths inside the group
-        uint32_t r_in = rl, q_in = ql;
+        uint32_t r_in = r_in0, q_in = q_in0;
+        if (g0 != c0) {
+            r_in = rl; q_in = ql;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t ur = __shfl_up_sync(0xFFFFFFFFu, r_in, d);
-            const uint32_t uq = __shfl_up_sync(0xFFFFFFFFu, q_in, d);
-            if ((int)lane >= d) { r_in += ur; q_in += uq; }
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t ur = __shfl_up_sync(0xFFFFFFFFu, r_in, d);
+                const uint32_t uq = __shfl_up_sync(0xFFFFFFFFu, q_in, d);
+                if ((int)lane >= d) { r_in += ur; q_in += uq; }
+            }
         }
         const uint32_t r_off = r_base + r_in - rl, q_off = q_base + q_in - ql;
-        // ops with something to deposit
-        // (with the word-parallel test below, match runs are not visited one by one)
-        uint32_t work = __ballot_sync(0xFFFFFFFFu, len != 0 && ((!wide && op_is_match(op)) || op == 2 || op == 3));
+        if (wide && !dp.replay && len != 0 && (op == 2 || op == 3)) {
+            // deletion / ref-skip entries, every such op of the group in its own lane: kept iff the NEXT query base
+            // passes the quality rule (pysam pileup_base_qual_skip on qpos = y; 0 if qpos >= l_qseq) -- SURVEY B3
+            const uint32_t q = (q_off < lq) ? (uint32_t)qual[q_off] : 0u;
+            if ((int)q >= dp.min_bq)
+                for (uint32_t j = 0; j < len; ++j) atomicAdd(&tv.dels[pos + r_off + j], 1u);
+        }
+        // without the word-parallel path: the ops with something to deposit, one after the other
+        uint32_t work = __ballot_sync(0xFFFFFFFFu, !wide && len != 0 && (op_is_match(op) || op == 2 || op == 3));
         while (work) {
             const int k = __ffs(work) - 1;
             work &= work - 1;
@@ -179,7 +207,6 @@ __device__ __forceinline__ void deposit_read_warp_impl(const BatchView& b, const
             const uint32_t qi = __shfl_sync(0xFFFFFFFFu, q_off, k);
             const uint32_t opk = ck & 15u, lenk = ck >> 4;
             if (op_is_match(opk)) {
-                if (wide) continue;                          // handled below for the whole group at once
                 for (uint32_t j = lane; j < lenk; j += 32) {
                     const uint32_t q = qual[qi + j];
                     if ((int)q < dp.min_bq) continue;
