@@ -223,14 +223,19 @@ __device__ __forceinline__ void deposit_read_warp_impl(const BatchView& b, const
             }
         }
         const uint32_t r_tot = __shfl_sync(0xFFFFFFFFu, r_in, 31), q_tot = __shfl_sync(0xFFFFFFFFu, q_in, 31);
-        if (wide && __any_sync(0xFFFFFFFFu, len != 0 && op_is_match(op))) {
+        const uint32_t match_ops = __ballot_sync(0xFFFFFFFFu, wide && len != 0 && op_is_match(op));
+        if (match_ops) {
+            // only the query bases between the first and the last match run of the group are tested (soft clips at the
+            // ends of the read would be dropped at the op lookup anyway)
+            const uint32_t t_lo = __shfl_sync(0xFFFFFFFFu, q_off, __ffs(match_ops) - 1);
+            const uint32_t t_hi = __shfl_sync(0xFFFFFFFFu, q_off + ql, 31 - __clz(match_ops));
             // query offsets of the group's ops, padded with +inf, for the op lookup
             const uint32_t q_key = g0 + lane < c1 ? q_off : 0xFFFFFFFFu;
             // resolve and deposit the first `cnt` (<= 32) entries of the ring
             auto flush = [&](uint32_t cnt) {
                 uint32_t x = 0, q = 0;
                 if (lane < cnt) { const uint32_t e = ring->e[(ring_head + lane) & (kRingEntries - 1)]; x = e & 0xFFFFFFu; q = e >> 24; }
-                else x = q_base;                              // idle lanes take part in the shuffles
+                else x = t_lo;                                // idle lanes take part in the shuffles
                 uint32_t k = 0;                               // number of ops with q_off <= x  (>= 1)
 #pragma unroll
                 for (int st = 16; st >= 1; st >>= 1)
@@ -246,18 +251,18 @@ __device__ __forceinline__ void deposit_read_warp_impl(const BatchView& b, const
                 ring_head = (ring_head + cnt) & (kRingEntries - 1);
                 ring_n -= cnt;
             };
-            // the group's query bases [q_base, q_base + q_tot) as aligned words of the quality array
+            // the query bases [t_lo, t_hi) as aligned words of the quality array
             const uint32_t mis = (uint32_t)(qb & 3u);                       // the read starts `mis` bytes into a word
             const uint32_t* qw = reinterpret_cast<const uint32_t*>(b.qual + (qb - mis));
-            const uint32_t w_end = (mis + q_base + q_tot + 3u) >> 2;
+            const uint32_t w_end = (mis + t_hi + 3u) >> 2;
             const uint32_t lt = (1u << lane) - 1u;
-            for (uint32_t w0 = (mis + q_base) >> 2; w0 < w_end; w0 += 32) {
+            for (uint32_t w0 = (mis + t_lo) >> 2; w0 < w_end; w0 += 32) {
                 const uint32_t w = w0 + lane;
                 uint32_t f = 0, word = 0;
-                const int32_t x0 = (int32_t)(w << 2) - (int32_t)mis;          // query index of byte 0 (may be < q_base)
+                const int32_t x0 = (int32_t)(w << 2) - (int32_t)mis;          // query index of byte 0 (may be < t_lo)
                 if (w < w_end) {
                     word = qw[w];
-                    const int32_t lo = max((int32_t)q_base - x0, 0), hi = min((int32_t)(q_base + q_tot) - x0, 4);
+                    const int32_t lo = max((int32_t)t_lo - x0, 0), hi = min((int32_t)t_hi - x0, 4);
                     if (hi > lo) f = ge_flags4(word, dp.min_bq) & (0xFFFFFFFFu << (8 * lo)) & (0xFFFFFFFFu >> (8 * (4 - hi)));
                 }
                 // exclusive prefix of the per-lane counts (0..4) from three ballots
