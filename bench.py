@@ -175,7 +175,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=5)
-    ap.add_argument("--kernel-impl", type=int, default=0, help="0 auto (=4), 1 general kernel, 2 tiled kernel (raw TMA staging), 4 tiled kernel (4-bit keys)")
+    ap.add_argument("--kernel-impl", type=int, default=0, help="0 auto (4 for short reads, 3 for long reads), 1 general kernel, 2 tiled kernel (raw TMA staging), 3 warp per read, 4 tiled kernel (4-bit keys)")
     ap.add_argument("--n-pairs", type=int, default=996_767)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
