@@ -183,6 +183,59 @@ k_deposit_tile4(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
                 if (hd.pos < 0 || (int64_t)hd.pos + l0 > tv.G) atomicAdd(&tv.status[ST_RANGE_ERR], 1u);
                 else { nr = 1; run_pos[0] = hd.pos; run_len[0] = l0; run_q[0] = 0; rspan = l0; }
             }
+        } else if (__all_sync(0xFFFFFFFFu, !rpass || (hd.nc >= 1u && hd.nc <= 3u && (hd.keep & 2u) &&
+                                                        (hd.so1 - hd.so) <= kMaxReadBytes))) {
+            // second warp-uniform shortcut: at most 3 CIGAR ops per read (one indel or soft clips), all of them
+            // already in registers: straight-line code, same results as the general walk below
+            if (rpass) {
+                const bool p1 = hd.nc > 1u, p2 = hd.nc > 2u;
+                const uint32_t o0 = hd.cg0 & 15u, o1 = hd.cg1 & 15u, o2 = hd.cg2 & 15u;
+                const uint32_t n0 = hd.cg0 >> 4, n1 = p1 ? hd.cg1 >> 4 : 0u, n2 = p2 ? hd.cg2 >> 4 : 0u;
+                const bool m0 = op_is_match(o0), m1 = p1 && op_is_match(o1), m2 = p2 && op_is_match(o2);
+                const bool d0 = o0 == 2 || o0 == 3, d1 = p1 && (o1 == 2 || o1 == 3), d2 = p2 && (o2 == 2 || o2 == 3);
+                const uint32_t qc0 = op_consumes_query(o0) ? n0 : 0u, qc1 = (p1 && op_consumes_query(o1)) ? n1 : 0u,
+                               qc2 = (p2 && op_consumes_query(o2)) ? n2 : 0u;
+                const uint32_t rc0 = (m0 || d0) ? n0 : 0u, rc1 = (m1 || d1) ? n1 : 0u, rc2 = (m2 || d2) ? n2 : 0u;
+                const uint32_t qo1 = qc0, qo2 = qc0 + qc1, lq = qo2 + qc2;
+                const uint32_t ro1 = rc0, ro2 = rc0 + rc1;
+                rspan = ro2 + rc2;
+                // match runs: a run starts at a match op that does not follow a match op
+                const bool s0 = m0, s1 = m1 && !m0, s2 = m2 && !m1;
+                const uint32_t len2 = n2, len1 = n1 + (m2 ? n2 : 0u), len0 = n0 + (m1 ? len1 : 0u);
+                nr = (uint32_t)s0 + (uint32_t)s1 + (uint32_t)s2;
+                if (s0) { run_pos[0] = hd.pos; run_len[0] = len0; run_q[0] = 0; }
+                else if (s1) { run_pos[0] = hd.pos + (int32_t)ro1; run_len[0] = len1; run_q[0] = qo1; }
+                else if (s2) { run_pos[0] = hd.pos + (int32_t)ro2; run_len[0] = len2; run_q[0] = qo2; }
+                if (s0 && s2) { run_pos[1] = hd.pos + (int32_t)ro2; run_len[1] = len2; run_q[1] = qo2; }
+                // deletion / ref-skip entries, in op order; their quality (the NEXT query base, 0 past the end) is
+                // requested here and tested where the entries are deposited
+                const uint32_t ndel = (uint32_t)d0 + (uint32_t)d1 + (uint32_t)d2;
+                bool tileable = ndel <= (uint32_t)kMaxDelsPerRead;
+                if (tileable && ndel) {
+                    const uint8_t* qrd = b.qual + so0 + so_rel;
+                    if (d0) { del_pos[0] = hd.pos; del_len[0] = n0; del_q[0] = 0u < lq ? (uint32_t)qrd[0] : 0u; nd = 1; }
+                    if (d1) {
+                        const uint32_t qv = qo1 < lq ? (uint32_t)qrd[qo1] : 0u;
+                        if (nd == 0) { del_pos[0] = hd.pos + (int32_t)ro1; del_len[0] = n1; del_q[0] = qv; }
+                        else { del_pos[1] = hd.pos + (int32_t)ro1; del_len[1] = n1; del_q[1] = qv; }
+                        ++nd;
+                    }
+                    if (d2) {
+                        const uint32_t qv = qo2 < lq ? (uint32_t)qrd[qo2] : 0u;
+                        if (nd == 0) { del_pos[0] = hd.pos + (int32_t)ro2; del_len[0] = n2; del_q[0] = qv; }
+                        else { del_pos[1] = hd.pos + (int32_t)ro2; del_len[1] = n2; del_q[1] = qv; }
+                        ++nd;
+                    }
+                }
+                bool any_ref = m0 || m1 || m2 || d0 || d1 || d2;
+                if (tileable && any_ref && (hd.pos < 0 || (int64_t)hd.pos + rspan > tv.G)) {
+                    atomicAdd(&tv.status[ST_RANGE_ERR], 1u);
+                    nr = 0; nd = 0; rspan = 0; any_ref = false;
+                }
+                if ((nr >= 1 && run_len[0] > 65535u) || (nr >= 2 && run_len[1] > 65535u)) tileable = false;
+                if (!tileable) { defer = any_ref; nr = 0; nd = 0; rspan = 0; }
+                else if (!any_ref) { nr = 0; nd = 0; rspan = 0; }
+            }
         } else if (rpass) {
             bool tileable = hd.nc <= (uint32_t)kMaxCigarTile && hd.nc > 0 && (hd.so1 - hd.so) <= kMaxReadBytes &&
                             (hd.keep & 2u);
