@@ -180,3 +180,51 @@ def test_halo_exchange_leaves_every_owner_with_the_full_history_of_its_slice(lib
         assert not tabs["covdiff"][:p0].any() and not tabs["covdiff"][hi:].any()
         assert sent < full_bytes                                        # a halo, not the table
     assert np.array_equal(total_cd, want_cd)
+
+
+def test_halo_plan_and_touched_ranges(lib, golden_synth):
+    """pure host logic of the halo exchange: every touched column outside a rank's own slice is sent to exactly its
+    owner, nothing inside the own slice is sent, and the plan is empty when chunks stay inside their slices"""
+    from lvc_b200 import packing, dist as ldist
+    b = packing.pack_reads(rows_to_tuples(golden_synth["amplicon_like"]["reads"]), 0)
+    G = len(golden_synth["amplicon_like"]["ref"])
+    for world in (2, 3, 5):
+        shards = ldist.shard_reads(b, world)
+        touched = ldist.touched_ranges(b, shards)
+        rl = ldist.ref_lengths(b)
+        for (a, c), (lo, hi) in zip(shards, touched):
+            if c > a:
+                assert lo == int(b.pos[a]) and hi == int((b.pos[a:c].astype(np.int64) + rl[a:c]).max())
+        plan = ldist.halo_plan(G, world, touched)
+        for src, (lo, hi) in enumerate(touched):
+            cols = np.zeros(G, dtype=np.int32)
+            for (s, d), (x, y) in plan.items():
+                if s == src:
+                    p0, p1 = ldist.position_slice(G, world, d)
+                    assert d != src and p0 <= x < y <= p1
+                    cols[x:y] += 1
+            own0, own1 = ldist.position_slice(G, world, src)
+            want = np.zeros(G, dtype=np.int32)
+            want[lo:hi] = 1
+            want[own0:own1] = 0
+            assert np.array_equal(cols, want)
+    # chunks that stay inside their own slices: nothing to exchange
+    assert ldist.halo_plan(100, 2, [(0, 50), (50, 100)]) == {}
+    assert ldist.halo_plan(100, 2, [(0, 60), (50, 100)]) == {(0, 1): (50, 60)}
+
+
+def test_ont_batch_fast_is_deterministic_and_well_formed(lib):
+    from lvc_b200 import synth, packing
+    ref = synth.random_reference(5000, 5)
+    a = synth.ont_batch_fast(11, ref, depth=20.0)
+    b = synth.ont_batch_fast(11, ref, depth=20.0)
+    for f in ("pos", "flag", "mapq", "keep", "cigar_off", "cigar", "seq_off", "seq4", "qual"):
+        assert np.array_equal(getattr(a, f), getattr(b, f)), f
+    n = a.n_reads
+    assert n == round(5000 * 20.0 / 400) and a.n_cigar == 21 * n
+    assert (np.diff(a.pos[:n]) >= 0).all()
+    lq = packing.query_lengths(a.cigar_off, a.cigar)
+    assert (np.diff(a.seq_off.astype(np.int64)) == lq + (lq & 1)).all()
+    from lvc_b200.dist import ref_lengths
+    assert (ref_lengths(a) == 400).all()
+    assert int(a.qual[:a.n_qual].max()) <= 90 and (a.keep[:n] & 2).all()
