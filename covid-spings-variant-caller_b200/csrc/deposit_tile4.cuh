@@ -1,15 +1,17 @@
 // Tiled deposit kernel, generation 4: 4-bit KEY staging.
 //
 // Same decomposition as deposit_tile.cuh (chunk of 256 coordinate-sorted reads per CTA, match-run table,
-// (slab, 32 runs) tasks, register SWAR counters, one RED per (column, allele) per chunk), but the staged
-// payload is no longer the raw 1.5 bytes per base: while it is copied from global memory (16-byte coalesced
-// loads) each base is reduced to a 4-bit KEY = its one-hot nibble if its quality equals the batch's primary
-// quality, else 0.  Bases with another passing quality are deposited right there (exact; their run is found by
-// binary search).  Consequences:
-//   * shared memory per CTA drops from 73 KB to 34 KB -> more resident CTAs to overlap the per-chunk latency
-//     phases (header loads -> CIGAR loads -> payload -> flush), which is what bounds the raw-staging kernel;
-//   * the inner loop touches 2 shared words per 8 bases and needs no quality arithmetic at all:
+// (32-column slab, group of kTaskRuns runs) tasks, register SWAR counters, one RED per (column, allele) per chunk),
+// but the staged payload is no longer the raw 1.5 bytes per base: while it is copied from global memory (16-byte
+// coalesced loads) each base is reduced to a 4-bit KEY = its one-hot nibble if its quality equals the batch's
+// primary quality, else 0.  Bases with another passing quality are deposited right there (exact; their run is found
+// by binary search).  Consequences:
+//   * shared memory per CTA drops from 73 KB to 36 KB and the kernel is held to 48 registers: 5 CTAs per SM overlap
+//     the per-chunk latency phases (header loads -> CIGAR loads -> payload -> flush);
+//   * the inner loop reads one packed run record and 3 shared key words per 16 bases and needs no quality arithmetic:
 //     counts for allele c are  (keys >> c) & 0x11111111  -- 8 bases per instruction.
+// Launched with programmatic stream serialization: everything before `griddepcontrol.wait` only reads the batch.
+// What was tried and measured around this kernel is listed in DESIGN.md sections 3.4 and 4.
 #pragma once
 #include "deposit_tile.cuh"
 
