@@ -497,11 +497,13 @@ k_deposit_tile4(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
                     if (warp == 0 && cmin < cmax) slab_setup(cmin);
                     for (uint32_t g = tid; g < n_grp; g += 2 * kTileThreads) {
                         const bool hasB = g + kTileThreads < n_grp;
-                        const uint4 qA = gq[g];
-                        const uint2 sA = gs[g];
+                        // streaming loads: the payload is read exactly once and should not displace the few hot lines
+                        // (plane pointers, key LUT) in the 38 KB of L1 left beside the shared memory: -4 %
+                        const uint4 qA = __ldcs(gq + g);
+                        const uint2 sA = __ldcs(gs + g);
                         uint4 qB = make_uint4(0, 0, 0, 0);
                         uint2 sB = make_uint2(0, 0);
-                        if (hasB) { qB = gq[g + kTileThreads]; sB = gs[g + kTileThreads]; }
+                        if (hasB) { qB = __ldcs(gq + g + kTileThreads); sB = __ldcs(gs + g + kTileThreads); }
                         stage_group(g, qA, sA);
                         if (hasB) stage_group(g + kTileThreads, qB, sB);
                     }
