@@ -209,3 +209,63 @@ def test_native_ingest_matches_python_readers(lib, golden_synth, tmp_path):
                   "a\t147\tc\t41\t60\t50M\t=\t11\t-80\t" + "A" * 50 + "\t" + "I" * 50 + "\n")
     with pytest.raises(packing.UnsupportedInput):
         samio.read_alignments_native(str(ov), None, 0)
+
+
+def test_native_ingest_random_files_match_python_readers(lib, tmp_path):
+    """seeded random SAM and BAM files (random CIGARs with every op, odd lengths, ambiguity codes, filtered flags,
+    unsorted SAM input, several contigs): the C++ ingest and the pure-Python readers must produce the same batch"""
+    from lvc_b200 import samio
+    rng = np.random.default_rng(20261018)
+    letters = "ACGTNRYKM"
+    ops_q = {"M": 1, "I": 1, "S": 1, "=": 1, "X": 1, "D": 0, "N": 0, "H": 0, "P": 0}
+    seen_reads = seen_kept = 0
+    for trial in range(12):
+        G = int(rng.integers(300, 3000))
+        n = int(rng.integers(1, 120))
+        rows = []
+        for i in range(n):
+            k = int(rng.integers(1, 9))
+            names = list(rng.choice(list("MIDNSHP=X"), size=k))
+            if not any(o in "MDN=X" for o in names):
+                names[int(rng.integers(0, k))] = "M"
+            lens = [int(rng.integers(1, 40)) for _ in names]
+            lq = sum(l for o, l in zip(names, lens) if ops_q[o])
+            if lq == 0:
+                names.append("M"); lens.append(5); lq = 5
+            rlen = sum(l for o, l in zip(names, lens) if o in "MDN=X")
+            pos = int(rng.integers(0, max(1, G - rlen - 1)))
+            flag = int(rng.choice([0, 16, 0, 16, 1024, 256, 4, 2048]))
+            seq = "".join(rng.choice(list(letters), size=lq, p=[.24, .24, .24, .24, .01, .01, .01, .005, .005]))
+            qual = "".join(chr(33 + int(q)) for q in rng.integers(0, 60, lq))
+            contig = "c2" if rng.random() < 0.15 else "c1"
+            rows.append((f"r{i}", flag, contig, pos, int(rng.integers(0, 61)), "".join(f"{l}{o}" for o, l in zip(names, lens)), seq, qual))
+        head = f"@HD\tVN:1.6\n@SQ\tSN:c1\tLN:{G}\n@SQ\tSN:c2\tLN:{G}\n"
+        sam = tmp_path / f"t{trial}.sam"
+        sam.write_text(head + "".join(f"{nm}\t{fl}\t{cg}\t{p + 1}\t{mq}\t{ci}\t*\t0\t0\t{s}\t{q}\n"
+                                      for nm, fl, cg, p, mq, ci, s, q in rows))
+        cases = [(str(sam), None), (str(sam), "c2")]
+        # the same reads of c1, sorted the samtools way, as a BAM
+        c1 = sorted([r for r in rows if r[2] == "c1"], key=lambda r: (r[3], (r[1] >> 4) & 1))
+        if c1:
+            opcode = {o: i for i, o in enumerate("MIDNSHP=X")}
+            import re
+            bam = str(tmp_path / f"t{trial}.bam")
+            samio.write_bam(bam, [("c1", G), ("c2", G)],
+                            [(fl, p, mq, [(opcode[o], int(l)) for l, o in re.findall(r"(\\d+)([MIDNSHP=X])", ci)], s,
+                              [ord(ch) - 33 for ch in q], nm) for nm, fl, cg, p, mq, ci, s, q in c1])
+            cases.append((bam, "c1"))
+        for path, contig in cases:
+            mq = int(rng.integers(0, 30))
+            _, pyb = samio.read_alignments(path, contig, mq)
+            nat = samio.read_alignments_native(path, contig, mq, n_threads=int(rng.integers(1, 6)))
+            nb = nat.as_readbatch()
+            assert nat.n_reads == pyb.n_reads, (path, contig)
+            for f in ("pos", "flag", "mapq", "keep", "cigar_off", "seq_off"):
+                assert getattr(nb, f).tolist() == getattr(pyb, f).tolist(), (path, contig, f)
+            assert nb.cigar[:nb.n_cigar].tolist() == pyb.cigar[:pyb.n_cigar].tolist()
+            assert nb.qual[:nb.n_qual].tolist() == pyb.qual[:pyb.n_qual].tolist()
+            assert nb.seq4[:nb.n_qual // 2].tolist() == pyb.seq4[:pyb.n_qual // 2].tolist()
+            seen_reads += nat.n_reads
+            seen_kept += int((nb.keep & 1).sum())
+            nat.close()
+    assert seen_reads > 500 and 0 < seen_kept < seen_reads          # the comparison saw real, partly filtered data
