@@ -113,7 +113,9 @@ int lvc_admit(uint32_t n_reads, const int32_t* pos, const uint16_t* flag, const 
  * input, pysam.sort's order (client_server/vc_queue.py:34).  Reads of `contig` (NULL / "" = first @SQ) are packed
  * into page-locked arrays when a CUDA device is present (lvc_push_batch then reads the payload in place), the keep
  * mask (lvc_admit + the ACGT-only hint) is filled in.  Records the path cannot reproduce (missing qualities,
- * overlapping proper pairs, CG-tag CIGARs) are refused with LVC_EINVAL and a message in errbuf. */
+ * overlapping proper pairs, CG-tag CIGARs) are refused with LVC_EINVAL and a message in errbuf.
+ * n_threads <= 0: all host threads.  The page-locked arrays of a freed lvc_reads go to a process-wide pool (at most
+ * 4 GiB parked) and are reused by later calls; LVC_INGEST_TIMING=1 in the environment prints the phase times. */
 typedef struct lvc_reads lvc_reads;
 int lvc_read_alignments(const char* path, const char* contig, int min_mapping_quality, int max_depth, int n_threads,
                         lvc_reads** out, char* errbuf, int errlen);
