@@ -3,7 +3,8 @@
 // Replaces, for this path, what pysam/htslib do for the reference before the pileup loop:
 // pysam.AlignmentFile(inputBam, 'rb') + region iteration (live_variant_caller.py:55-60) and
 // pysam.sort for SAM input (client_server/vc_queue.py:34; samtools order: position, forward strand first,
-// input order).  Included by lvc_api.cu (host code only).
+// input order).  Mate overlaps (pysam's ignore_overlaps=True default) are handled at pack time by the admission pass
+// of overlap.hpp.  Included by lvc_api.cu (host code only).
 #include <zlib.h>
 
 #include <atomic>
@@ -24,6 +25,7 @@ struct lvc_reads {
     uint32_t* cigar_off = nullptr; uint32_t* cigar = nullptr; uint64_t* seq_off = nullptr;
     uint8_t* seq4 = nullptr; uint8_t* qual = nullptr;
     bool pinned = false;
+    uint64_t overlap_pairs = 0, overlap_bases = 0;   // mate pairs / quality bytes rewritten by the overlap model
     std::vector<std::pair<void*, size_t>> allocs;    // (pointer, capacity)
 };
 
@@ -39,7 +41,6 @@ struct PhaseTimer {
         t = n;
     }
 };
-static PhaseTimer* g_timer = nullptr;
 
 // Page-locking half a gigabyte costs ~200 ms, more than inflating and packing the file: page-locked buffers of freed
 // batches are kept in a small process-wide pool and handed to the next batch (live batches arrive every few seconds
@@ -104,7 +105,9 @@ struct Rec {                 // one alignment before packing
     const uint8_t* cig;      // BAM-encoded u32 ops (little endian) -- or owned storage for SAM
     const uint8_t* seq;      // BAM 4-bit packed
     const uint8_t* qual;     // raw phred
-    int32_t next_pos; bool next_same;
+    int32_t next_pos; int8_t next_ref;      // mate: PNEXT (0-based), RNEXT 1 = this contig, 0 = another, -1 = absent
+    int32_t tlen;
+    const char* name; uint32_t l_name;       // QNAME (not terminated)
 };
 
 static inline uint32_t rd32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
@@ -131,22 +134,25 @@ struct RawBuf {
 };
 
 static std::string bgzf_inflate(const std::vector<uint8_t>& file, RawBuf& out, int n_threads) {
-    struct Blk { size_t coff, clen, uoff; uint32_t ulen; };
+    struct Blk { size_t coff, clen, uoff; uint32_t ulen, crc; };
     std::vector<Blk> blks;
     size_t i = 0, n = file.size(), total = 0;
     while (i + 18 <= n) {
         if (!(file[i] == 0x1f && file[i + 1] == 0x8b && file[i + 2] == 8 && (file[i + 3] & 4))) return fail("not a BGZF/BAM file");
         const uint16_t xlen = rd16(&file[i + 10]);
         size_t j = i + 12, xend = i + 12 + xlen;
+        if (xend > n) return fail("corrupt BGZF block header");
         int bsize = -1;
         while (j + 4 <= xend) {
             const uint16_t slen = rd16(&file[j + 2]);
             if (file[j] == 66 && file[j + 1] == 67) bsize = rd16(&file[j + 4]);
             j += 4 + slen;
         }
-        if (bsize < 0 || i + bsize + 1 > n) return fail("corrupt BGZF block header");
+        // the block (bsize + 1 bytes) holds the 12 + xlen header bytes, the deflate stream and the 8-byte trailer
+        if (bsize < 0 || i + bsize + 1 > n || (size_t)bsize + 1 < (xend - i) + 8) return fail("corrupt BGZF block header");
         const uint32_t isize = rd32(&file[i + bsize + 1 - 4]);
-        blks.push_back({xend, (size_t)(bsize + 1) - (xend - i) - 8, total, isize});
+        if (isize > 65536u) return fail("corrupt BGZF block (uncompressed size > 64 KiB)");
+        blks.push_back({xend, (size_t)(bsize + 1) - (xend - i) - 8, total, isize, rd32(&file[i + bsize + 1 - 8])});
         total += isize;
         i += bsize + 1;
     }
@@ -167,6 +173,7 @@ static std::string bgzf_inflate(const std::vector<uint8_t>& file, RawBuf& out, i
                 zs.next_out = &out[b.uoff]; zs.avail_out = b.ulen;
                 const int rc = inflate(&zs, Z_FINISH);
                 if (rc != Z_STREAM_END || zs.avail_out != 0) { bad = true; break; }
+                if ((uint32_t)crc32(crc32(0L, Z_NULL, 0), &out[b.uoff], b.ulen) != b.crc) { bad = true; break; }   // htslib checks it too
             }
         }
         inflateEnd(&zs);
@@ -176,7 +183,7 @@ static std::string bgzf_inflate(const std::vector<uint8_t>& file, RawBuf& out, i
     for (int t = 1; t < n_threads; ++t) th.emplace_back(work);
     work();
     for (auto& t : th) t.join();
-    if (bad) return fail("BGZF inflate failed");
+    if (bad) return fail("BGZF inflate failed (corrupt block or CRC mismatch)");
     return "";
 }
 
@@ -206,13 +213,9 @@ struct NotAcgtPair {
 static const NotAcgtPair kNotAcgtPair;
 #define kAsciiToNib kNib.t
 
-static bool refuse_overlap(uint16_t flag, int64_t pos, int64_t rlen, bool next_same, int64_t pnext) {
-    // proper pair whose mate starts inside this read's reference span: htslib would tweak qualities
-    return (flag & 1) && (flag & 2) && !(flag & 8) && next_same && pnext >= pos && pnext < pos + rlen;
-}
-
 // pack `recs` (already in coordinate order) into the SoA arrays of `r`
-static std::string pack(lvc_reads* r, const std::vector<Rec>& recs, int min_mapq, int max_depth, int n_threads) {
+static std::string pack(lvc_reads* r, const std::vector<Rec>& recs, int min_mapq, int max_depth, int n_threads,
+                        int overlap_model, PhaseTimer& timer) {
     const size_t n = recs.size();
     std::vector<uint64_t> coff(n + 1, 0), soff(n + 1, 0);
     for (size_t i = 0; i < n; ++i) {
@@ -235,7 +238,7 @@ static std::string pack(lvc_reads* r, const std::vector<Rec>& recs, int min_mapq
         if (attempt == 1) return fail("out of host memory");
         r->pinned = false;
     }
-    if (g_timer) g_timer->mark("offsets + alloc");
+    timer.mark("offsets + alloc");
     memset(r->seq4 + soff[n] / 2, 0, 64);
     memset(r->qual + soff[n], 0, 64);
     std::atomic<size_t> next{0};
@@ -271,13 +274,28 @@ static std::string pack(lvc_reads* r, const std::vector<Rec>& recs, int min_mapq
     for (auto& t : th) t.join();
     r->cigar_off[n] = (uint32_t)coff[n];
     r->seq_off[n] = soff[n];
-    if (g_timer) g_timer->mark("pack");
+    timer.mark("pack");
     std::vector<uint8_t> adm(n ? n : 1);
-    const int rc = lvc_admit((uint32_t)n, r->pos, r->flag, r->mapq, r->cigar_off, r->cigar, min_mapq, max_depth, adm.data());
+    // unpaired data (ONT, single-end) has nothing to pair up: skip the overlap bookkeeping altogether
+    bool any_pair = false;
+    if (overlap_model != LVC_OVERLAP_OFF)
+        for (size_t i = 0; i < n && !any_pair; ++i) any_pair = (recs[i].flag & 0x3u) == 0x3u && !(recs[i].flag & 0x8u);
+    std::vector<int32_t> mpos, tlen;
+    std::vector<int8_t> mref;
+    if (any_pair) {
+        mpos.resize(n); tlen.resize(n); mref.resize(n);
+        for (size_t i = 0; i < n; ++i) { mpos[i] = recs[i].next_pos; tlen[i] = recs[i].tlen; mref[i] = recs[i].next_ref; }
+    }
+    auto name = [&](uint32_t i) { return lvc_overlap::NameKey{recs[i].name, recs[i].l_name}; };
+    const int rc = lvc_overlap::admit_core((uint32_t)n, r->pos, r->flag, r->mapq, r->cigar_off, r->cigar, r->seq_off, r->seq4,
+                                           r->qual, name, any_pair ? mpos.data() : nullptr, any_pair ? mref.data() : nullptr,
+                                           any_pair ? tlen.data() : nullptr, min_mapq, max_depth,
+                                           any_pair ? overlap_model : LVC_OVERLAP_OFF, adm.data(), &r->overlap_pairs,
+                                           &r->overlap_bases);
     if (rc == LVC_EUNSORTED) return fail("reads are not coordinate sorted");
     if (rc) return fail("admission failed (%d)", rc);
     for (size_t i = 0; i < n; ++i) r->keep[i] |= adm[i];
-    if (g_timer) g_timer->mark("admit");
+    timer.mark("admit + overlaps");
     return "";
 }
 
@@ -291,23 +309,25 @@ static std::string validate(const Rec& x, const char* what) {
     }
     if (rl > 0 && lq != x.l_seq) return fail("%s: read at %d: CIGAR query length %llu != sequence length %u", what, x.pos, (unsigned long long)lq, x.l_seq);
     if (rl > 0 && x.l_seq && x.qual[0] == 0xFF && !(x.flag & 4)) return fail("%s: a read has no base qualities (the reference raises TypeError)", what);
-    if (refuse_overlap(x.flag, x.pos, (int64_t)rl, x.next_same, x.next_pos))
-        return fail("%s: proper pair with overlapping mates at %d; htslib's overlap quality tweak is not reproduced", what, x.pos);
     return "";
 }
 
 static std::string read_bam(lvc_reads* r, const std::vector<uint8_t>& file, const char* contig, int min_mapq, int max_depth,
-                            int n_threads, RawBuf& raw) {
+                            int n_threads, RawBuf& raw, int overlap_model, PhaseTimer& timer) {
     std::string e = bgzf_inflate(file, raw, n_threads);
     if (!e.empty()) return e;
-    if (g_timer) g_timer->mark("bgzf inflate");
+    timer.mark("bgzf inflate");
     if (raw.size() < 12 || memcmp(raw.data(), "BAM\1", 4) != 0) return fail("bad BAM magic");
-    size_t off = 8 + (size_t)rdi32(&raw[4]);
+    const int32_t l_text = rdi32(&raw[4]);
+    if (l_text < 0 || (size_t)l_text > raw.size() - 12) return fail("truncated BAM header");
+    size_t off = 8 + (size_t)l_text;
     if (off + 4 > raw.size()) return fail("truncated BAM header");
     const int32_t n_ref = rdi32(&raw[off]); off += 4;
+    if (n_ref < 0) return fail("corrupt BAM header");
     for (int32_t k = 0; k < n_ref; ++k) {
         if (off + 8 > raw.size()) return fail("truncated BAM header");
         const int32_t l_name = rdi32(&raw[off]);
+        if (l_name < 1 || (size_t)l_name > raw.size() - off - 8) return fail("corrupt BAM header");
         std::string name((const char*)&raw[off + 4], (size_t)std::max(0, l_name - 1));
         const int32_t l_ref = rdi32(&raw[off + 4 + l_name]);
         r->contigs.push_back({name, l_ref});
@@ -345,12 +365,14 @@ static std::string read_bam(lvc_reads* r, const std::vector<uint8_t>& file, cons
                 const uint32_t l_rn = p[8];
                 x.mapq = p[9];
                 x.n_cig = rd16(p + 12); x.flag = rd16(p + 14); x.l_seq = (uint32_t)rdi32(p + 16);
-                x.next_same = rdi32(p + 20) == tid; x.next_pos = rdi32(p + 24);
+                const int32_t nref = rdi32(p + 20);
+                x.next_ref = nref < 0 ? -1 : (nref == tid ? 1 : 0); x.next_pos = rdi32(p + 24); x.tlen = rdi32(p + 28);
+                x.name = (const char*)(p + 32); x.l_name = l_rn ? l_rn - 1 : 0;
                 x.cig = p + 32 + l_rn;
                 x.seq = x.cig + 4 * (size_t)x.n_cig;
                 x.qual = x.seq + (x.l_seq + 1) / 2;
                 std::string v;
-                if (x.qual + x.l_seq > p + bs) v = fail("corrupt BAM record");
+                if (x.qual + x.l_seq > p + bs || (int32_t)x.l_seq < 0) v = fail("corrupt BAM record");
                 if (v.empty() && x.n_cig == 2) {
                     uint32_t c0; memcpy(&c0, x.cig, 4);
                     uint32_t c1; memcpy(&c1, x.cig + 4, 4);
@@ -379,8 +401,8 @@ static std::string read_bam(lvc_reads* r, const std::vector<uint8_t>& file, cons
         for (auto& t : th) t.join();
     }
     if (err_at < offs.size()) return err_msg;
-    if (g_timer) g_timer->mark("record scan");
-    return pack(r, recs, min_mapq, max_depth, n_threads);
+    timer.mark("record scan");
+    return pack(r, recs, min_mapq, max_depth, n_threads, overlap_model, timer);
 }
 
 static inline int64_t parse_int(const char* p, size_t n) {
@@ -391,7 +413,7 @@ static inline int64_t parse_int(const char* p, size_t n) {
 }
 
 static std::string read_sam(lvc_reads* r, const std::vector<uint8_t>& file, const char* contig, int min_mapq, int max_depth,
-                            int n_threads, std::vector<uint8_t>& /*unused*/) {
+                            int n_threads, int overlap_model, PhaseTimer& timer) {
     // text -> per-record binary blobs (cigar u32s, packed seq, qual), parsed by all threads on line-aligned pieces
     // of the file, then the samtools-order sort and the common packer
     struct Tmp { Rec rec; size_t cig_o, seq_o, qual_o; uint32_t piece; };
@@ -471,8 +493,11 @@ static std::string read_sam(lvc_reads* r, const std::vector<uint8_t>& file, cons
                     t.rec.flag = (uint16_t)parse_int(f[1], fl[1]);
                     t.rec.pos = (int32_t)parse_int(f[3], fl[3]) - 1;
                     t.rec.mapq = (uint8_t)parse_int(f[4], fl[4]);
-                    t.rec.next_same = (fl[6] == 1 && f[6][0] == '=') || (fl[6] == want.size() && memcmp(f[6], want.data(), fl[6]) == 0);
+                    const bool next_same = (fl[6] == 1 && f[6][0] == '=') || (fl[6] == want.size() && memcmp(f[6], want.data(), fl[6]) == 0);
+                    t.rec.next_ref = next_same ? 1 : ((fl[6] == 1 && f[6][0] == '*') ? -1 : 0);
                     t.rec.next_pos = (int32_t)parse_int(f[7], fl[7]) - 1;
+                    t.rec.tlen = (int32_t)parse_int(f[8], fl[8]);
+                    t.rec.name = f[0]; t.rec.l_name = (uint32_t)fl[0];
                     // CIGAR
                     t.cig_o = pc.store.size(); t.rec.n_cig = 0;
                     if (!(fl[5] == 1 && f[5][0] == '*')) {
@@ -501,7 +526,8 @@ static std::string read_sam(lvc_reads* r, const std::vector<uint8_t>& file, cons
                     t.qual_o = t.seq_o + (t.rec.l_seq + 1) / 2;
                     uint8_t* ql = pc.store.data() + t.qual_o;
                     const bool has_q = !(fl[10] == 1 && f[10][0] == '*');
-                    for (uint32_t k = 0; k < t.rec.l_seq; ++k) ql[k] = has_q && k < fl[10] ? (uint8_t)(f[10][k] - 33) : 0xFF;
+                    if (has_q && has_seq && fl[10] != fl[9]) { pc.err = fail("SAM: QUAL length %zu != SEQ length %zu", fl[10], fl[9]); return; }
+                    for (uint32_t k = 0; k < t.rec.l_seq; ++k) ql[k] = has_q ? (uint8_t)(f[10][k] - 33) : 0xFF;
                     pc.tmp.push_back(t);
                 }
             }
@@ -523,7 +549,7 @@ static std::string read_sam(lvc_reads* r, const std::vector<uint8_t>& file, cons
     }
     size_t total = 0;
     for (auto& pc : pieces) { if (!pc.err.empty()) return pc.err; total += pc.tmp.size(); }
-    if (g_timer) g_timer->mark("sam parse");
+    timer.mark("sam parse");
     std::vector<Tmp> tmp;
     tmp.reserve(total);
     for (auto& pc : pieces) { tmp.insert(tmp.end(), pc.tmp.begin(), pc.tmp.end()); std::vector<Tmp>().swap(pc.tmp); }
@@ -532,7 +558,7 @@ static std::string read_sam(lvc_reads* r, const std::vector<uint8_t>& file, cons
         if (a.rec.pos != b.rec.pos) return a.rec.pos < b.rec.pos;
         return ((a.rec.flag >> 4) & 1) < ((b.rec.flag >> 4) & 1);
     });
-    if (g_timer) g_timer->mark("sort");
+    timer.mark("sort");
     std::vector<Rec> recs;
     recs.reserve(tmp.size());
     for (auto& t : tmp) {
@@ -545,20 +571,19 @@ static std::string read_sam(lvc_reads* r, const std::vector<uint8_t>& file, cons
         if (rl == 0) { t.rec.n_cig = 0; t.rec.l_seq = 0; }
         recs.push_back(t.rec);
     }
-    if (g_timer) g_timer->mark("validate");
-    return pack(r, recs, min_mapq, max_depth, n_threads);
+    timer.mark("validate");
+    return pack(r, recs, min_mapq, max_depth, n_threads, overlap_model, timer);
 }
 
 }  // namespace ingest
 
 extern "C" {
 
-int lvc_read_alignments(const char* path, const char* contig, int min_mapq, int max_depth, int n_threads,
-                        lvc_reads** out, char* errbuf, int errlen) {
-    ingest::PhaseTimer timer;
-    ingest::g_timer = &timer;
+int lvc_read_alignments_ex(const char* path, const char* contig, int min_mapq, int max_depth, int n_threads,
+                           int overlap_model, lvc_reads** out, char* errbuf, int errlen) {
+    ingest::PhaseTimer timer;                                    // per call: the entry point is re-entrant
     auto seterr = [&](const std::string& s) { if (errbuf && errlen > 0) snprintf(errbuf, (size_t)errlen, "%s", s.c_str()); };
-    if (!path || !out) { seterr("bad arguments"); return LVC_EINVAL; }
+    if (!path || !out || overlap_model < LVC_OVERLAP_OFF || overlap_model > LVC_OVERLAP_HTSLIB_1_13) { seterr("bad arguments"); return LVC_EINVAL; }
     // whole file in one read (a stream iterator would copy it byte by byte)
     FILE* fh = fopen(path, "rb");
     if (!fh) { seterr(std::string("cannot open ") + path); return LVC_EIO; }
@@ -579,12 +604,11 @@ int lvc_read_alignments(const char* path, const char* contig, int min_mapq, int 
     fclose(fh);
     timer.mark("file read");
     lvc_reads* r = new lvc_reads();
-    std::vector<uint8_t> scratch;
     ingest::RawBuf rawbuf;
     if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
     std::string e;
-    if (file.size() >= 2 && file[0] == 0x1f && file[1] == 0x8b) e = ingest::read_bam(r, file, contig, min_mapq, max_depth, n_threads, rawbuf);
-    else e = ingest::read_sam(r, file, contig, min_mapq, max_depth, n_threads, scratch);
+    if (file.size() >= 2 && file[0] == 0x1f && file[1] == 0x8b) e = ingest::read_bam(r, file, contig, min_mapq, max_depth, n_threads, rawbuf, overlap_model, timer);
+    else e = ingest::read_sam(r, file, contig, min_mapq, max_depth, n_threads, overlap_model, timer);
     if (!e.empty()) {
         seterr(e);
         const bool unsorted = e.find("not coordinate sorted") != std::string::npos;
@@ -593,8 +617,19 @@ int lvc_read_alignments(const char* path, const char* contig, int min_mapq, int 
         return unsorted ? LVC_EUNSORTED : LVC_EINVAL;
     }
     timer.mark("total tail");
-    ingest::g_timer = nullptr;
     *out = r;
+    return LVC_OK;
+}
+
+int lvc_read_alignments(const char* path, const char* contig, int min_mapq, int max_depth, int n_threads,
+                        lvc_reads** out, char* errbuf, int errlen) {
+    return lvc_read_alignments_ex(path, contig, min_mapq, max_depth, n_threads, LVC_OVERLAP_DEFAULT, out, errbuf, errlen);
+}
+
+int lvc_reads_overlap_stats(const lvc_reads* r, uint64_t* n_pairs, uint64_t* n_bases) {
+    if (!r) return LVC_EINVAL;
+    if (n_pairs) *n_pairs = r->overlap_pairs;
+    if (n_bases) *n_bases = r->overlap_bases;
     return LVC_OK;
 }
 

@@ -14,7 +14,9 @@
 #include "deposit_general.cuh"
 #include "deposit_tile.cuh"
 #include "deposit_tile4.cuh"
+#include "deposit_tile5.cuh"
 #include "genotype.cuh"
+#include "overlap.hpp"
 
 using namespace lvc;
 
@@ -33,6 +35,7 @@ struct lvc_handle {
     bool own_stream = false;
     std::string err;
     int impl = 0;
+    int tile_impl = 4;                       // what impl 0 (auto) picks for short-read batches (LVC_TILE_IMPL overrides)
     int sm_count = 148;
     uint64_t launches = 0;
     bool zero_copy_ok = true;                // read page-locked caller payload in place (LVC_ZERO_COPY=0 disables)
@@ -185,6 +188,7 @@ int lvc_create(lvc_handle** out, int device, int64_t ref_len, const uint8_t* ref
     h->min_mq = min_mapping_quality;
     for (int k = 0; k < kMaxKeys; ++k) h->lut[k] = kNoPlane;
     if (const char* zc = getenv("LVC_ZERO_COPY")) h->zero_copy_ok = atoi(zc) != 0;
+    if (const char* ti = getenv("LVC_TILE_IMPL")) { const int v = atoi(ti); if (v == 2 || v == 4 || v == 5) h->tile_impl = v; }
     auto body = [&]() -> int {
         CU(cudaSetDevice(device));
         cudaDeviceProp prop;
@@ -222,6 +226,8 @@ int lvc_create(lvc_handle** out, int device, int64_t ref_len, const uint8_t* ref
         CU(cudaFuncSetAttribute(k_deposit_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
         CU(cudaFuncSetAttribute(k_deposit_tile4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTile4SmemBytes));
         CU(cudaFuncSetAttribute(k_deposit_tile4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTile4SmemBytes));
+        CU(cudaFuncSetAttribute(k_deposit_tile5<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTile5SmemBytes));
+        CU(cudaFuncSetAttribute(k_deposit_tile5<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTile5SmemBytes));
         CU(cudaStreamSynchronize(h->stream));
         return LVC_OK;
     };
@@ -274,7 +280,7 @@ int lvc_sync(lvc_handle* h) {
 }
 
 int lvc_set_impl(lvc_handle* h, int impl) {
-    if (!h || impl < 0 || impl > 4) return LVC_EINVAL;
+    if (!h || impl < 0 || impl > 5) return LVC_EINVAL;
     h->impl = impl;
     return LVC_OK;
 }
@@ -306,59 +312,22 @@ void lvc_host_free(void* p) { if (p) cudaFreeHost(p); }
 int lvc_admit(uint32_t n, const int32_t* pos, const uint16_t* flag, const uint8_t* mapq, const uint32_t* cigar_off,
               const uint32_t* cigar, int min_mq, int max_depth, uint8_t* keep) {
     if (n && (!pos || !flag || !mapq || !cigar_off || !cigar || !keep)) return LVC_EINVAL;
-    // buffered-read end positions: ring of counters indexed by end position relative to a base
-    std::vector<uint32_t> ring;          // counts of buffered reads by end position
-    int64_t ring_base = 0;               // position of ring[0]
-    auto ring_add = [&](int64_t e, int64_t p) {
-        if (ring.empty()) { ring.assign(4096, 0); ring_base = p; }   // every later end is > p
-        if (e < ring_base) return;       // cannot happen (end > pos >= ring_base)
-        size_t off = (size_t)(e - ring_base);
-        if (off >= ring.size()) ring.resize(std::max(ring.size() * 2, off + 1), 0);
-        ring[off]++;
-    };
-    int64_t iter_pos = 0, max_pos = -1;
-    int64_t nbuf = 0;
-    for (uint32_t i = 0; i < n; ++i) {
-        keep[i] = 0;
-        const uint32_t f = flag[i];
-        if (f & kFlagFilter) continue;
-        if ((int)mapq[i] < min_mq) continue;
-        if ((f & 0x1u) && !(f & 0x2u)) continue;
-        int64_t rlen = 0;
-        for (uint32_t k = cigar_off[i]; k < cigar_off[i + 1]; ++k) {
-            const uint32_t op = cigar[k] & 15u;
-            if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) rlen += cigar[k] >> 4;
-        }
-        if (rlen == 0) continue;         // malformed: no reference-consuming op (htslib asserts)
-        const int64_t p = pos[i], e = p + rlen;
-        if (p < max_pos) return LVC_EUNSORTED;
-        if (p == iter_pos && nbuf + 1 > (int64_t)max_depth) continue;     // bam_plp_push: cnt > maxcnt
-        max_pos = p;
-        keep[i] = 1;
-        nbuf++;
-        ring_add(e, p);
-        // bam_plp_next: emit columns while max_pos > iter_pos; each built column frees ended reads
-        while (max_pos > iter_pos) {
-            const int64_t c = iter_pos;
-            if (!ring.empty() && c >= ring_base && (size_t)(c - ring_base) < ring.size()) {
-                nbuf -= ring[(size_t)(c - ring_base)];
-                ring[(size_t)(c - ring_base)] = 0;
-            }
-            if (nbuf - 1 == 0) iter_pos = max_pos;     // only the new read is buffered: jump to it
-            else iter_pos = c + 1;
-        }
-        // slide the ring so it does not grow with the genome
-        if (!ring.empty() && iter_pos - ring_base > (int64_t)ring.size() / 2) {
-            const size_t shift = (size_t)(iter_pos - ring_base);
-            if (shift >= ring.size()) { std::fill(ring.begin(), ring.end(), 0); }
-            else {
-                std::move(ring.begin() + shift, ring.end(), ring.begin());
-                std::fill(ring.end() - shift, ring.end(), 0);
-            }
-            ring_base = iter_pos;
-        }
-    }
-    return LVC_OK;
+    auto no_name = [](uint32_t) { return lvc_overlap::NameKey{nullptr, 0}; };
+    return lvc_overlap::admit_core(n, pos, flag, mapq, cigar_off, cigar, nullptr, nullptr, nullptr, no_name, nullptr, nullptr,
+                                   nullptr, min_mq, max_depth, LVC_OVERLAP_OFF, keep, nullptr, nullptr);
+}
+
+int lvc_admit_overlaps(uint32_t n, const int32_t* pos, const uint16_t* flag, const uint8_t* mapq, const uint32_t* cigar_off,
+                       const uint32_t* cigar, const uint64_t* seq_off, const uint8_t* seq4, uint8_t* qual,
+                       const uint32_t* name_off, const char* names, const int32_t* mate_pos, const int8_t* mate_ref,
+                       const int32_t* tlen, int min_mq, int max_depth, int overlap_model, uint8_t* keep, uint64_t* n_pairs,
+                       uint64_t* n_bases) {
+    if (n && (!pos || !flag || !mapq || !cigar_off || !cigar || !keep)) return LVC_EINVAL;
+    if (overlap_model < LVC_OVERLAP_OFF || overlap_model > LVC_OVERLAP_HTSLIB_1_13) return LVC_EINVAL;
+    if (overlap_model != LVC_OVERLAP_OFF && n && (!seq_off || !seq4 || !qual || !name_off || !names)) return LVC_EINVAL;
+    auto name = [&](uint32_t i) { return lvc_overlap::NameKey{names + name_off[i], name_off[i + 1] - name_off[i]}; };
+    return lvc_overlap::admit_core(n, pos, flag, mapq, cigar_off, cigar, seq_off, seq4, qual, name, mate_pos, mate_ref, tlen,
+                                   min_mq, max_depth, overlap_model, keep, n_pairs, n_bases);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -377,7 +346,7 @@ static int launch_deposit(lvc_handle* h, const BatchView& bv, int replay, uint64
     // auto: batches of long reads (many CIGAR ops per read: ONT) take the warp-per-read kernel, short-read batches
     // the tiled kernel
     const bool long_reads = n_cigar_ops > 4ull * n;
-    const int impl = h->impl == 0 ? (long_reads ? 3 : 4) : h->impl;
+    const int impl = h->impl == 0 ? (long_reads ? 3 : h->tile_impl) : h->impl;
     // the tiled kernels' byte arithmetic assumes a primary quality and a threshold below 128
     const bool tile_ok = h->qprim < 128 && h->min_bq <= 128 && h->lut[h->qprim] != kNoPlane;
     if (impl == 3 || ((replay || !tile_ok) && impl != 1 && long_reads)) {
@@ -400,17 +369,21 @@ static int launch_deposit(lvc_handle* h, const BatchView& bv, int replay, uint64
         tp.qprim = (uint32_t)h->qprim;
         tp.prim_plane = h->lut[h->qprim];
         { KernelTimer t(h, 0);
-          if (impl == 4) {
+          if (impl == 4 || impl == 5) {
               // programmatic stream serialization: the chunk headers are read (and dead chunks retire) while the
               // previous kernel of the stream drains; the kernel waits for it before its first table access
               cudaLaunchConfig_t cfg = {};
-              cfg.gridDim = dim3(tp.grid); cfg.blockDim = dim3(kTileThreads); cfg.dynamicSmemBytes = kTile4SmemBytes;
+              cfg.gridDim = dim3(tp.grid); cfg.blockDim = dim3(kTileThreads);
+              cfg.dynamicSmemBytes = impl == 5 ? kTile5SmemBytes : kTile4SmemBytes;
               cfg.stream = h->stream;
               cudaLaunchAttribute at[1];
               at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
               at[0].val.programmaticStreamSerializationAllowed = 1;
               cfg.attrs = at; cfg.numAttrs = 1;
-              if (h->min_bq <= 0) CU(cudaLaunchKernelEx(&cfg, k_deposit_tile4<true>, bv, tv, dp, tp));
+              if (impl == 5) {
+                  if (h->min_bq <= 0) CU(cudaLaunchKernelEx(&cfg, k_deposit_tile5<true>, bv, tv, dp, tp));
+                  else CU(cudaLaunchKernelEx(&cfg, k_deposit_tile5<false>, bv, tv, dp, tp));
+              } else if (h->min_bq <= 0) CU(cudaLaunchKernelEx(&cfg, k_deposit_tile4<true>, bv, tv, dp, tp));
               else CU(cudaLaunchKernelEx(&cfg, k_deposit_tile4<false>, bv, tv, dp, tp));
           } else if (h->min_bq <= 0)
               k_deposit_tile<true><<<tp.grid, kTileThreads, kTileSmemBytes, h->stream>>>(bv, tv, dp, tp);
@@ -945,4 +918,4 @@ uint64_t lvc_h2d_payload_bytes(lvc_handle* h) { return h ? h->h2d_payload_bytes 
 
 }  // extern "C"
 
-#include "ingest.cpp.inc"
+#include "ingest.hpp"

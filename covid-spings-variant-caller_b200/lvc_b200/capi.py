@@ -19,6 +19,11 @@ ERRORS = {-1: "LVC_EINVAL", -2: "LVC_ECUDA", -3: "LVC_ENOMEM", -4: "LVC_EUNSORTE
           -6: "LVC_ENODEVICE", -7: "LVC_EAGAIN", -8: "LVC_EIO"}
 GENO_EMIT_ALL = 1
 MAX_DEPTH_DEFAULT = 8000
+# htslib mate-overlap models (include/lvc.h): pysam's pileup() default is ignore_overlaps=True
+OVERLAP_OFF, OVERLAP_HTSLIB_1_10, OVERLAP_HTSLIB_1_13 = 0, 1, 2
+OVERLAP_DEFAULT = OVERLAP_HTSLIB_1_13
+OVERLAP_MODELS = {None: OVERLAP_DEFAULT, "off": OVERLAP_OFF, "htslib-1.10": OVERLAP_HTSLIB_1_10,
+                  "htslib-1.13": OVERLAP_HTSLIB_1_13}
 
 
 class LvcError(RuntimeError):
@@ -59,8 +64,13 @@ SIGNATURES = [
     ("lvc_sync", C.c_int, [_H]),
     ("lvc_admit", C.c_int, [C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                             C.c_void_p]),
+    ("lvc_admit_overlaps", C.c_int, [C.c_uint32] + [C.c_void_p] * 13 + [C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                                                       C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     ("lvc_read_alignments", C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_char_p,
                                       C.c_int]),
+    ("lvc_read_alignments_ex", C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p),
+                                         C.c_char_p, C.c_int]),
+    ("lvc_reads_overlap_stats", C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     ("lvc_reads_batch", C.c_int, [C.c_void_p, C.POINTER(Batch)]),
     ("lvc_reads_info", C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int),
                                  C.POINTER(C.c_int)]),
@@ -145,18 +155,56 @@ def admit(pos: np.ndarray, flag: np.ndarray, mapq: np.ndarray, cigar_off: np.nda
     return keep
 
 
+def overlap_model_id(model) -> int:
+    """None / "off" / "htslib-1.10" / "htslib-1.13" (or the integer ids of include/lvc.h)"""
+    if isinstance(model, int) and not isinstance(model, bool):
+        if model in (OVERLAP_OFF, OVERLAP_HTSLIB_1_10, OVERLAP_HTSLIB_1_13):
+            return model
+    elif model in OVERLAP_MODELS:
+        return OVERLAP_MODELS[model]
+    raise ValueError(f"unknown overlap model {model!r}; one of {[k for k in OVERLAP_MODELS if k]}")
+
+
+def admit_overlaps(pos, flag, mapq, cigar_off, cigar, seq_off, seq4, qual, names, mate_pos, mate_ref, tlen,
+                   min_mapq: int, max_depth: int = MAX_DEPTH_DEFAULT, overlap_model: int = OVERLAP_DEFAULT):
+    """lvc_admit_overlaps: keep mask + htslib's mate-overlap quality rewrite, IN PLACE on `qual`; needs no GPU.
+    `names`: list of QNAME strings.  Returns (keep, pairs rewritten, quality bytes rewritten)."""
+    lib = load_library()
+    n = len(pos)
+    keep = np.zeros(n, dtype=np.uint8)
+    if n == 0:
+        return keep, 0, 0
+    enc = [x.encode("latin-1") for x in names]
+    name_off = np.zeros(n + 1, dtype=np.uint32)
+    np.cumsum([len(x) for x in enc], out=name_off[1:])
+    blob = np.frombuffer(b"".join(enc) + b"\0", dtype=np.uint8)
+    mate_pos = np.ascontiguousarray(mate_pos, dtype=np.int32)
+    mate_ref = np.ascontiguousarray(mate_ref, dtype=np.int8)
+    tlen = np.ascontiguousarray(tlen, dtype=np.int32)
+    pairs, bases = C.c_uint64(0), C.c_uint64(0)
+    rc = lib.lvc_admit_overlaps(n, _ptr(pos), _ptr(flag), _ptr(mapq), _ptr(cigar_off), _ptr(cigar), _ptr(seq_off),
+                                _ptr(seq4), _ptr(qual), _ptr(name_off), _ptr(blob), _ptr(mate_pos), _ptr(mate_ref),
+                                _ptr(tlen), int(min_mapq), int(max_depth), int(overlap_model), _ptr(keep),
+                                C.byref(pairs), C.byref(bases))
+    if rc == -4:
+        raise ValueError("reads are not coordinate sorted (the reference's pileup engine errors out too)")
+    if rc != LVC_OK:
+        raise LvcError(rc, "lvc_admit_overlaps failed")
+    return keep, int(pairs.value), int(bases.value)
+
+
 class NativeReads:
     """Alignments of one contig read and packed by the native ingest (lvc_read_alignments)."""
 
     def __init__(self, path: str, contig: Optional[str], min_mapq: int, max_depth: int = MAX_DEPTH_DEFAULT,
-                 n_threads: int = 0):
+                 n_threads: int = 0, overlap_model: int = OVERLAP_DEFAULT):
         self.lib = load_library()
         if not os.path.exists(path):
             raise FileNotFoundError(path)                      # pysam raises OSError for a missing file too
         r = C.c_void_p()
         err = C.create_string_buffer(512)
-        rc = self.lib.lvc_read_alignments(path.encode(), (contig or "").encode(), int(min_mapq), int(max_depth),
-                                          int(n_threads), C.byref(r), err, 512)
+        rc = self.lib.lvc_read_alignments_ex(path.encode(), (contig or "").encode(), int(min_mapq), int(max_depth),
+                                             int(n_threads), int(overlap_model), C.byref(r), err, 512)
         if rc != LVC_OK:
             msg = err.value.decode()
             if "invalid contig" in msg or "not coordinate sorted" in msg:
@@ -173,6 +221,9 @@ class NativeReads:
         ln, nc, pinned = C.c_int64(0), C.c_int(0), C.c_int(0)
         self.lib.lvc_reads_info(self.r, name, 256, C.byref(ln), C.byref(nc), C.byref(pinned))
         self.contig, self.contig_len, self.pinned = name.value.decode(), ln.value, bool(pinned.value)
+        op, ob = C.c_uint64(0), C.c_uint64(0)
+        self.lib.lvc_reads_overlap_stats(self.r, C.byref(op), C.byref(ob))
+        self.overlap_pairs, self.overlap_bases = int(op.value), int(ob.value)
 
     @property
     def n_reads(self) -> int:

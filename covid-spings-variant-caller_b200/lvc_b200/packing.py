@@ -85,8 +85,11 @@ class ReadBatch:
 
 
 def finalize_batch(pos, flag, mapq, cigar_off, cigar, seq_off, seq4, qual, min_mapq: int,
-                   max_depth: int = capi.MAX_DEPTH_DEFAULT, acgt_only: Optional[np.ndarray] = None) -> ReadBatch:
-    """Validate, compute the keep mask (host admission, SURVEY B2+B4) and the ACGT-only hint."""
+                   max_depth: int = capi.MAX_DEPTH_DEFAULT, acgt_only: Optional[np.ndarray] = None,
+                   mates: Optional[dict] = None, overlap_model: int = capi.OVERLAP_DEFAULT) -> ReadBatch:
+    """Validate, compute the keep mask (host admission, SURVEY B2+B4) and the ACGT-only hint.
+    `mates` = {"names": [...], "mate_pos": [...], "mate_ref": [...], "tlen": [...]} switches htslib's mate-overlap
+    quality rewrite on (pysam's default); without it, or with overlap_model OFF, qualities stay as given."""
     pos = np.ascontiguousarray(pos, dtype=np.int32)
     flag = np.ascontiguousarray(flag, dtype=np.uint16)
     mapq = np.ascontiguousarray(mapq, dtype=np.uint8)
@@ -101,11 +104,21 @@ def finalize_batch(pos, flag, mapq, cigar_off, cigar, seq_off, seq4, qual, min_m
     if n and (seq_off & np.uint64(1)).any():
         raise ValueError("seq_off entries must be even")
     cig_store = cigar if len(cigar) else np.zeros(1, dtype=np.uint32)
-    keep = capi.admit(pos, flag, mapq, cigar_off, cig_store, min_mapq, max_depth)
+    overlap_stats = (0, 0)
+    if mates is not None and overlap_model != capi.OVERLAP_OFF and n:
+        qual = np.array(qual, dtype=np.uint8, copy=True)              # rewritten in place
+        keep, pairs, nb = capi.admit_overlaps(pos, flag, mapq, cigar_off, cig_store, seq_off, seq4, qual, mates["names"],
+                                              mates["mate_pos"], mates["mate_ref"], mates["tlen"], min_mapq, max_depth,
+                                              overlap_model)
+        overlap_stats = (pairs, nb)
+    else:
+        keep = capi.admit(pos, flag, mapq, cigar_off, cig_store, min_mapq, max_depth)
     if acgt_only is None:
         acgt_only = acgt_only_hint(seq4, seq_off, n, query_lengths(cigar_off, cig_store))
     keep = (keep | (acgt_only.astype(np.uint8) << 1)).astype(np.uint8)
-    return ReadBatch(pos, flag, mapq, keep, cigar_off, cig_store, seq_off, seq4, qual)
+    out = ReadBatch(pos, flag, mapq, keep, cigar_off, cig_store, seq_off, seq4, qual)
+    out.overlap_pairs, out.overlap_bases = overlap_stats
+    return out
 
 
 def _with_slack(a: np.ndarray, used: int, slack: int = 64) -> np.ndarray:
@@ -148,13 +161,19 @@ def acgt_only_hint(seq4: np.ndarray, seq_off: np.ndarray, n: int, lq: Optional[n
     return (csum[ends] - csum[starts]) == 0
 
 
-def pack_reads(reads: Iterable[Tuple[int, int, int, Sequence[Tuple[int, int]], str, Sequence[int]]],
-               min_mapq: int, max_depth: int = capi.MAX_DEPTH_DEFAULT) -> ReadBatch:
-    """reads: iterable of (flag, pos0, mapq, [(op, len)...], seq_str, qual_ints) in coordinate order."""
+def pack_reads(reads: Iterable[Tuple], min_mapq: int, max_depth: int = capi.MAX_DEPTH_DEFAULT,
+               overlap_model: int = capi.OVERLAP_DEFAULT) -> ReadBatch:
+    """reads: iterable of (flag, pos0, mapq, [(op, len)...], seq_str, qual_ints[, name, mate_pos0, mate_ref, tlen]) in
+    coordinate order; the four optional mate fields (mate_ref: 1 same contig, 0 other, -1 absent) enable the
+    mate-overlap handling."""
     pos, flag, mapq, coff, cig, soff = [], [], [], [0], [], [0]
     seq_parts: List[np.ndarray] = []
     qual_parts: List[np.ndarray] = []
-    for f, p, m, ops, seq, qual in reads:
+    names, mpos, mref, tlen = [], [], [], []
+    for rec in reads:
+        f, p, m, ops, seq, qual = rec[:6]
+        if len(rec) >= 10:
+            names.append(rec[6]); mpos.append(rec[7]); mref.append(rec[8]); tlen.append(rec[9])
         ops = [(o, l) for o, l in ops if l > 0]                  # zero-length ops carry no information
         lq = sum(l for o, l in ops if o in (0, 1, 4, 7, 8))
         if len(seq) != lq or len(qual) != lq:
@@ -176,7 +195,9 @@ def pack_reads(reads: Iterable[Tuple[int, int, int, Sequence[Tuple[int, int]], s
         soff.append(soff[-1] + len(q))
     seq4 = np.concatenate(seq_parts) if seq_parts else np.zeros(0, np.uint8)
     qual = np.concatenate(qual_parts) if qual_parts else np.zeros(0, np.uint8)
-    return finalize_batch(pos, flag, mapq, coff, cig, soff, seq4, qual, min_mapq, max_depth)
+    mates = dict(names=names, mate_pos=mpos, mate_ref=mref, tlen=tlen) if len(names) == len(pos) and names else None
+    return finalize_batch(pos, flag, mapq, coff, cig, soff, seq4, qual, min_mapq, max_depth, mates=mates,
+                          overlap_model=overlap_model)
 
 
 class _Pinned:

@@ -65,19 +65,9 @@ def _parse_cigar_text(text: str) -> List[Tuple[int, int]]:
     return out
 
 
-def _check_mate_overlap(flag: int, pos: int, rlen: int, rnext_same: bool, pnext: int, name: str):
-    """htslib's mate-overlap quality tweak (ignore_overlaps=True -> tweak_overlap_quality) is
-    htslib-version dependent and not implemented: refuse proper pairs whose mates overlap instead of
-    silently diverging.  htslib only tweaks when both mates are buffered, so testing from the leftmost
-    mate (its partner starts inside its own reference span) finds every such pair."""
-    if (flag & 0x1) and (flag & 0x2) and not (flag & 0x8) and rnext_same and pos <= pnext < pos + rlen:
-        raise UnsupportedInput(
-            f"read {name!r}: proper pair with overlapping mates (pos {pos}, mate {pnext}); "
-            "htslib's overlap quality tweak is not reproduced yet")
-
-
 def read_sam(path: str, contig: Optional[str], min_mapq: int, sort: bool = True,
-             max_depth: int = packing.capi.MAX_DEPTH_DEFAULT) -> Tuple[List[Tuple[str, int]], ReadBatch]:
+             max_depth: int = packing.capi.MAX_DEPTH_DEFAULT,
+             overlap_model: int = packing.capi.OVERLAP_DEFAULT) -> Tuple[List[Tuple[str, int]], ReadBatch]:
     """SAM text -> packed batch of the reads on `contig` (default: first @SQ), coordinate sorted the way
     `samtools sort` does (position, forward strand first, input order) when `sort`."""
     contigs: List[Tuple[str, int]] = []
@@ -102,12 +92,13 @@ def read_sam(path: str, contig: Optional[str], min_mapq: int, sort: bool = True,
                 raise UnsupportedInput(f"read {t[0]!r} has no base qualities (the reference raises TypeError)")
             qual = [ord(c) - 33 for c in t[10]] if t[10] != "*" else []
             seq = t[9] if t[9] != "*" else ""
-            rlen = sum(l for o, l in ops if o in (0, 2, 3, 7, 8))
-            _check_mate_overlap(flag, pos, rlen, t[6] in ("=", t[2]), int(t[7]) - 1, t[0])
-            rows.append((flag, pos, mapq, ops, seq, qual))
+            if qual and len(qual) != len(seq):
+                raise UnsupportedInput(f"read {t[0]!r}: QUAL length {len(qual)} != SEQ length {len(seq)}")
+            mref = 1 if t[6] in ("=", t[2]) else (-1 if t[6] == "*" else 0)
+            rows.append((flag, pos, mapq, ops, seq, qual, t[0], int(t[7]) - 1, mref, int(t[8])))
     if sort:
         rows.sort(key=lambda r: (r[1], 1 if r[0] & 0x10 else 0))
-    return contigs, packing.pack_reads(rows, min_mapq, max_depth)
+    return contigs, packing.pack_reads(rows, min_mapq, max_depth, overlap_model)
 
 
 # ------------------------------------------------------------------------------------------ BAM
@@ -136,7 +127,8 @@ def _bgzf_decompress(path: str) -> bytes:
 
 
 def read_bam(path: str, contig: Optional[str], min_mapq: int,
-             max_depth: int = packing.capi.MAX_DEPTH_DEFAULT) -> Tuple[List[Tuple[str, int]], ReadBatch]:
+             max_depth: int = packing.capi.MAX_DEPTH_DEFAULT,
+             overlap_model: int = packing.capi.OVERLAP_DEFAULT) -> Tuple[List[Tuple[str, int]], ReadBatch]:
     """BAM -> packed batch of the records whose reference is `contig` (file order = coordinate order).
     No index is needed (the reference needs one only because pysam's region iterator does)."""
     raw = _bgzf_decompress(path)
@@ -163,6 +155,7 @@ def read_bam(path: str, contig: Optional[str], min_mapq: int,
     arr = np.frombuffer(raw, dtype=np.uint8)
     pos, flag, mapq, coff, soff = [], [], [], [0], [0]
     cig_parts, seq_parts, qual_parts = [], [], []
+    names, mpos, mref, tlens = [], [], [], []
     n = len(raw)
     while off + 4 <= n:
         bs = struct.unpack_from("<i", raw, off)[0]
@@ -187,7 +180,8 @@ def read_bam(path: str, contig: Optional[str], min_mapq: int,
                 raise UnsupportedInput(f"{path}: CIGAR stored in the CG tag (>65535 ops) is not supported")
             if lq != l_seq and rlen > 0:
                 raise UnsupportedInput(f"{path}: read at {p}: CIGAR query length {lq} != l_seq {l_seq}")
-            _check_mate_overlap(fl, p, rlen, next_ref == ref_id, next_pos, "?")
+            names.append(raw[off + 36:off + 36 + max(l_rn - 1, 0)].decode("latin-1"))
+            mpos.append(next_pos); mref.append(-1 if next_ref < 0 else (1 if next_ref == ref_id else 0)); tlens.append(_tlen)
             pos.append(p); flag.append(fl); mapq.append(mq)
             if lq != l_seq:
                 cig = cig[:0]; sq = sq[:0]; ql = ql[:0]; l_seq = 0
@@ -202,30 +196,35 @@ def read_bam(path: str, contig: Optional[str], min_mapq: int,
     cigar = np.concatenate(cig_parts).astype(np.uint32) if cig_parts else np.zeros(0, np.uint32)
     seq4 = np.concatenate(seq_parts) if seq_parts else np.zeros(0, np.uint8)
     qual = np.concatenate(qual_parts) if qual_parts else np.zeros(0, np.uint8)
-    return contigs, packing.finalize_batch(pos, flag, mapq, coff, cigar, soff, seq4, qual, min_mapq, max_depth)
+    return contigs, packing.finalize_batch(pos, flag, mapq, coff, cigar, soff, seq4, qual, min_mapq, max_depth,
+                                           mates=dict(names=names, mate_pos=mpos, mate_ref=mref, tlen=tlens),
+                                           overlap_model=overlap_model)
 
 
 def read_alignments_native(path: str, contig: Optional[str], min_mapq: int,
-                           max_depth: int = packing.capi.MAX_DEPTH_DEFAULT, n_threads: int = 0):
+                           max_depth: int = packing.capi.MAX_DEPTH_DEFAULT, n_threads: int = 0,
+                           overlap_model: int = packing.capi.OVERLAP_DEFAULT):
     """BAM or SAM through the library's native ingest (multi-threaded BGZF inflate, page-locked output).
     Returns a capi.NativeReads; `.batch` goes straight to Handle.push_batch, `.as_readbatch()` gives numpy views."""
-    return packing.capi.NativeReads(path, contig, min_mapq, max_depth, n_threads)
+    return packing.capi.NativeReads(path, contig, min_mapq, max_depth, n_threads, overlap_model)
 
 
 def read_alignments(path: str, contig: Optional[str], min_mapq: int,
-                    max_depth: int = packing.capi.MAX_DEPTH_DEFAULT):
+                    max_depth: int = packing.capi.MAX_DEPTH_DEFAULT,
+                    overlap_model: int = packing.capi.OVERLAP_DEFAULT):
     """Pure-Python reader (kept as an independent cross-check of the native ingest).
     Dispatch on the file content: BGZF magic -> BAM, otherwise SAM text."""
     with open(path, "rb") as fh:
         magic = fh.read(4)
     if magic[:2] == b"\x1f\x8b":
-        return read_bam(path, contig, min_mapq, max_depth)
-    return read_sam(path, contig, min_mapq, True, max_depth)
+        return read_bam(path, contig, min_mapq, max_depth, overlap_model)
+    return read_sam(path, contig, min_mapq, True, max_depth, overlap_model)
 
 
 def write_bam(path: str, contigs: List[Tuple[str, int]], reads, header_text: Optional[str] = None):
-    """Write records (flag, pos0, mapq, [(op,len)], seq, qual_ints[, name]) on contig 0 as an uncompressed-
-    deflate BGZF BAM (tests and synthetic fixtures).  Records must already be coordinate sorted."""
+    """Write records (flag, pos0, mapq, [(op,len)], seq, qual_ints[, name[, mate_pos0, mate_ref, tlen]]) on contig 0 as a
+    BGZF BAM (tests and synthetic fixtures).  Records must already be coordinate sorted.  mate_ref: 1 = same contig,
+    0 = another contig (written as reference id 1), -1 = absent."""
     if header_text is None:
         header_text = "@HD\tVN:1.6\tSO:coordinate\n" + "".join(f"@SQ\tSN:{n}\tLN:{l}\n" for n, l in contigs)
     body = bytearray()
@@ -244,7 +243,9 @@ def write_bam(path: str, contigs: List[Tuple[str, int]], reads, header_text: Opt
         ql = bytes(qual) if len(qual) == l_seq else b"\xff" * l_seq
         cig = b"".join(struct.pack("<I", (l << 4) | o) for o, l in ops)
         rlen = sum(l for o, l in ops if o in (0, 2, 3, 7, 8))
-        core = struct.pack("<iiBBHHHiiii", 0, p, len(name), mq, 4680, len(ops), fl, l_seq, -1, -1, 0)
+        m_pos, m_ref, t_len = (rec[7], rec[8], rec[9]) if len(rec) > 9 else (-1, -1, 0)
+        core = struct.pack("<iiBBHHHiiii", 0, p, len(name), mq, 4680, len(ops), fl, l_seq,
+                           0 if m_ref == 1 else (1 if m_ref == 0 else -1), m_pos, t_len)
         rec_b = core + name + cig + sq + ql
         body += struct.pack("<i", len(rec_b)) + rec_b
         _ = rlen

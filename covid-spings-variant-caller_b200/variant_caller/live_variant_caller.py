@@ -58,7 +58,7 @@ def _default_device() -> int:
 class LiveVariantCaller:
     def __init__(self, referenceFasta: str, minBaseQuality: int, minMappingQuality: int, minTotalDepth: int,
                  minAlleleDepth: int, minEvidenceRatio: float, maxVariants: int, device: Optional[int] = None,
-                 maxDepth: int = capi.MAX_DEPTH_DEFAULT):
+                 maxDepth: int = capi.MAX_DEPTH_DEFAULT, ignoreOverlaps: bool = True, overlapModel: Optional[str] = None):
         self.minBaseQuality = minBaseQuality
         self.minMappingQuality = minMappingQuality
         self.minTotalDepth = minTotalDepth
@@ -66,6 +66,9 @@ class LiveVariantCaller:
         self.minEvidenceRatio = minEvidenceRatio
         self.maxVariants = maxVariants                      # stored, never used (reference :29)
         self.maxDepth = maxDepth                            # pysam's pileup(max_depth=8000) default
+        # pysam's pileup(ignore_overlaps=True) default: htslib rewrites the qualities of overlapping mates.  The rule
+        # changed between htslib releases and the reference does not pin pysam: "htslib-1.13" (default) or "htslib-1.10"
+        self.overlapModel = capi.overlap_model_id(overlapModel) if ignoreOverlaps else capi.OVERLAP_OFF
         self.fastaFile = samio.Fasta(referenceFasta)
         self._device = _default_device() if device is None else device
         self._lock = threading.RLock()                      # the reference's callers use bare threads
@@ -111,10 +114,13 @@ class LiveVariantCaller:
         packs them and deposits them into the device tables."""
         with self._lock:
             self._open_contig(referenceIndex)
-            reads = samio.read_alignments_native(inputBam, self._contig, int(self.minMappingQuality), self.maxDepth)
-            if reads.n_reads:
-                self._handle.push_batch(reads.batch)
-            reads.close()
+            reads = samio.read_alignments_native(inputBam, self._contig, int(self.minMappingQuality), self.maxDepth,
+                                                 overlap_model=self.overlapModel)
+            try:
+                if reads.n_reads:
+                    self._handle.push_batch(reads.batch)
+            finally:
+                reads.close()
 
     def process_batch(self, batch: ReadBatch):
         """Deposit one packed, coordinate-sorted batch (the fast entry point for live batches)."""

@@ -108,27 +108,54 @@ int lvc_admit(uint32_t n_reads, const int32_t* pos, const uint16_t* flag, const 
               const uint32_t* cigar_off, const uint32_t* cigar, int min_mapping_quality, int max_depth,
               uint8_t* keep_out);
 
+/* ---- mate overlaps (no GPU needed) --------------------------------------------------------------
+ * The reference calls pileup() with pysam's default ignore_overlaps=True (live_variant_caller.py:56-60): htslib
+ * rewrites the base qualities of the two reads of a proper pair where they cover the same reference positions
+ * (bam_plp overlap hash + tweak_overlap_quality), and both pysam's base-quality filter and the phreds
+ * the reference stores (:97-103) see the rewritten values.  lvc_admit_overlaps is lvc_admit plus that rewrite, done
+ * IN PLACE on `qual` inside the same sequential pass (entries leave the hash when a read is swept or dropped by
+ * max_depth, exactly as in the pileup engine).  htslib changed the rule between releases and pysam is unpinned in
+ * the reference (requirements.txt:1): `overlap_model` selects the release line.
+ *   name_off[n_reads+1] / names: concatenated QNAMEs (no terminators); mate_pos = PNEXT (0-based, -1 if absent);
+ *   mate_ref: 1 = RNEXT is this contig, 0 = another contig, -1 = absent; tlen = TLEN.
+ *   n_pairs / n_bases (optional): pairs whose qualities were rewritten / quality bytes rewritten. */
+#define LVC_OVERLAP_OFF 0          /* pileup(ignore_overlaps=False) */
+#define LVC_OVERLAP_HTSLIB_1_10 1  /* htslib <= 1.10: the later mate is zeroed */
+#define LVC_OVERLAP_HTSLIB_1_13 2  /* htslib >= 1.13: mate chosen by a hash of the read name; deletions handled */
+#define LVC_OVERLAP_DEFAULT LVC_OVERLAP_HTSLIB_1_13
+int lvc_admit_overlaps(uint32_t n_reads, const int32_t* pos, const uint16_t* flag, const uint8_t* mapq,
+                       const uint32_t* cigar_off, const uint32_t* cigar, const uint64_t* seq_off, const uint8_t* seq4,
+                       uint8_t* qual, const uint32_t* name_off, const char* names, const int32_t* mate_pos,
+                       const int8_t* mate_ref, const int32_t* tlen, int min_mapping_quality, int max_depth,
+                       int overlap_model, uint8_t* keep_out, uint64_t* n_pairs, uint64_t* n_bases);
+
 /* ---- native host ingest (no GPU needed): BAM (BGZF, multi-threaded inflate) or SAM text -> packed batch ----
  * Replaces pysam.AlignmentFile(inputBam, 'rb') + the region iterator (live_variant_caller.py:55-60) and, for SAM
  * input, pysam.sort's order (client_server/vc_queue.py:34).  Reads of `contig` (NULL / "" = first @SQ) are packed
  * into page-locked arrays when a CUDA device is present (lvc_push_batch then reads the payload in place), the keep
- * mask (lvc_admit + the ACGT-only hint) is filled in.  Records the path cannot reproduce (missing qualities,
- * overlapping proper pairs, CG-tag CIGARs) are refused with LVC_EINVAL and a message in errbuf.
+ * mask (lvc_admit_overlaps + the ACGT-only hint) is filled in and the qualities of overlapping mates are rewritten
+ * (lvc_read_alignments uses LVC_OVERLAP_DEFAULT; lvc_read_alignments_ex takes the model).  Records the path cannot
+ * reproduce (missing qualities, CG-tag CIGARs) are refused with LVC_EINVAL and a message in errbuf.  Re-entrant: any
+ * number of threads may call it at once (the phase timer is per call).
  * n_threads <= 0: all host threads.  The page-locked arrays of a freed lvc_reads go to a process-wide pool (at most
  * 4 GiB parked) and are reused by later calls; LVC_INGEST_TIMING=1 in the environment prints the phase times. */
 typedef struct lvc_reads lvc_reads;
 int lvc_read_alignments(const char* path, const char* contig, int min_mapping_quality, int max_depth, int n_threads,
                         lvc_reads** out, char* errbuf, int errlen);
+int lvc_read_alignments_ex(const char* path, const char* contig, int min_mapping_quality, int max_depth, int n_threads,
+                           int overlap_model, lvc_reads** out, char* errbuf, int errlen);
+int lvc_reads_overlap_stats(const lvc_reads* r, uint64_t* n_pairs, uint64_t* n_bases);
 int lvc_reads_batch(const lvc_reads* r, lvc_batch* batch_out);   /* pointers stay valid until lvc_reads_free */
 int lvc_reads_info(const lvc_reads* r, char* contig_name, int name_cap, int64_t* contig_len, int* n_contigs, int* pinned);
 void lvc_reads_free(lvc_reads* r);
 
 /* ---- deposit: process_bam / process_pileup_column / process_svn (live_variant_caller.py:54-103) ----
  * Walks every kept read's CIGAR on the device and adds its bases/qualities to the persistent
- * per-position tables.  Accumulates across calls (live batches).  `impl`: 0 = auto (4 for short-read batches, 3 for
- * batches averaging more than 4 CIGAR ops per read), 1 = general kernel only (one thread per read), 2 = tiled kernel
- * staging the raw payload with TMA, 3 = one warp per read (long reads, wide quality alphabets), 4 = tiled kernel
- * staging 4-bit keys (the tiled kernels use the warp path for the reads they cannot take). */
+ * per-position tables.  Accumulates across calls (live batches).  `impl`: 0 = auto (the tiled kernel for short-read
+ * batches, 3 for batches averaging more than 4 CIGAR ops per read), 1 = general kernel only (one thread per read),
+ * 2 = tiled kernel staging the raw payload with TMA, 3 = long-read kernel (wide quality alphabets), 4 = tiled kernel
+ * staging 4-bit keys with SWAR counters, 5 = tiled kernel with bit-sliced counters and per-task flush (the tiled
+ * kernels use the warp path for the reads they cannot take). */
 int lvc_push_batch(lvc_handle* h, const lvc_batch* host_batch);
 int lvc_push_batch_device(lvc_handle* h, const lvc_batch* device_batch);
 int lvc_set_impl(lvc_handle* h, int impl);

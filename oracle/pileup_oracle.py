@@ -79,11 +79,14 @@ def _seq_prod(values: Sequence[float]) -> float:
 # --------------------------------------------------------------------------------------------
 class Read:
     """One alignment record as the pileup engine sees it (pos is 0-based)."""
-    __slots__ = ("name", "flag", "pos", "mapq", "cigar", "seq", "qual")
+    __slots__ = ("name", "flag", "pos", "mapq", "cigar", "seq", "qual", "mpos", "mref", "tlen")
 
     def __init__(self, flag: int, pos: int, mapq: int, cigar: List[Tuple[int, int]], seq: str,
-                 qual: Sequence[int], name: str = "r"):
+                 qual: Sequence[int], name: str = "r", mpos: int = -1, mref: int = -1, tlen: int = 0):
         self.name = name
+        self.mpos = mpos              # PNEXT, 0-based (-1: absent)
+        self.mref = mref              # RNEXT: 1 = this contig, 0 = another contig, -1 = absent
+        self.tlen = tlen
         self.flag = flag
         self.pos = pos
         self.mapq = mapq
@@ -131,7 +134,9 @@ def read_sam(path: str, contig: Optional[str] = None) -> Tuple[List[Tuple[str, i
             if t[2] != contig:
                 continue
             qual = [ord(c) - 33 for c in t[10]] if t[10] != "*" else [255] * len(t[9])
-            reads.append(Read(int(t[1]), int(t[3]) - 1, int(t[4]), parse_cigar(t[5]), t[9].upper(), qual, t[0]))
+            mref = 1 if t[6] in ("=", t[2]) else (-1 if t[6] == "*" else 0)
+            reads.append(Read(int(t[1]), int(t[3]) - 1, int(t[4]), parse_cigar(t[5]), t[9].upper(), qual, t[0],
+                              int(t[7]) - 1, mref, int(t[8])))
     return contigs, reads
 
 
@@ -156,12 +161,221 @@ def passes_read_filter(r: Read, min_mapq: int) -> bool:
 
 
 # --------------------------------------------------------------------------------------------
+# htslib mate-overlap handling (pysam pileup default ignore_overlaps=True)  [EXT B5, parity unpinned]
+# --------------------------------------------------------------------------------------------
+OVERLAP_OFF, OVERLAP_HTSLIB_1_10, OVERLAP_HTSLIB_1_13 = 0, 1, 2
+
+
+def _x31_hash_string(name: str) -> int:
+    """khash.h __ac_X31_hash_string."""
+    b = name.encode("latin-1")
+    if not b:
+        return 0
+    h = b[0]
+    for c in b[1:]:
+        h = ((h << 5) - h + c) & 0xFFFFFFFF
+    return h
+
+
+def _wang_hash(key: int) -> int:
+    """khash.h __ac_Wang_hash (32 bit)."""
+    m = 0xFFFFFFFF
+    key = (key + (~(key << 15) & m)) & m
+    key ^= key >> 10
+    key = (key + (key << 3)) & m
+    key ^= key >> 6
+    key = (key + (~(key << 11) & m)) & m
+    key ^= key >> 16
+    return key
+
+
+class _Cur:
+    """state of htslib's cigar_iref2iseq_set / cigar_iref2iseq_next over one read"""
+    __slots__ = ("cig", "k", "icig", "iseq", "iref")
+
+    def __init__(self, cigar):
+        self.cig, self.k, self.icig, self.iseq, self.iref = cigar, 0, 0, 0, 0
+
+
+def _iref2iseq_set(c: _Cur, want: int) -> int:
+    pos = want
+    if pos < 0:
+        return -1
+    c.icig = c.iseq = c.iref = 0
+    while c.k < len(c.cig):
+        op, n = c.cig[c.k]
+        if op == 4:
+            c.k += 1; c.iseq += n; c.icig = 0
+        elif op in (5, 6):
+            c.k += 1; c.icig = 0
+        elif op in _MATCH_OPS:
+            pos -= n
+            if pos < 0:
+                c.icig = n + pos; c.iseq += c.icig; c.iref += c.icig
+                return 0
+            c.k += 1; c.iseq += n; c.icig = 0; c.iref += n
+        elif op == 1:
+            c.k += 1; c.iseq += n; c.icig = 0
+        elif op in (2, 3):
+            pos -= n
+            if pos < 0:
+                pos = 0
+            c.k += 1; c.icig = 0; c.iref += n
+        else:
+            return -2
+    c.iseq = -1
+    return -1
+
+
+def _iref2iseq_next(c: _Cur) -> int:
+    while c.k < len(c.cig):
+        op, n = c.cig[c.k]
+        if op in _MATCH_OPS:
+            if c.icig >= n - 1:
+                c.icig = -1; c.k += 1
+                continue
+            c.iseq += 1; c.icig += 1; c.iref += 1
+            return 0
+        if op in (2, 3):
+            c.k += 1; c.iref += n; c.icig = -1
+        elif op in (1, 4):
+            c.k += 1; c.iseq += n; c.icig = -1
+        elif op in (5, 6):
+            c.k += 1; c.icig = -1
+        else:
+            return -2
+    c.iseq = -1
+    c.iref = -1
+    return -1
+
+
+def tweak_overlap_quality(a: Read, b: Read, model: int) -> int:
+    """htslib sam.c tweak_overlap_quality(a = buffered first read, b = read being pushed): rewrites a.qual / b.qual
+    in place over the reference positions both reads cover.  Returns the number of rewritten positions."""
+    ca, cb = _Cur(a.cigar), _Cur(b.cigar)
+    iref = b.pos
+    a_ret = _iref2iseq_set(ca, iref - a.pos)
+    if a_ret < 0:
+        return 0
+    b_ret = _iref2iseq_set(cb, iref - b.pos)
+    if b_ret < 0:
+        return 0
+    legacy = model == OVERLAP_HTSLIB_1_10
+    if legacy:
+        amul, bmul = 1, 0
+    elif _wang_hash(_x31_hash_string(a.name)) & 1:
+        amul, bmul = 1, 0
+    else:
+        amul, bmul = 0, 1
+    touched = 0
+    while True:
+        while a_ret >= 0 and ca.iref >= 0 and ca.iref < iref - a.pos:
+            a_ret = _iref2iseq_next(ca)
+        if a_ret < 0:
+            break
+        if iref < ca.iref + a.pos:
+            iref = ca.iref + a.pos
+        while b_ret >= 0 and cb.iref >= 0 and cb.iref < iref - b.pos:
+            b_ret = _iref2iseq_next(cb)
+        if b_ret < 0:
+            break
+        if iref < cb.iref + b.pos:
+            iref = cb.iref + b.pos
+        iref += 1
+        if ca.iref + a.pos != cb.iref + b.pos:
+            if legacy:
+                continue
+            if ca.iref + a.pos < cb.iref + b.pos and cb.k > 0 and b.cigar[cb.k - 1][0] == 2:
+                done = False
+                while True:
+                    if 0 <= ca.iseq < len(a.qual):
+                        a.qual[ca.iseq] = int(a.qual[ca.iseq] * 0.8) if amul else 0
+                        touched += 1
+                    a_ret = _iref2iseq_next(ca)
+                    if a_ret < 0:
+                        done = True
+                        break
+                    if not ca.iref + a.pos < cb.iref + b.pos:
+                        break
+                if done:
+                    return touched
+            elif ca.k > 0 and a.cigar[ca.k - 1][0] == 2:
+                done = False
+                while True:
+                    if 0 <= cb.iseq < len(b.qual):
+                        b.qual[cb.iseq] = int(b.qual[cb.iseq] * 0.8) if bmul else 0
+                        touched += 1
+                    b_ret = _iref2iseq_next(cb)
+                    if b_ret < 0:
+                        done = True
+                        break
+                    if not cb.iref + b.pos < ca.iref + a.pos:
+                        break
+                if done:
+                    return touched
+            else:
+                continue
+        if ca.iseq < 0 or cb.iseq < 0 or ca.iseq >= len(a.qual) or cb.iseq >= len(b.qual):
+            return touched
+        qa, qb = a.qual[ca.iseq], b.qual[cb.iseq]
+        touched += 1
+        if CHAR_TO_NIBBLE.get(a.seq[ca.iseq], 15) == CHAR_TO_NIBBLE.get(b.seq[cb.iseq], 15):
+            q = min(qa + qb, 200)
+            if legacy:
+                qa, qb = q, 0
+            else:
+                qa, qb = amul * q, bmul * q
+        elif legacy:
+            if qa >= qb:
+                qa, qb = int(0.8 * qa), 0
+            else:
+                qa, qb = 0, int(0.8 * qb)
+        else:
+            if qa > qb:
+                qa, qb = int(0.8 * qa), 0
+            elif qa < qb:
+                qa, qb = 0, int(0.8 * qb)
+            else:
+                qa, qb = int((amul * 0.8) * qa), int((bmul * 0.8) * qb)
+        a.qual[ca.iseq], b.qual[cb.iseq] = qa, qb
+    return touched
+
+
+def _query_length(r: Read) -> int:
+    return sum(l for op, l in r.cigar if op in _QRY_OPS)
+
+
+def _overlap_push(olap: Dict[str, "_Node"], nd: "_Node", model: int) -> int:
+    """htslib overlap_push for a node that has just been admitted.  Returns rewritten positions."""
+    r = nd.read
+    if (r.flag & 0x8) or not (r.flag & 0x2):
+        return 0
+    lq = _query_length(r)
+    if model == OVERLAP_HTSLIB_1_10:
+        if abs(r.tlen) >= 2 * lq:
+            return 0
+    else:
+        if r.mref == 0 or (abs(r.tlen) >= 2 * lq and r.mpos >= nd.end):
+            return 0
+    other = olap.get(r.name)
+    if other is None:
+        if model == OVERLAP_HTSLIB_1_10 or r.mpos >= r.pos or ((r.flag & 0x1) and r.mpos == -1):
+            olap[r.name] = nd
+        return 0
+    del olap[r.name]
+    return tweak_overlap_quality(other.read, r, model)
+
+
+# --------------------------------------------------------------------------------------------
 # literal emulation of htslib bam_plp (push / next) -- small inputs only
 # --------------------------------------------------------------------------------------------
 class _Node:
     __slots__ = ("idx", "read", "beg", "end", "k", "x", "y")
 
-    def __init__(self, idx, read):
+    def __init__(self, idx, read, own_copy=False):
+        if own_copy:       # htslib buffers a copy (bam_copy1); the overlap handling rewrites that copy's qualities
+            read = Read(read.flag, read.pos, read.mapq, read.cigar, read.seq, list(read.qual), read.name, read.mpos,
+                        read.mref, read.tlen)
         self.idx, self.read = idx, read
         self.beg, self.end = read.pos, read.end()
         self.k, self.x, self.y = -1, 0, 0
@@ -212,14 +426,19 @@ def _resolve_cigar2(node: _Node, pos: int):
 
 
 def pileup_columns(reads: Iterable[Read], min_mapq: int, max_depth: int = MAX_DEPTH,
-                   admitted: Optional[List[int]] = None) -> Iterator[Tuple[int, List[Tuple[int, Read, bool, bool, int]]]]:
+                   admitted: Optional[List[int]] = None, overlap_model: int = OVERLAP_OFF,
+                   tweaked: Optional[Dict[int, List[int]]] = None
+                   ) -> Iterator[Tuple[int, List[Tuple[int, Read, bool, bool, int]]]]:
     """Literal restatement of bam_plp_auto/bam_plp_push/bam_plp_next for ONE contig (tid fixed).
 
     Yields (pos, [(read_index, read, is_del, is_refskip, qpos), ...]) for every column with >=1 entry,
     BEFORE the pysam base-quality filter.  `admitted`, when given, collects the indices of the reads
     that were admitted into the buffer (read-level filter passed and not dropped by max_depth).
+    `overlap_model` != OVERLAP_OFF emulates bam_plp_init_overlaps: the entries then carry the engine's own copies
+    of the reads with the rewritten qualities; `tweaked` collects {read index: rewritten quality list}.
     """
     buf: List[_Node] = []          # the linked list head..tail (without the sentinel)
+    olap: Dict[str, _Node] = {}    # htslib iter->overlaps: QNAME -> buffered node
     state = {"pos": 0, "max_pos": -1, "eof": False, "started": False}
 
     def plp_next():
@@ -232,7 +451,8 @@ def pileup_columns(reads: Iterable[Read], min_mapq: int, max_depth: int = MAX_DE
             keep = []
             for nd in buf:
                 if nd.end <= pos:
-                    continue                      # freed (mp_free): cnt decreases
+                    olap.pop(nd.read.name, None)  # overlap_remove, then freed (mp_free): cnt decreases
+                    continue
                 if nd.beg <= pos:
                     is_del, is_skip, qpos = _resolve_cigar2(nd, pos)
                     entries.append((nd.idx, nd.read, is_del, is_skip, qpos))
@@ -269,14 +489,20 @@ def pileup_columns(reads: Iterable[Read], min_mapq: int, max_depth: int = MAX_DE
             # bam_plp_push (iter->tid == b->core.tid: single contig, tid 0 -- see DESIGN.md)
             cnt = len(buf) + 1                     # mempool count incl. the tail sentinel
             if r.pos == state["pos"] and cnt > max_depth:
+                olap.pop(r.name, None)             # overlap_remove
                 continue                           # dropped by maxcnt
-            nd = _Node(idx, r)
+            nd = _Node(idx, r, own_copy=overlap_model != OVERLAP_OFF)
             state["max_pos"] = nd.beg
             state["started"] = True
             if nd.end > state["pos"]:
                 buf.append(nd)
                 if admitted is not None:
                     admitted.append(idx)
+                if overlap_model != OVERLAP_OFF:
+                    partner = olap.get(nd.read.name)
+                    if _overlap_push(olap, nd, overlap_model) and tweaked is not None:
+                        tweaked[partner.idx] = partner.read.qual
+                        tweaked[idx] = nd.read.qual
             col = plp_next()
             if col is not None:
                 yield col
@@ -338,7 +564,7 @@ class OracleCaller:
 
     def __init__(self, reference: str, minBaseQuality: int, minMappingQuality: int, minTotalDepth: int,
                  minAlleleDepth: int, minEvidenceRatio: float, maxVariants: int = 1,
-                 contig: str = "NC_045512.2", max_depth: int = MAX_DEPTH):
+                 contig: str = "NC_045512.2", max_depth: int = MAX_DEPTH, overlap_model: int = OVERLAP_OFF):
         self.reference = reference
         self.contig = contig
         self.minBaseQuality = minBaseQuality
@@ -348,6 +574,7 @@ class OracleCaller:
         self.minEvidenceRatio = minEvidenceRatio
         self.maxVariants = maxVariants
         self.max_depth = max_depth
+        self.overlap_model = overlap_model     # pysam's default is ignore_overlaps=True (OVERLAP_HTSLIB_*)
         self.memory: Dict[int, dict] = {}
 
     def reset_memory(self):
@@ -355,7 +582,8 @@ class OracleCaller:
 
     # live_variant_caller.py:54-72 + :74-103
     def process_reads(self, reads: Iterable[Read]):
-        for pos, entries in pileup_columns(reads, self.minMappingQuality, self.max_depth):
+        for pos, entries in pileup_columns(reads, self.minMappingQuality, self.max_depth,
+                                           overlap_model=self.overlap_model):
             # pysam PileupColumn.pileups: drop entries with qual[qpos] < min_base_quality (0 if qpos>=l_qseq)
             kept = []
             for idx, r, is_del, is_skip, qpos in entries:

@@ -117,14 +117,22 @@ def test_sam_and_bam_readers_agree(lib, tmp_path):
         samio.read_alignments(str(tmp_path / "missing.bam"), None, 0)
 
 
-def test_overlapping_mates_are_refused(lib, tmp_path):
-    from lvc_b200 import samio, packing
+def test_overlapping_mates_are_rewritten_not_refused(lib, tmp_path):
+    """proper pairs whose mates overlap (every real 2x150 amplicon run) are processed the way pysam's default
+    pileup(ignore_overlaps=True) does: qualities rewritten over the shared columns (tests/test_overlap_cpu.py has
+    the htslib emulation); ignore_overlaps=False leaves them alone"""
+    from lvc_b200 import samio, capi
     p = tmp_path / "ov.sam"
     p.write_text("@SQ\tSN:c\tLN:1000\n"
                  "a\t99\tc\t11\t60\t50M\t=\t41\t80\t" + "A" * 50 + "\t" + "I" * 50 + "\n"
                  "a\t147\tc\t41\t60\t50M\t=\t11\t-80\t" + "A" * 50 + "\t" + "I" * 50 + "\n")
-    with pytest.raises(packing.UnsupportedInput):
-        samio.read_sam(str(p), None, 0)
+    _, b = samio.read_sam(str(p), None, 0, overlap_model=capi.OVERLAP_HTSLIB_1_10)
+    assert b.overlap_pairs == 1 and b.overlap_bases == 20
+    assert b.qual[:50].tolist() == [40] * 30 + [80] * 20 and b.qual[50:100].tolist() == [0] * 20 + [40] * 30
+    _, b = samio.read_sam(str(p), None, 0, overlap_model=capi.OVERLAP_OFF)
+    assert b.overlap_pairs == 0 and b.qual[:100].tolist() == [40] * 100
+    _, b = samio.read_sam(str(p), None, 0)                    # default model: one of the mates keeps the sum
+    assert sorted([b.qual[30:50].tolist(), b.qual[50:70].tolist()]) == [[0] * 20, [80] * 20]
 
 
 def test_record_finalisation_matches_golden(golden_synth):
@@ -207,8 +215,13 @@ def test_native_ingest_matches_python_readers(lib, golden_synth, tmp_path):
     ov.write_text("@SQ\tSN:c\tLN:1000\n"
                   "a\t99\tc\t11\t60\t50M\t=\t41\t80\t" + "A" * 50 + "\t" + "I" * 50 + "\n"
                   "a\t147\tc\t41\t60\t50M\t=\t11\t-80\t" + "A" * 50 + "\t" + "I" * 50 + "\n")
-    with pytest.raises(packing.UnsupportedInput):
-        samio.read_alignments_native(str(ov), None, 0)
+    nat = samio.read_alignments_native(str(ov), None, 0)      # overlapping mates: rewritten, not refused
+    assert nat.overlap_pairs == 1 and nat.overlap_bases == 20
+    nat.close()
+    bad = tmp_path / "badq.sam"
+    bad.write_text("@SQ\tSN:c\tLN:1000\na\t0\tc\t11\t60\t5M\t*\t0\t0\tACGTA\tIII\n")
+    with pytest.raises(packing.UnsupportedInput):               # len(QUAL) != len(SEQ)
+        samio.read_alignments_native(str(bad), None, 0)
 
 
 def test_native_ingest_random_files_match_python_readers(lib, tmp_path):

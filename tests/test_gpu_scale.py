@@ -72,7 +72,7 @@ def check_against_c_oracle(ref, batches, th, impl, max_depth=8000):
     return n_emit
 
 
-@pytest.mark.parametrize("impl", [1, 2, 4])
+@pytest.mark.parametrize("impl", [1, 2, 4, 5])
 def test_amplicon_medium(lib, impl):
     from lvc_b200 import synth
     ref, b = synth.amplicon_sample(seed=7, n_pairs=120_000)
@@ -90,7 +90,7 @@ def test_amplicon_multi_quality(lib, th):
     check_against_c_oracle(ref, [b], th, 4)
 
 
-@pytest.mark.parametrize("impl", [1, 2, 4])
+@pytest.mark.parametrize("impl", [1, 2, 4, 5])
 def test_shotgun_small_genome(lib, impl):
     from lvc_b200 import synth
     ref, b = synth.shotgun_sample(seed=9, ref_len=200_000, depth=60.0)
@@ -110,7 +110,7 @@ def test_live_batches_ont(lib):
     ref = synth.random_reference(6000, 3)
     batches = [synth.ont_batch(100 + k, ref, depth=40.0) for k in range(3)]
     th = dict(minBQ=13, minMQ=20, minDP=10, minAD=3, ratio=0.05)
-    for impl in (0, 1, 2, 3, 4):          # 0 = auto: picks the warp-per-read kernel for these batches
+    for impl in (0, 1, 2, 3, 4, 5):          # 0 = auto: picks the warp-per-read kernel for these batches
         check_against_c_oracle(ref, batches, th, impl)
 
 
@@ -134,7 +134,7 @@ def test_full_size_config2_properties(lib):
     check_against_c_oracle(ref, [b], TH, 2)
     # both kernels agree bit for bit; depositing the batch twice doubles every count
     tabs = []
-    for impl, times in ((1, 1), (4, 1), (2, 2)):
+    for impl, times in ((1, 1), (4, 1), (2, 2), (5, 1)):
         h = capi.Handle(ref.encode("latin-1"), TH["minBQ"], TH["minMQ"], device=0)
         h.set_impl(impl)
         for _ in range(times):
@@ -146,6 +146,8 @@ def test_full_size_config2_properties(lib):
     assert np.array_equal(tabs[0][2], tabs[1][2])
     assert np.array_equal(tabs[2][0], 2 * tabs[1][0]) and np.array_equal(tabs[2][1], 2 * tabs[1][1])
     assert np.array_equal(tabs[2][2], tabs[1][2])                       # first-seen ranks do not move
+    for x, y in zip(tabs[3], tabs[1]):                                  # generation-5 tiled kernel == generation 4
+        assert np.array_equal(x, y)
 
 
 def test_pinned_host_buffers_are_read_in_place(lib):
@@ -179,6 +181,6 @@ def test_long_reads_with_many_cigar_ops(lib):
     b1 = synth.ont_batch_fast(501, ref, depth=40.0, ref_span=2400, n_runs=60)
     b2 = synth.ont_batch_fast(502, ref, depth=25.0, ref_span=6000, n_runs=200)
     assert b1.n_cigar == 121 * b1.n_reads and b2.n_cigar == 401 * b2.n_reads
-    for impl in (0, 3, 4):
+    for impl in (0, 3, 4, 5):
         check_against_c_oracle(ref, [b1, b2], dict(minBQ=20, minMQ=20, minDP=5, minAD=2, ratio=0.05), impl)
     check_against_c_oracle(ref, [b2, b1], dict(minBQ=0, minMQ=0, minDP=1, minAD=1, ratio=0.0), 0)
