@@ -29,9 +29,11 @@ __device__ __forceinline__ void deposit_base(const TableView& tv, const DepositP
     atomicAdd(&tv.planes[pl][cell], 1u);
     // first-seen ordinal.  Every quality plane of a group shares ONE first-seen cell per (column, allele): at depth d
     // an unconditional RED.MIN would put d same-address atomics per batch on it (they serialise in L2), so test first;
-    // after the first reads of a column the test fails and nothing is written
+    // after the first reads of a column the test fails and nothing is written.  The test may read a STALE line from L1:
+    // the cell only ever decreases, so a stale value is >= the current one and can only cause a redundant atomicMin,
+    // never a missed one (and the reads of a CTA share a few hundred columns, so the test mostly hits L1).
     uint32_t* f = tv.first[gs >> 2] + cell;
-    if (__ldcg(f) > ord) atomicMin(f, ord);
+    if (*f > ord) atomicMin(f, ord);
 }
 
 // Walk one read (one thread).

@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -21,6 +22,9 @@
 using namespace lvc;
 
 static thread_local std::string g_create_error;
+// every per-position table is allocated with this many extra rows, so that an in-place reduce-scatter onto position
+// slices of ceil((G+1)/n) rows (lvc_reduce_tables) stays inside the allocation for any n < kRowSlack - 1
+constexpr int kRowSlack = 258;
 
 struct DevBuf {
     void* p = nullptr;
@@ -59,6 +63,8 @@ struct lvc_handle {
     uint32_t* d_replay = nullptr;            // [32]
     uint32_t* d_status = nullptr;            // [ST_WORDS]
     uint32_t* h_status = nullptr;            // pinned [ST_WORDS + 32]
+    uint8_t* d_keymap = nullptr;             // [kMaxKeys] plane presence map (lvc_reduce_tables)
+    uint64_t last_exchange_bytes = 0;        // bytes this rank put into the last lvc_reduce_tables
 
     // batch staging (device copies of host batches)
     DevBuf b_pos, b_flag, b_mapq, b_keep, b_coff, b_cig, b_soff, b_seq, b_qual;
@@ -147,7 +153,7 @@ static int add_plane(lvc_handle* h, uint16_t key) {
     if (key >= kMaxKeys) return fail(h, LVC_EINVAL, "plane key %u out of range", key);
     if (h->lut[key] != kNoPlane) return LVC_OK;
     const int g = key >> 8;
-    const size_t bytes = (size_t)h->G * 4 * sizeof(uint32_t);
+    const size_t bytes = ((size_t)h->G + kRowSlack) * 4 * sizeof(uint32_t);
     if (!h->d_first[g]) {
         CU(cudaMalloc(&h->d_first[g], bytes));
         CU(cudaMemsetAsync(h->d_first[g], 0xFF, bytes, h->stream));
@@ -203,10 +209,10 @@ int lvc_create(lvc_handle** out, int device, int64_t ref_len, const uint8_t* ref
         CU(cudaMemsetAsync(h->d_planes, 0, kMaxKeys * sizeof(uint32_t*), h->stream));
         CU(cudaMalloc(&h->d_lut, kMaxKeys * sizeof(uint16_t)));
         CU(cudaMemsetAsync(h->d_lut, 0xFF, kMaxKeys * sizeof(uint16_t), h->stream));
-        CU(cudaMalloc(&h->d_dels, G * sizeof(uint32_t)));
-        CU(cudaMemsetAsync(h->d_dels, 0, G * sizeof(uint32_t), h->stream));
-        CU(cudaMalloc(&h->d_covdiff, (G + 1) * sizeof(int32_t)));
-        CU(cudaMemsetAsync(h->d_covdiff, 0, (G + 1) * sizeof(int32_t), h->stream));
+        CU(cudaMalloc(&h->d_dels, (G + kRowSlack) * sizeof(uint32_t)));
+        CU(cudaMemsetAsync(h->d_dels, 0, (G + kRowSlack) * sizeof(uint32_t), h->stream));
+        CU(cudaMalloc(&h->d_covdiff, (G + kRowSlack) * sizeof(int32_t)));
+        CU(cudaMemsetAsync(h->d_covdiff, 0, (G + kRowSlack) * sizeof(int32_t), h->stream));
         CU(cudaMalloc(&h->d_first_arr, 4 * sizeof(uint32_t*)));
         CU(cudaMemsetAsync(h->d_first_arr, 0, 4 * sizeof(uint32_t*), h->stream));
         CU(cudaMalloc(&h->d_newkeys, 32 * sizeof(uint32_t)));
@@ -220,6 +226,10 @@ int lvc_create(lvc_handle** out, int device, int64_t ref_len, const uint8_t* ref
         CU(cudaMalloc(&h->d_out_depth, G * sizeof(uint32_t)));
         CU(cudaMalloc(&h->d_out_ad, G * 4 * sizeof(uint32_t)));
         CU(cudaMalloc(&h->d_out_lik, G * 4 * sizeof(double)));
+        // positions outside a restricted genotype range are never written: they read back as zero, not as garbage
+        CU(cudaMemsetAsync(h->d_out_depth, 0, G * sizeof(uint32_t), h->stream));
+        CU(cudaMemsetAsync(h->d_out_ad, 0, G * 4 * sizeof(uint32_t), h->stream));
+        CU(cudaMemsetAsync(h->d_out_lik, 0, G * 4 * sizeof(double), h->stream));
         CU(cudaMalloc(&h->d_cand_count, 2 * sizeof(uint32_t)));
         CU(cudaMemsetAsync(h->d_cand_count, 0, 2 * sizeof(uint32_t), h->stream));
         CU(cudaFuncSetAttribute(k_deposit_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
@@ -248,7 +258,7 @@ void lvc_destroy(lvc_handle* h) {
     for (auto p : h->planes) cudaFree(p);
     for (int g = 0; g < 4; ++g) cudaFree(h->d_first[g]);
     cudaFree(h->d_ref); cudaFree(h->d_planes); cudaFree(h->d_lut); cudaFree(h->d_dels); cudaFree(h->d_covdiff);
-    cudaFree(h->d_first_arr); cudaFree(h->d_newkeys); cudaFree(h->d_replay); cudaFree(h->d_status);
+    cudaFree(h->d_first_arr); cudaFree(h->d_newkeys); cudaFree(h->d_replay); cudaFree(h->d_status); cudaFree(h->d_keymap);
     if (h->h_status) cudaFreeHost(h->h_status);
     if (h->h_sample) cudaFreeHost(h->h_sample);
     for (int w = 0; w < 3; ++w) for (auto& pr : h->ev[w]) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
@@ -294,6 +304,9 @@ int lvc_reset(lvc_handle* h) {
         if (h->d_first[g]) CU(cudaMemsetAsync(h->d_first[g], 0xFF, G * 4 * sizeof(uint32_t), h->stream));
     CU(cudaMemsetAsync(h->d_dels, 0, G * sizeof(uint32_t), h->stream));
     CU(cudaMemsetAsync(h->d_covdiff, 0, (G + 1) * sizeof(int32_t), h->stream));
+    CU(cudaMemsetAsync(h->d_out_depth, 0, G * sizeof(uint32_t), h->stream));
+    CU(cudaMemsetAsync(h->d_out_ad, 0, G * 4 * sizeof(uint32_t), h->stream));
+    CU(cudaMemsetAsync(h->d_out_lik, 0, G * 4 * sizeof(double), h->stream));
     h->ordinal = 0;
     CU(cudaStreamSynchronize(h->stream));
     return LVC_OK;
@@ -892,8 +905,9 @@ int lvc_import_first(lvc_handle* h, int group, const uint32_t* src) {
     if (!h || !src || group < 0 || group > 3) return LVC_EINVAL;
     CU(cudaSetDevice(h->device));
     if (!h->d_first[group]) {
-        const size_t bytes = (size_t)h->G * 16;
+        const size_t bytes = ((size_t)h->G + kRowSlack) * 16;
         CU(cudaMalloc(&h->d_first[group], bytes));
+        CU(cudaMemsetAsync(h->d_first[group], 0xFF, bytes, h->stream));
         CU(cudaMemcpyAsync(h->d_first_arr + group, &h->d_first[group], sizeof(uint32_t*), cudaMemcpyHostToDevice, h->stream));
     }
     CU(cudaMemcpyAsync(h->d_first[group], src, (size_t)h->G * 16, cudaMemcpyHostToDevice, h->stream));
@@ -918,4 +932,5 @@ uint64_t lvc_h2d_payload_bytes(lvc_handle* h) { return h ? h->h2d_payload_bytes 
 
 }  // extern "C"
 
+#include "reduce_nccl.hpp"
 #include "ingest.hpp"

@@ -108,6 +108,12 @@ SIGNATURES = [
     ("lvc_dels_devptr", C.c_void_p, [_H]),
     ("lvc_covdiff_devptr", C.c_void_p, [_H]),
     ("lvc_first_devptr", C.c_void_p, [_H, C.c_int]),
+    ("lvc_nccl_unique_id", C.c_int, [C.c_void_p]),
+    ("lvc_nccl_comm_create", C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    ("lvc_nccl_comm_destroy", None, [C.c_void_p]),
+    ("lvc_position_slice", C.c_int, [_H, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    ("lvc_reduce_tables", C.c_int, [_H, C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    ("lvc_last_exchange_bytes", C.c_uint64, [_H]),
     ("lvc_launch_count", C.c_uint64, [_H]),
     ("lvc_h2d_payload_bytes", C.c_uint64, [_H]),
 ]
@@ -259,6 +265,44 @@ class NativeReads:
             pass
 
 
+REDUCE_ALL, REDUCE_SCATTER = 0, 1
+
+
+def nccl_unique_id() -> bytes:
+    """128 bytes identifying a new NCCL communicator (rank 0 creates it and ships it to the other ranks)."""
+    lib = load_library()
+    buf = C.create_string_buffer(128)
+    rc = lib.lvc_nccl_unique_id(buf)
+    if rc != LVC_OK:
+        raise LvcError(rc, lib.lvc_last_error(None).decode())
+    return buf.raw
+
+
+class NcclComm:
+    """An ncclComm_t owned by the library (one per process = per GPU)."""
+
+    def __init__(self, device: int, n_ranks: int, rank: int, unique_id: bytes):
+        self.lib = load_library()
+        self.n_ranks, self.rank = int(n_ranks), int(rank)
+        c = C.c_void_p()
+        idb = C.create_string_buffer(unique_id, 128)
+        rc = self.lib.lvc_nccl_comm_create(C.byref(c), int(device), self.n_ranks, self.rank, idb)
+        if rc != LVC_OK:
+            raise LvcError(rc, self.lib.lvc_last_error(None).decode())
+        self.c = c
+
+    def close(self):
+        if getattr(self, "c", None):
+            self.lib.lvc_nccl_comm_destroy(self.c)
+            self.c = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Handle:
     """Owns one lvc_handle (one contig's persistent device tables)."""
 
@@ -358,6 +402,16 @@ class Handle:
         out = np.zeros(max(n.value, 1), dtype=CANDIDATE_DTYPE)
         self._check(self.lib.lvc_fetch_candidates(self.h, out.ctypes.data, len(out), C.byref(n)))
         return out[:n.value]
+
+    def reduce_tables(self, comm: NcclComm, mode: int = REDUCE_SCATTER) -> int:
+        """the one exchange step of the read-chunk sharding (lvc_reduce_tables); returns the bytes fed in"""
+        self._check(self.lib.lvc_reduce_tables(self.h, comm.c, comm.n_ranks, comm.rank, int(mode)))
+        return int(self.lib.lvc_last_exchange_bytes(self.h))
+
+    def position_slice(self, n_ranks: int, rank: int):
+        p0, p1 = C.c_int64(0), C.c_int64(0)
+        self._check(self.lib.lvc_position_slice(self.h, int(n_ranks), int(rank), C.byref(p0), C.byref(p1)))
+        return int(p0.value), int(p1.value)
 
     def set_genotype_range(self, p0: int, p1: int):
         self._check(self.lib.lvc_set_genotype_range(self.h, int(p0), int(p1)))

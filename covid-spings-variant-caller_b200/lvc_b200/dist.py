@@ -126,8 +126,9 @@ def allreduce_handle(handle, group=None) -> int:
 
 
 def position_slice(G: int, world_size: int, rank: int) -> Tuple[int, int]:
-    """contiguous slice of positions a rank genotypes after the table reduce"""
-    per = (G + world_size - 1) // world_size
+    """contiguous slice of positions a rank owns / genotypes after the exchange: ceil((G+1)/n) rows per rank, the
+    same rule as the library's lvc_position_slice (the coverage difference array has G + 1 entries)"""
+    per = (G + 1 + world_size - 1) // world_size
     return min(rank * per, G), min((rank + 1) * per, G)
 
 
@@ -293,6 +294,41 @@ def process_batch_halo(caller, batch: ReadBatch, group=None) -> int:
     p0, p1 = position_slice(h.G, world, rank)
     h.set_genotype_range(p0, p1)
     return sent
+
+
+def make_library_comm(device: int, group=None):
+    """an NCCL communicator owned by liblvc_b200.so (capi.NcclComm) spanning the ranks of the torch.distributed
+    group: rank 0 draws the unique id, torch.distributed ships its 128 bytes"""
+    import torch.distributed as dist
+    from . import capi
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    box = [capi.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    return capi.NcclComm(device, world, rank, box[0])
+
+
+def process_batch_library(caller, batch: ReadBatch, comm, mode: str = "scatter") -> int:
+    """One sample, read-chunk sharding through the C-ABI exchange (lvc_reduce_tables): every rank deposits its
+    contiguous chunk of the coordinate-sorted batch, then ONE grouped NCCL collective over all tables:
+    mode "scatter": reduce-scatter in place onto position slices (each rank keeps the history of its slice and
+    genotypes it); mode "all": all-reduce (every rank holds the complete tables; rank 0 keeps the history between
+    batches, like process_batch_sharded).  Use one mode per caller.  Returns the bytes this rank fed in."""
+    from . import capi
+    h = caller._handle
+    world, rank = comm.n_ranks, comm.rank
+    base = h.ordinal
+    if mode == "all" and rank != 0:
+        h.reset()
+    a, b = shard_reads(batch, world)[rank]
+    h.ordinal = base + a                      # first-seen ordinals are global read indices
+    if b > a:
+        h.push_batch(batch.slice(a, b).as_capi())
+    h.ordinal = base + batch.n_reads
+    n = h.reduce_tables(comm, capi.REDUCE_SCATTER if mode == "scatter" else capi.REDUCE_ALL)
+    if mode == "all":
+        p0, p1 = h.position_slice(world, rank)
+        h.set_genotype_range(p0, p1)
+    return n
 
 
 def gather_variants(caller, group=None) -> List[dict]:

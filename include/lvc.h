@@ -215,6 +215,28 @@ void* lvc_dels_devptr(lvc_handle* h);
 void* lvc_covdiff_devptr(lvc_handle* h);
 void* lvc_first_devptr(lvc_handle* h, int group);
 
+/* ---- multi-GPU: the one exchange step of the read-chunk sharding -----------------------------
+ * The reference is a single process (client_server/vc_queue.py:99); its state update is a commutative integer
+ * add per (position, allele, quality) and a min per first-seen rank, so ranks that deposited different chunks
+ * of one coordinate-sorted batch combine with ONE collective.  lvc_reduce_tables issues it as one NCCL group on
+ * the handle's stream, on the device tables themselves: integer SUM for the count planes / deletion counts /
+ * coverage, unsigned MIN for the first-seen ordinals; the set of (allele group, quality) planes is agreed first.
+ *   LVC_REDUCE_ALL     all-reduce: every rank holds the complete tables afterwards.
+ *   LVC_REDUCE_SCATTER reduce-scatter in place onto position slices (lvc_position_slice): rank r keeps the complete
+ *                      history of its slice only, the rest of its tables is cleared, and its genotype range is set to
+ *                      the slice.  Ranks must then keep owning the same slice for the lifetime of the handle.
+ * `nccl_comm` is an ncclComm_t (from lvc_nccl_comm_create, or the caller's own).  NCCL is bound at run time
+ * (dlopen of libnccl.so.2); without it these return LVC_EIO.  The max_depth keep mask must be computed over the
+ * WHOLE batch before it is split, and each rank sets lvc_set_ordinal(base + first read index of its chunk). */
+#define LVC_REDUCE_ALL 0
+#define LVC_REDUCE_SCATTER 1
+int lvc_nccl_unique_id(uint8_t id_out[128]);                       /* rank 0; ship the 128 bytes to the other ranks */
+int lvc_nccl_comm_create(void** comm_out, int device, int n_ranks, int rank, const uint8_t id[128]);
+void lvc_nccl_comm_destroy(void* comm);
+int lvc_position_slice(const lvc_handle* h, int n_ranks, int rank, int64_t* p0, int64_t* p1);
+int lvc_reduce_tables(lvc_handle* h, void* nccl_comm, int n_ranks, int rank, int mode);
+uint64_t lvc_last_exchange_bytes(lvc_handle* h);    /* bytes this rank fed into the last lvc_reduce_tables */
+
 /* ---- introspection ---------------------------------------------------------------------------- */
 /* number of kernels this library has launched on the handle since creation (bench gpu_launches) */
 uint64_t lvc_launch_count(lvc_handle* h);

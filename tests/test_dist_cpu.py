@@ -209,8 +209,10 @@ def test_halo_plan_and_touched_ranges(lib, golden_synth):
             want[own0:own1] = 0
             assert np.array_equal(cols, want)
     # chunks that stay inside their own slices: nothing to exchange
-    assert ldist.halo_plan(100, 2, [(0, 50), (50, 100)]) == {}
-    assert ldist.halo_plan(100, 2, [(0, 60), (50, 100)]) == {(0, 1): (50, 60)}
+    # slices of ceil((G + 1) / n) = 51 rows: [0, 51) and [51, 100)
+    assert ldist.position_slice(100, 2, 0) == (0, 51) and ldist.position_slice(100, 2, 1) == (51, 100)
+    assert ldist.halo_plan(100, 2, [(0, 51), (51, 100)]) == {}
+    assert ldist.halo_plan(100, 2, [(0, 60), (51, 100)]) == {(0, 1): (51, 60)}
 
 
 def test_ont_batch_fast_is_deterministic_and_well_formed(lib):

@@ -39,17 +39,21 @@ def _worker(rank, world, port, rows, ref, q, mode="full"):
     th = dict(minBQ=13, minMQ=0, minDP=3, minAD=2, ratio=0.05)
     lvc = LiveVariantCaller(fa, th["minBQ"], th["minMQ"], th["minDP"], th["minAD"], th["ratio"], 1, device=rank)
     out = []
+    comm = ldist.make_library_comm(rank) if mode in ("lib_scatter", "lib_all") else None
     for k in range(3):                                   # three live batches
         sel = list(range(k, len(rows), 3))
         batch = packing.pack_reads(r2t([rows[i] for i in sel]), th["minMQ"])
-        if mode == "halo":
+        if comm is not None:
+            nbytes = ldist.process_batch_library(lvc, batch, comm, "scatter" if mode == "lib_scatter" else "all")
+            assert nbytes > 0
+        elif mode == "halo":
             sent = ldist.process_batch_halo(lvc, batch)
             assert sent < 4 * 4 * len(ref) * len(lvc._handle.plane_keys())      # a halo, not the tables
         else:
             ldist.process_batch_sharded(lvc, batch)
         out.append(ldist.gather_variants(lvc))
     lvc._handle.set_genotype_range(0, -1)
-    if mode == "halo":
+    if mode in ("halo", "lib_scatter"):
         # every rank keeps the history of its own slice of positions only
         p0, p1 = ldist.position_slice(len(ref), world, rank)
         lvc._candidates()                                  # genotype pass over all positions: fills the dense outputs
@@ -64,6 +68,8 @@ def _worker(rank, world, port, rows, ref, q, mode="full"):
         q.put((out, mem))
     dist.barrier()
     lvc.close()
+    if comm is not None:
+        comm.close()
     dist.destroy_process_group()
 
 
@@ -135,4 +141,47 @@ def test_two_ranks_halo_exchange_equal_one(lib, golden_synth, tmp_path):
     for p0, p1, d, a, outside in slices:
         assert d == depth[p0:p1].tolist() and a == ad[p0:p1].tolist()
         assert not outside
+    one.close()
+
+
+@pytest.mark.parametrize("mode", ["lib_scatter", "lib_all"])
+def test_two_ranks_library_exchange_equal_one(lib, golden_synth, tmp_path, mode):
+    """lvc_reduce_tables (the C-ABI exchange: one grouped NCCL reduce-scatter / all-reduce over the device tables):
+    records of every live batch and the tables must equal the single-GPU run"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from lvc_b200 import packing
+    from variant_caller.live_variant_caller import LiveVariantCaller
+    from helpers import memory_tables
+    g = golden_synth["amplicon_like"]
+    rows, ref = g["reads"], g["ref"]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, rows, ref, q, mode)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out, res = q.get(timeout=300)
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    fa = str(tmp_path / "c.fasta")
+    with open(fa, "w") as fh:
+        fh.write(">c\n" + ref + "\n")
+    th = dict(minBQ=13, minMQ=0, minDP=3, minAD=2, ratio=0.05)
+    one = LiveVariantCaller(fa, th["minBQ"], th["minMQ"], th["minDP"], th["minAD"], th["ratio"], 1, device=0)
+    for k in range(3):
+        sel = list(range(k, len(rows), 3))
+        one.process_batch(packing.pack_reads(rows_to_tuples([rows[i] for i in sel]), th["minMQ"]))
+        assert_variants_equal(out[k], one.prepare_variants(), f"batch {k}")
+    if mode == "lib_all":
+        assert res == memory_tables(one.memory)
+    else:
+        one._candidates()
+        depth, ad, _ = one._handle.copy_dense()
+        for p0, p1, d, a, outside in res:
+            assert d == depth[p0:p1].tolist() and a == ad[p0:p1].tolist()
+            assert not outside
     one.close()
