@@ -185,9 +185,10 @@ struct ReadHdr {
     uint32_t cg0, cg1, cg2;    // first CIGAR ops
 };
 
+template <int READS = kTileReads>
 __device__ __forceinline__ void hdr_load1(const BatchView& b, uint32_t chunk, int tid, ReadHdr& h, uint64_t& so0) {
-    const uint32_t chunk0 = chunk * kTileReads;
-    const uint32_t n = min((uint32_t)kTileReads, b.n_reads - chunk0);
+    const uint32_t chunk0 = chunk * READS;
+    const uint32_t n = min((uint32_t)READS, b.n_reads - chunk0);
     const bool mine = (uint32_t)tid < n;
     const uint32_t i = chunk0 + (mine ? tid : 0);
     h.pos = b.pos[i];

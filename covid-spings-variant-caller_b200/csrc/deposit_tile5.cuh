@@ -22,21 +22,33 @@
 namespace lvc {
 
 #ifndef LVC5_CTAS_PER_SM
-#define LVC5_CTAS_PER_SM 5
+#define LVC5_CTAS_PER_SM 7
 #endif
+#ifndef LVC5_THREADS
+#define LVC5_THREADS 192
+#endif
+// CTA = 192 threads = 192 reads: a chunk of 150 bp shotgun reads at 1,000x then spans 6 slabs of 32 columns whose
+// candidate runs fit ONE task each (<= 224 runs): 6 tasks for 6 warps, one reduction per warp per chunk, where 256
+// reads gave 12 tasks for 8 warps (two rounds, a quarter of the task phase idle)
+constexpr int kT5Threads = LVC5_THREADS;
+constexpr int kT5Warps = kT5Threads / 32;
+constexpr int kT5Reads = kT5Threads;              // one read header per thread
+static_assert(kT5Threads % 32 == 0 && kT5Threads <= 256, "read index in a chunk is stored in 8 bits");
+constexpr uint32_t kT5WinStride = kT5Reads * 160u;                   // payload bytes per staged window
+constexpr uint32_t kT5KeyCapBases = kT5WinStride + kMaxReadBytes;    // + one longest tileable read
 constexpr int kTile5CtasPerSM = LVC5_CTAS_PER_SM;
 constexpr int kTask5Runs = 224;                  // runs per task: 7 units per lane, three bit planes hold <= 7
 
 struct Tile5Smem {
     static constexpr uint32_t key_off = 0;                                     // 4-bit keys, little-endian nibble order
-    static constexpr uint32_t key_bytes = kSlack + kKeyCapBases / 2 + 32 + kSlack;
+    static constexpr uint32_t key_bytes = kSlack + kT5KeyCapBases / 2 + 32 + kSlack;
     static constexpr uint32_t pos_off = key_off + key_bytes;                   // i32 [kMaxRuns]
     static constexpr uint32_t qo_off = pos_off + kMaxRuns * 4;                 // u32 [kMaxRuns]
     static constexpr uint32_t len_off = qo_off + kMaxRuns * 4;                 // u16 [kMaxRuns]
     static constexpr uint32_t rd_off = len_off + kMaxRuns * 2;                 // u16 [kMaxRuns]
     static constexpr uint32_t rix_off = rd_off + kMaxRuns * 2;                 // u16 [kMaxRuns]
-    static constexpr uint32_t dlist_off = rix_off + kMaxRuns * 2;              // u16 [kTileReads]
-    static constexpr uint32_t slab_a_off = dlist_off + kTileReads * 2;         // u32 [kMaxSlabs]
+    static constexpr uint32_t dlist_off = rix_off + kMaxRuns * 2;              // u16 [kT5Reads]
+    static constexpr uint32_t slab_a_off = dlist_off + kT5Reads * 2;         // u32 [kMaxSlabs]
     static constexpr uint32_t slab_pre_off = slab_a_off + kMaxSlabs * 4;       // u32 [kMaxSlabs+1]
     static constexpr uint32_t slab_n_off = slab_pre_off + (kMaxSlabs + 1) * 4; // u32 [kMaxSlabs]
     static constexpr uint32_t slab_per_off = slab_n_off + kMaxSlabs * 4;       // u32 [kMaxSlabs] runs per task of the slab
@@ -80,7 +92,7 @@ __device__ __forceinline__ void bs_add(const uint32_t (&a)[N], const uint32_t (&
 // kernel parameters stay in the constant bank even where their address is taken (the warp-per-read helper takes
 // the views by reference): without this every thread copies them to local memory first
 template <bool GE_ALL>
-__global__ void __launch_bounds__(kTileThreads, kTile5CtasPerSM)
+__global__ void __launch_bounds__(kT5Threads, kTile5CtasPerSM)
 k_deposit_tile5(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp, LVC_GC TileParams tp) {
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t sbase = smem_u32(smem);
@@ -114,7 +126,7 @@ k_deposit_tile5(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
     const uint32_t cur = blockIdx.x;
     ReadHdr hd;
     uint64_t so0;
-    hdr_load1(b, cur, tid, hd, so0);
+    hdr_load1<kT5Reads>(b, cur, tid, hd, so0);
     uint32_t* sc = s_misc + 8;                                       // per-chunk scalars
     uint32_t* wc = s_misc + 32;                                      // runs per warp
     if (tid == 0) {
@@ -161,14 +173,25 @@ k_deposit_tile5(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
         }
         __syncthreads();
         const uint32_t n_def = s_misc[6];
-        for (uint32_t d = warp; d < n_def; d += kTileWarps) deposit_read_warp(b, tv, dp, cur * kTileReads + s_dlist[d], lane);
+        for (uint32_t d = warp; d < n_def; d += kT5Warps) deposit_read_warp(b, tv, dp, cur * kT5Reads + s_dlist[d], lane);
         return;
     }
     // staging base: 16-byte aligned start of the first such read
     const uint64_t base_abs = (so0 + min_rel) & ~15ull;
+#ifndef LVC5_NO_PREFETCH
+    {
+        // ask L2 for the chunk's payload now: classification and the run table hide the DRAM latency of the staging
+        // loads (measured on config 5: 0.524 -> 0.498 ms)
+        const uint64_t q0 = base_abs, q1 = so0 + max_rel;
+        for (uint64_t a = q0 + (uint64_t)tid * 128u; a < q1; a += (uint64_t)kT5Threads * 128u)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(b.qual + a));
+        for (uint64_t a = (q0 >> 1) + (uint64_t)tid * 128u; a < ((q1 + 1) >> 1); a += (uint64_t)kT5Threads * 128u)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(b.seq4 + a));
+    }
+#endif
     const uint32_t base_rel = (uint32_t)(base_abs - so0);            // may wrap below zero: used mod 2^32
     {
-        const uint32_t chunk0 = cur * kTileReads;
+        const uint32_t chunk0 = cur * kT5Reads;
         // ---- (2) classify this thread's read: filter, match runs, deletion entries
         int32_t run_pos[kMaxRunsPerRead] = {0, 0, 0};
         uint32_t run_len[kMaxRunsPerRead] = {0, 0, 0}, run_q[kMaxRunsPerRead] = {0, 0, 0};
@@ -320,7 +343,7 @@ k_deposit_tile5(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
         __syncthreads();                                                   // barrier A
         uint32_t n_runs = 0, my_base = 0;
 #pragma unroll
-        for (int w = 0; w < kTileWarps; ++w) {
+        for (int w = 0; w < kT5Warps; ++w) {
             const uint32_t c = wc[w];
             if (w < warp) my_base += c;
             n_runs += c;
@@ -358,7 +381,7 @@ k_deposit_tile5(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
         if (n_runs) {
             if (nr) {
                 const uint32_t off = so_rel - base_rel;                   // read's first byte relative to the base
-                const uint32_t win = off / kWinStride;
+                const uint32_t win = off / kT5WinStride;
                 const uint32_t idx0 = my_base + wprefix;
 #pragma unroll
                 for (int k = 0; k < kMaxRunsPerRead; ++k) {
@@ -370,7 +393,7 @@ k_deposit_tile5(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
                         s_rd[idx] = (uint16_t)(run_pos[k] - hd.pos);
                         s_rix[idx] = (uint16_t)((win << 8) | (uint32_t)tid);
                         // (start column, key offset inside the read's window | length << 16): one 8-byte load per unit
-                        s_pk[idx] = make_uint2((uint32_t)run_pos[k], ((off + run_q[k] - win * kWinStride) & 0xFFFFu) | (run_len[k] << 16));
+                        s_pk[idx] = make_uint2((uint32_t)run_pos[k], ((off + run_q[k] - win * kT5WinStride) & 0xFFFFu) | (run_len[k] << 16));
                     }
                 }
             }
@@ -389,7 +412,7 @@ k_deposit_tile5(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
                     a1 = lo;
                 }
                 if (a1 == a0 && win > 0) continue;
-                const uint32_t w_rel = win * kWinStride;                   // window start relative to the base
+                const uint32_t w_rel = win * kT5WinStride;                   // window start relative to the base
                 const uint64_t qbeg = base_abs + w_rel;                    // 16-byte aligned
                 // column range of these runs
                 const int32_t cmin = s_pos[a0] - (int32_t)s_rd[a0];
@@ -399,7 +422,7 @@ k_deposit_tile5(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
                     if (tid == 0) s_misc[4] = 0;
                     __syncthreads();
                     int32_t e = 0;
-                    for (uint32_t r = a0 + tid; r < a1; r += kTileThreads) e = max(e, s_pos[r] + (int32_t)s_len[r]);
+                    for (uint32_t r = a0 + tid; r < a1; r += kT5Threads) e = max(e, s_pos[r] + (int32_t)s_len[r]);
                     e = __reduce_max_sync(0xFFFFFFFFu, e);
                     if (lane == 0 && e) atomicMax(reinterpret_cast<int32_t*>(&s_misc[4]), e);
                     __syncthreads();
@@ -446,7 +469,7 @@ k_deposit_tile5(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
                 // ---- stage this window as KEYS: coalesced 16-byte loads, 16 bases per step, written in place once
                 if (a1 > a0) {
                     const uint64_t qend_all = so0 + max_rel;
-                    const uint64_t qend = qend_all < qbeg + kKeyCapBases ? qend_all : qbeg + kKeyCapBases;
+                    const uint64_t qend = qend_all < qbeg + kT5KeyCapBases ? qend_all : qbeg + kT5KeyCapBases;
                     const uint32_t n_grp = (uint32_t)(((qend - qbeg) + 15) >> 4);
                     const uint32_t chunk_ord = dp.ord_base + chunk0;
                     const uint4* gq = reinterpret_cast<const uint4*>(b.qual + qbeg);
@@ -500,17 +523,17 @@ k_deposit_tile5(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
                     // groups in flight costs 12 more live registers under the 48-register cap and measured 4 % slower:
                     // with 5 CTAs per SM the load latency is covered by the other CTAs.  One group per iteration is 8 % slower.)
                     if (warp == 0 && cmin < cmax) slab_setup(cmin);
-                    for (uint32_t g = tid; g < n_grp; g += 2 * kTileThreads) {
-                        const bool hasB = g + kTileThreads < n_grp;
+                    for (uint32_t g = tid; g < n_grp; g += 2 * kT5Threads) {
+                        const bool hasB = g + kT5Threads < n_grp;
                         // streaming loads: the payload is read exactly once and should not displace the few hot lines
                         // (plane pointers, key LUT) in the 38 KB of L1 left beside the shared memory: -4 %
                         const uint4 qA = __ldcs(gq + g);
                         const uint2 sA = __ldcs(gs + g);
                         uint4 qB = make_uint4(0, 0, 0, 0);
                         uint2 sB = make_uint2(0, 0);
-                        if (hasB) { qB = __ldcs(gq + g + kTileThreads); sB = __ldcs(gs + g + kTileThreads); }
+                        if (hasB) { qB = __ldcs(gq + g + kT5Threads); sB = __ldcs(gs + g + kT5Threads); }
                         stage_group(g, qA, sA);
-                        if (hasB) stage_group(g + kTileThreads, qB, sB);
+                        if (hasB) stage_group(g + kT5Threads, qB, sB);
                     }
                 }
 
@@ -694,7 +717,7 @@ k_deposit_tile5(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
         // ---- reads the tiled path could not take (many runs, long, exotic base codes): general path, one warp each
         __syncthreads();
         const uint32_t n_def = s_misc[6];
-        for (uint32_t d = warp; d < n_def; d += kTileWarps) deposit_read_warp(b, tv, dp, chunk0 + s_dlist[d], lane);
+        for (uint32_t d = warp; d < n_def; d += kT5Warps) deposit_read_warp(b, tv, dp, chunk0 + s_dlist[d], lane);
     }
 }
 

@@ -39,7 +39,7 @@ struct lvc_handle {
     bool own_stream = false;
     std::string err;
     int impl = 0;
-    int tile_impl = 4;                       // what impl 0 (auto) picks for short-read batches (LVC_TILE_IMPL overrides)
+    int tile_impl = 5;                       // what impl 0 (auto) picks for short-read batches (LVC_TILE_IMPL overrides)
     int sm_count = 148;
     uint64_t launches = 0;
     bool zero_copy_ok = true;                // read page-locked caller payload in place (LVC_ZERO_COPY=0 disables)
@@ -386,7 +386,8 @@ static int launch_deposit(lvc_handle* h, const BatchView& bv, int replay, uint64
               // programmatic stream serialization: the chunk headers are read (and dead chunks retire) while the
               // previous kernel of the stream drains; the kernel waits for it before its first table access
               cudaLaunchConfig_t cfg = {};
-              cfg.gridDim = dim3(tp.grid); cfg.blockDim = dim3(kTileThreads);
+              cfg.gridDim = dim3(impl == 5 ? (n + kT5Reads - 1) / kT5Reads : tp.grid);
+              cfg.blockDim = dim3(impl == 5 ? kT5Threads : kTileThreads);
               cfg.dynamicSmemBytes = impl == 5 ? kTile5SmemBytes : kTile4SmemBytes;
               cfg.stream = h->stream;
               cudaLaunchAttribute at[1];
@@ -417,12 +418,24 @@ static int deposit_with_replay(lvc_handle* h, const BatchView& bv, uint64_t n_ci
     CU(cudaMemcpyAsync(h->h_status, h->d_status, ST_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaMemcpyAsync(h->h_status + ST_WORDS, h->d_newkeys, 32 * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
     if (account) {
-        // zero-copy push: the payload bytes of admitted reads are what the kernel pulls over PCIe.  Counted here, on
-        // the host, while the kernel runs (branch-free: 2e6 reads in a fraction of a millisecond)
-        uint64_t live = 0;
+        // zero-copy push: what crosses PCIe is what the kernel requests -- per chunk of 256 reads the 16-byte groups
+        // of the byte extent [first live read, end of last live read) (dead reads in between ride along; chunks with no
+        // live read request nothing).  Counted here, on the host, while the kernel runs.
+        uint64_t moved = 0;
         const size_t n = account->n_reads;
-        for (size_t i = 0; i < n; ++i) live += (uint64_t)(account->keep[i] & 1u) * (account->seq_off[i + 1] - account->seq_off[i]);
-        h->h2d_payload_bytes += live + live / 2;
+        const size_t chunk = h->tile_impl == 5 ? (size_t)kT5Reads : (size_t)kTileReads;
+        for (size_t c0 = 0; c0 < n; c0 += chunk) {
+            const size_t c1 = std::min(n, c0 + chunk);
+            uint64_t lo = ~0ull, hi = 0;
+            for (size_t i = c0; i < c1; ++i) {
+                const uint32_t f = account->flag[i];
+                const bool live = (account->keep[i] & 1u) && !(f & kFlagFilter) && (int)account->mapq[i] >= h->min_mq &&
+                                  !((f & 1u) && !(f & 2u));
+                if (live) { lo = std::min<uint64_t>(lo, account->seq_off[i]); hi = std::max<uint64_t>(hi, account->seq_off[i + 1]); }
+            }
+            if (hi > lo) { const uint64_t q = ((hi + 15) & ~15ull) - (lo & ~15ull); moved += q + q / 2; }
+        }
+        h->h2d_payload_bytes += moved;
     }
     CU(cudaStreamSynchronize(h->stream));
     if (h->h_status[ST_RANGE_ERR]) {

@@ -261,26 +261,36 @@ def write_bam(path: str, contigs: List[Tuple[str, int]], reads, header_text: Opt
         fh.write(_BGZF_EOF)
 
 
-def write_bam_batch(path: str, contig: Tuple[str, int], batch, level: int = 1):
+def write_bam_batch(path: str, contig: Tuple[str, int], batch, level: int = 1, name_id: Optional[np.ndarray] = None,
+                    mate_pos: Optional[np.ndarray] = None, tlen: Optional[np.ndarray] = None):
     """Write a packed ReadBatch as a BGZF BAM without a per-read Python loop (ingest benchmarks and
-    large fixtures).  Every read gets the 2-byte name "r"; mates are written unpaired-position (-1)."""
+    large fixtures).  Read names are 8 hex digits of `name_id` (default: the read index, i.e. all distinct; the two
+    reads of a pair must share their id); `mate_pos` / `tlen` fill PNEXT (same contig) / TLEN, else the mate
+    fields are written as absent (-1)."""
     n = batch.n_reads
     ncig = np.diff(batch.cigar_off[:n + 1]).astype(np.int64)
     lq = np.diff(batch.seq_off[:n + 1].astype(np.int64))
     lq_true = packing.query_lengths(batch.cigar_off, batch.cigar)[:n].astype(np.int64)
     sbytes = (lq_true + 1) // 2
-    rec_len = 32 + 2 + 4 * ncig + sbytes + lq_true
+    rec_len = 32 + 9 + 4 * ncig + sbytes + lq_true
     offs = np.zeros(n + 1, dtype=np.int64)
     np.cumsum(rec_len + 4, out=offs[1:])
     out = np.zeros(int(offs[-1]), dtype=np.uint8)
     core = np.zeros(n, dtype=np.dtype([("bs", "<i4"), ("ref", "<i4"), ("pos", "<i4"), ("lname", "u1"), ("mapq", "u1"),
                                        ("bin", "<u2"), ("ncig", "<u2"), ("flag", "<u2"), ("lseq", "<i4"),
-                                       ("nref", "<i4"), ("npos", "<i4"), ("tlen", "<i4"), ("name", "S2")]))
-    core["bs"], core["pos"], core["lname"], core["mapq"] = rec_len, batch.pos[:n], 2, batch.mapq[:n]
+                                       ("nref", "<i4"), ("npos", "<i4"), ("tlen", "<i4"), ("name", "u1", (9,))]))
+    core["bs"], core["pos"], core["lname"], core["mapq"] = rec_len, batch.pos[:n], 9, batch.mapq[:n]
     core["bin"], core["ncig"], core["flag"], core["lseq"] = 4680, ncig, batch.flag[:n], lq_true
-    core["nref"], core["npos"], core["name"] = -1, -1, b"r"
-    hdr = core.view(np.uint8).reshape(n, 38)
-    out[(offs[:n, None] + np.arange(38)[None, :]).ravel()] = hdr.ravel()
+    core["nref"] = -1 if mate_pos is None else 0
+    core["npos"] = -1 if mate_pos is None else np.asarray(mate_pos)[:n]
+    core["tlen"] = 0 if tlen is None else np.asarray(tlen)[:n]
+    ids = (np.arange(n, dtype=np.uint32) if name_id is None else np.asarray(name_id)[:n].astype(np.uint32))
+    hexd = np.frombuffer(b"0123456789abcdef", dtype=np.uint8)
+    for k in range(8):
+        core["name"][:, k] = hexd[(ids >> np.uint32(4 * (7 - k))) & np.uint32(15)]
+    core["name"][:, 8] = 0
+    hdr = core.view(np.uint8).reshape(n, 45)
+    out[(offs[:n, None] + np.arange(45)[None, :]).ravel()] = hdr.ravel()
 
     def scatter(dst0, src0, lens, src):
         tot = int(lens.sum())
@@ -292,10 +302,10 @@ def write_bam_batch(path: str, contig: Tuple[str, int], batch, level: int = 1):
         out[np.repeat(dst0, lens) + within] = src[np.repeat(src0, lens) + within]
 
     cig8 = np.ascontiguousarray(batch.cigar).view(np.uint8)
-    scatter(offs[:n] + 38, batch.cigar_off[:n].astype(np.int64) * 4, 4 * ncig, cig8)
+    scatter(offs[:n] + 45, batch.cigar_off[:n].astype(np.int64) * 4, 4 * ncig, cig8)
     so = batch.seq_off[:n].astype(np.int64)
-    scatter(offs[:n] + 38 + 4 * ncig, so // 2, sbytes, batch.seq4)
-    scatter(offs[:n] + 38 + 4 * ncig + sbytes, so, lq_true, batch.qual)
+    scatter(offs[:n] + 45 + 4 * ncig, so // 2, sbytes, batch.seq4)
+    scatter(offs[:n] + 45 + 4 * ncig + sbytes, so, lq_true, batch.qual)
     _ = lq
     name, length = contig
     header_text = f"@HD\tVN:1.6\tSO:coordinate\n@SQ\tSN:{name}\tLN:{length}\n"

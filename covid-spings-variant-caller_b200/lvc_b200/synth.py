@@ -152,6 +152,26 @@ def amplicon_sample(seed: int = 20260101, n_pairs: int = 996_767, ref: Optional[
     return ref, _assemble(*cat, min_mapq=min_mapq, max_depth=max_depth)
 
 
+def amplicon_pairing(batch: ReadBatch, n_pairs: int = 996_767, ref_len: int = SARS2_LEN, read_len: int = 150,
+                     amplicon_len: int = 400, amplicon_step: int = 300):
+    """(name_id, mate_pos, tlen) of the reads of amplicon_sample(n_pairs=...): the k-th forward read of an amplicon
+    and its k-th reverse read are mates (insert = amplicon length, so 2x150 mates of a 400 bp amplicon do not overlap)."""
+    n_amp = (ref_len - amplicon_len) // amplicon_step + 1
+    per = np.full(n_amp, n_pairs // n_amp)
+    per[: n_pairs % n_amp] += 1
+    pair_base = np.concatenate([[0], np.cumsum(per)])[:-1]
+    ids, mpos, tl = [], [], []
+    for a in range(n_amp):
+        k = np.arange(per[a], dtype=np.int64) + pair_base[a]
+        start = a * amplicon_step
+        ids += [k, k]
+        mpos += [np.full(per[a], start + amplicon_len - read_len), np.full(per[a], start)]
+        tl += [np.full(per[a], amplicon_len), np.full(per[a], -amplicon_len)]
+    ids, mpos, tl = np.concatenate(ids), np.concatenate(mpos), np.concatenate(tl)
+    assert len(ids) == batch.n_reads
+    return ids.astype(np.uint32), mpos.astype(np.int32), tl.astype(np.int32)
+
+
 def shotgun_sample(seed: int = 20260400, ref_len: int = 5_000_000, depth: float = 1000.0, read_len: int = 150,
                    ref: Optional[str] = None, min_mapq: int = 20, max_depth: int = 8000, n_snvs: int = 500,
                    block: int = 1 << 18) -> Tuple[str, ReadBatch]:
