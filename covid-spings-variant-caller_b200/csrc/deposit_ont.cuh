@@ -1,0 +1,268 @@
+// Long-read deposit kernel (ONT-like batches: tens of CIGAR ops per read, a wide quality alphabet, most bases below
+// the base-quality threshold).
+//
+// Replaces, for such batches, the per-(column, read) Python loop of live_variant_caller.py:69-70,89-103 and the
+// htslib CIGAR walk behind it.  The warp-per-read kernel (deposit_general.cuh: k_deposit_warp) spends ~1,100 warp
+// instructions per 520-base read: a CIGAR scan with 21 of 32 lanes busy, a quality test over the whole query
+// (soft clips included), a ring of passing bases and a shuffle binary search per passing base to find its op.
+// Here nothing is searched.  A CTA owns `reads_per_cta` consecutive (coordinate-sorted) reads and works in two phases
+// (DESIGN.md section 3.5):
+//   (1) CIGAR phase, one warp per read in turn: lane = op, warp scan of the reference / query offsets (no dependent
+//       global load per op); coverage and deletion entries are deposited; every MATCH op becomes a run record
+//       (payload offset, length, first column) in a per-read slot table in shared memory, and the lane that holds the
+//       op appends the run's UNITS -- the aligned 16-byte pieces of the quality array it touches -- to a CTA-wide
+//       unit list;
+//   (2) unit phase, all threads, one unit per thread per step: one aligned 16-byte load of qualities + one 8-byte
+//       load of bases, byte-parallel threshold test, bytes outside the run masked off, then one RED per PASSING
+//       base (~16 % at minBQ 30) straight into the plane of its quality -- the unit knows its run, so the column is
+//       an addition.  Soft clips and insertions are never looked at.
+// Per read: ~35 units = 1.1 warp steps instead of 5 test steps + 3 resolve-and-deposit steps with a 6-level shuffle
+// search each.  The (column, allele, quality) histogram of a CTA is sparse (a 64-read CTA puts ~30 passing bases on
+// a column, spread over 61 quality planes x 4 alleles), so a shared-memory count tile would merge almost nothing:
+// the reductions go to L2 directly, and the first-seen ordinal is tested in L1 before it is reduced.
+// Counts stay exact for any input: reads with more ops / runs / units than the tables hold take the warp-per-read path
+// inside the same CTA; unknown (group, quality) keys are recorded for the replay exactly as in the other kernels.
+#pragma once
+#include "lvc_common.cuh"
+#include "deposit_general.cuh"
+#include <limits.h>
+
+namespace lvc {
+
+constexpr int kOntThreads = 256;
+constexpr int kOntWarps = kOntThreads / 32;
+constexpr int kOntMaxReads = 32;                // reads per CTA, at most (the launch picks fewer for longer reads)
+constexpr int kOntSlots = 32;                   // one slot per CIGAR op of a read: slot = lane (reads with more ops: warp path)
+constexpr uint32_t kOntMaxUnits = 2560;         // units per CTA (more: the remaining reads take the warp path)
+constexpr uint32_t kOntMaxWindow = 1u << 30;    // payload window of a CTA addressed with 32-bit offsets
+constexpr uint32_t kOntDelUnit = 0x80000000u;   // unit flag: deletion / ref-skip entry instead of 16 bases of a match run
+constexpr uint32_t kOntNoQual = 0xFFFFFFFFu;    // deletion at the very end of the query: its quality is 0
+
+struct OntSmem {
+    uint32_t run_q[kOntMaxReads * kOntSlots];   // match run: first byte, offset in the CTA's payload window; deletion: the NEXT query byte
+    uint32_t run_len[kOntMaxReads * kOntSlots];
+    int32_t run_ref[kOntMaxReads * kOntSlots];  // first reference column of the op
+    uint32_t unit[kOntMaxUnits];                // slot | unit index inside the run << 16, or slot | kOntDelUnit
+    uint32_t* plane[128];                       // group 0 (A,C,G,T) plane of quality q < 128, or nullptr
+    uint32_t hdr_c0[kOntMaxReads], hdr_nc[kOntMaxReads], hdr_so[kOntMaxReads];
+    int32_t hdr_pos[kOntMaxReads];
+    uint32_t deferred[kOntMaxReads];
+    uint32_t n_deferred, n_units, n_valid;
+};
+
+#ifndef LVC_ONT_CTAS
+#define LVC_ONT_CTAS 4
+#endif
+__global__ void __launch_bounds__(kOntThreads, LVC_ONT_CTAS)
+k_deposit_ont(const __grid_constant__ BatchView b, const __grid_constant__ TableView tv,
+              const __grid_constant__ DepositParams dp, uint32_t n, uint32_t reads_per_cta) {
+    __shared__ OntSmem sm;
+    asm volatile("griddepcontrol.launch_dependents;");
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t r0 = blockIdx.x * reads_per_cta;
+    const uint32_t nr_cta = min(reads_per_cta, n - r0);
+    // payload window of the CTA: the reads' qualities are contiguous, [seq_off[r0], seq_off[r0 + nr_cta])
+    const uint64_t win0 = b.seq_off[r0] & ~15ull;                        // 16-byte aligned
+    const uint64_t win1 = b.seq_off[r0 + nr_cta];
+    const bool window_ok = win1 - win0 < kOntMaxWindow;
+    if (tid == 0) { sm.n_deferred = 0; sm.n_units = 0; sm.n_valid = kOntMaxUnits; }
+    if (tid < 128) {
+        const uint16_t pl = tv.lut[tid];
+        sm.plane[tid] = pl == kNoPlane ? nullptr : tv.planes[pl];
+    } else if (tid - 128u < nr_cta) {
+        // read headers, one read per thread: one round of loads for the whole CTA
+        const uint32_t rl = tid - 128u, i = r0 + rl;
+        const bool ok = read_passes_filter(b.flag[i], b.mapq[i], b.keep[i], dp.min_mq);
+        const uint32_t c0 = b.cigar_off[i];
+        sm.hdr_c0[rl] = c0;
+        sm.hdr_nc[rl] = ok ? b.cigar_off[i + 1] - c0 : 0u;                // 0 ops: nothing to do for this read
+        sm.hdr_so[rl] = (uint32_t)(b.seq_off[i] - win0);
+        sm.hdr_pos[rl] = b.pos[i];
+    }
+    __syncthreads();
+    // the tables may still be read by the previous kernel of the stream (programmatic stream serialization)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
+    // ---- (1) CIGAR phase: warp w takes reads w, w + 8, ...; the next read's ops are requested before this one's are used
+    auto load_ops = [&](uint32_t rl) -> uint32_t {
+        return (rl < nr_cta && lane < min(sm.hdr_nc[rl], 32u)) ? b.cigar[sm.hdr_c0[rl] + lane] : 0u;   // padding: a match of length 0
+    };
+    uint32_t cg_next = load_ops(warp);
+    for (uint32_t rl = warp; rl < nr_cta; rl += kOntWarps) {
+        const uint32_t cg = cg_next;
+        cg_next = load_ops(rl + kOntWarps);
+        const uint32_t nc = sm.hdr_nc[rl];
+        if (nc == 0) continue;
+        const uint32_t so = sm.hdr_so[rl];
+        const int64_t pos = sm.hdr_pos[rl];
+        const uint32_t op = cg & 15u, len = cg >> 4;
+        const bool is_m = len != 0 && op_is_match(op);
+        const bool is_d = len != 0 && (op == 2 || op == 3);
+        uint32_t r_in = op_consumes_ref(op) ? len : 0u, q_in = op_consumes_query(op) ? len : 0u;
+        const uint32_t rlen1 = r_in, qlen1 = q_in;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t ur = __shfl_up_sync(0xFFFFFFFFu, r_in, d);
+            const uint32_t uq = __shfl_up_sync(0xFFFFFFFFu, q_in, d);
+            if ((int)lane >= d) { r_in += ur; q_in += uq; }
+        }
+        const uint32_t r_off = r_in - rlen1, q_off = q_in - qlen1;
+        // units of this lane's op: a match run touches some aligned 16-byte groups of the window; a deletion is one unit
+        const uint32_t rq = so + q_off;
+        const uint32_t my_units = is_m ? (((rq & 15u) + len + 15u) >> 4) : (is_d ? 1u : 0u);
+        uint32_t u_in = my_units;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t uu = __shfl_up_sync(0xFFFFFFFFu, u_in, d);
+            if ((int)lane >= d) u_in += uu;
+        }
+        const uint32_t u_tot = __shfl_sync(0xFFFFFFFFu, u_in, 31);
+        // anything the tables cannot hold goes to the warp-per-read path (which does its own coverage / deletions)
+        bool big = nc > 32u || !window_ok || dp.replay || __any_sync(0xFFFFFFFFu, len >= (1u << 19)) || u_tot > kOntMaxUnits;
+        const uint32_t rlen = __shfl_sync(0xFFFFFFFFu, r_in, 31), lq = __shfl_sync(0xFFFFFFFFu, q_in, 31);
+        if (!big) {
+            if (rlen == 0) continue;         // no M/D/N/=/X op: htslib asserts on such records; skipped
+            if (pos < 0 || pos + (int64_t)rlen > tv.G) {
+                if (lane == 0) atomicAdd(&tv.status[ST_RANGE_ERR], 1u);
+                continue;
+            }
+        }
+        uint32_t u_base = 0;
+        if (!big) {
+            if (lane == 0) u_base = atomicAdd(&sm.n_units, u_tot);
+            u_base = __shfl_sync(0xFFFFFFFFu, u_base, 0);
+            if (u_base + u_tot > kOntMaxUnits) {                              // list full: this read and every later one
+                if (lane == 0) atomicMin(&sm.n_valid, u_base);
+                big = true;
+            }
+        }
+        if (big) {
+            if (lane == 0) sm.deferred[atomicAdd(&sm.n_deferred, 1u)] = rl;
+            continue;
+        }
+        if (lane == 0) {
+            atomicAdd(&tv.covdiff[pos], 1);
+            atomicAdd(&tv.covdiff[pos + (int64_t)rlen], -1);
+        }
+        if (my_units) {
+            const uint32_t slot = rl * kOntSlots + lane;
+            // deletion / ref-skip entries are kept iff the NEXT query base passes the quality rule (pysam
+            // pileup_base_qual_skip on qpos = y; quality 0 if qpos >= l_qseq) -- SURVEY B3; tested in the unit phase
+            sm.run_q[slot] = is_m ? rq : (q_off < lq ? rq : kOntNoQual);
+            sm.run_len[slot] = len;
+            sm.run_ref[slot] = (int32_t)(pos + r_off);
+            uint32_t* up = sm.unit + u_base + (u_in - my_units);
+            if (is_m) for (uint32_t k = 0; k < my_units; ++k) up[k] = slot | (k << 16);
+            else up[0] = slot | kOntDelUnit;
+        }
+    }
+    __syncthreads();
+
+    // ---- (2) unit phase: the next unit's loads are in flight while this one is deposited
+    {
+        const uint32_t n_units = min(sm.n_units, sm.n_valid);
+        const uint8_t* qbase = b.qual + win0;
+        const uint8_t* sbase = b.seq4 + (win0 >> 1);
+        uint32_t* first0 = tv.first[0];
+        const uint32_t* seen = tv.seen;
+        const int mbq = dp.min_bq;
+        struct Unit {
+            uint4 q4;            // 16 qualities (deletion unit: x = the one quality that decides)
+            uint2 sraw;          // 16 bases, 4 bit each
+            uint32_t w0, w1, w2; // "allele seen in an earlier batch" nibbles of the columns around the unit
+            uint32_t slot, len;
+            int32_t lo, hi;      // bytes [lo, hi) of the unit belong to the run; lo = INT_MIN marks a deletion unit
+            int32_t col0;        // column of the unit's byte 0 (deletion unit: first column)
+        };
+        auto fetch = [&](uint32_t u, Unit& x) {
+            const uint32_t e = sm.unit[u];
+            x.slot = e & 0xFFFFu;
+            const uint32_t rq = sm.run_q[x.slot];
+            x.len = sm.run_len[x.slot];
+            const int32_t ref0 = sm.run_ref[x.slot];
+            if (e & kOntDelUnit) {
+                x.lo = INT32_MIN; x.hi = 0; x.col0 = ref0;
+                x.q4.x = rq == kOntNoQual ? 0u : (uint32_t)qbase[rq];
+                return;
+            }
+            const uint32_t A = (rq & ~15u) + ((e >> 16) << 4);                  // window offset of the unit's byte 0
+            x.q4 = __ldcs(reinterpret_cast<const uint4*>(qbase + A));
+            x.sraw = __ldcs(reinterpret_cast<const uint2*>(sbase + (A >> 1)));
+            x.lo = (int32_t)rq - (int32_t)A;                                    // > 0 only in the run's first unit
+            x.hi = (int32_t)(rq + x.len) - (int32_t)A;                          // < 16 only in its last unit
+            x.col0 = ref0 - x.lo;
+            x.w0 = x.w1 = x.w2 = 0;
+            if (seen) {
+                const uint32_t* sw = seen + (x.col0 >> 3);                      // two words of padding in front: col0 >= -15
+                x.w0 = sw[0]; x.w1 = sw[1]; x.w2 = sw[2];
+            }
+        };
+        auto deposit = [&](const Unit& x) {
+            if (x.lo == INT32_MIN) {
+                // deletion / ref-skip entry: kept iff the NEXT query base passes the quality rule
+                if ((int)x.q4.x >= mbq) {
+                    uint32_t* d = tv.dels + x.col0;
+                    for (uint32_t j = 0; j < x.len; ++j) atomicAdd(d + j, 1u);
+                }
+                return;
+            }
+            const uint32_t f0 = ge_flags4(x.q4.x, mbq), f1 = ge_flags4(x.q4.y, mbq), f2 = ge_flags4(x.q4.z, mbq),
+                           f3 = ge_flags4(x.q4.w, mbq);
+            // 0x80 per passing byte -> one bit per base
+            uint32_t m16 = ((((f0 >> 7) * 0x00204081u) >> 21) & 15u) | (((((f1 >> 7) * 0x00204081u) >> 21) & 15u) << 4) |
+                           (((((f2 >> 7) * 0x00204081u) >> 21) & 15u) << 8) | (((((f3 >> 7) * 0x00204081u) >> 21) & 15u) << 12);
+            if (x.lo > 0) m16 &= 0xFFFFu << x.lo;
+            if (x.hi < 16) m16 &= 0xFFFFu >> (16 - x.hi);
+            if (!m16) return;
+            // base nibbles in little-endian nibble order (base j of the unit at bits 4j of s1:s0)
+            uint32_t s0, s1;
+            asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(s0) : "r"(x.sraw.x >> 4), "r"(x.sraw.x << 4), "r"(0x0F0F0F0Fu));
+            asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(s1) : "r"(x.sraw.y >> 4), "r"(x.sraw.y << 4), "r"(0x0F0F0F0Fu));
+            // seen nibbles of the unit's 16 columns, column j at bits 4j of n1:n0
+            const uint32_t sh = ((uint32_t)x.col0 & 7u) * 4u;
+            const uint32_t n0 = __funnelshift_r(x.w0, x.w1, sh), n1 = __funnelshift_r(x.w1, x.w2, sh);
+            const uint32_t ord = dp.ord_base + r0 + (x.slot / kOntSlots);
+            while (m16) {
+                const uint32_t j = (uint32_t)__ffs(m16) - 1u;
+                m16 &= m16 - 1u;
+                const uint32_t qw = j < 8u ? (j < 4u ? x.q4.x : x.q4.y) : (j < 12u ? x.q4.z : x.q4.w);
+                const uint32_t q = (qw >> ((j & 3u) * 8u)) & 255u;
+                const uint32_t jb = (j & 7u) * 4u;
+                const uint32_t nib = ((j < 8u ? s0 : s1) >> jb) & 15u;
+                const uint32_t sl = (uint32_t)__ffs(nib) - 1u;                   // A,C,G,T = 1,2,4,8 -> slot 0..3
+                uint32_t* pl = (q < 128u && (nib & (nib - 1u)) == 0u && nib) ? sm.plane[q] : nullptr;
+                const int64_t col = (int64_t)x.col0 + (int64_t)j;
+                if (pl) {
+                    const int64_t cell = col * 4 + sl;
+                    atomicAdd(&pl[cell], 1u);
+                    // First-seen ordinal.  An allele the genotype pass found present after an earlier batch cannot get
+                    // a smaller ordinal from this one: its nibble bit in `seen` is set and nothing is read.  Otherwise
+                    // test before reducing (all quality planes of a group share the cell; a stale L1 line is safe:
+                    // the cell only decreases).
+                    if (!(((j < 8u ? n0 : n1) >> jb) & nib)) {
+                        uint32_t* f = first0 + cell;
+                        if (*f > ord) atomicMin(f, ord);
+                    }
+                } else {
+                    deposit_base(tv, dp, col, nib, q, ord);         // other allele groups, new keys
+                }
+            }
+        };
+        uint32_t u = tid;
+        Unit cur, nxt;
+        bool have = u < n_units;
+        if (have) fetch(u, cur);
+        while (have) {
+            const uint32_t un = u + kOntThreads;
+            const bool have_n = un < n_units;
+            if (have_n) fetch(un, nxt);
+            deposit(cur);
+            cur = nxt; u = un; have = have_n;
+        }
+    }
+    // ---- reads the tables could not hold: the warp-per-read path, one warp each
+    const uint32_t n_def = sm.n_deferred;
+    for (uint32_t d = warp; d < n_def; d += kOntWarps) deposit_read_warp(b, tv, dp, r0 + sm.deferred[d], lane);
+}
+
+}  // namespace lvc

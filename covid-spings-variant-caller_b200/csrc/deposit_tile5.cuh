@@ -127,6 +127,21 @@ k_deposit_tile5(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
     ReadHdr hd;
     uint64_t so0;
     hdr_load1<kT5Reads>(b, cur, tid, hd, so0);
+#ifdef LVC5_HDR_PREFETCH
+    if (warp == 0) {
+        // the chunk that will run in this CTA slot about one wave from now: ask L2 for its header lines
+        const uint64_t i0 = ((uint64_t)cur + tp.n_chunks /* = prefetch distance, see launch */) * kT5Reads;
+        if (i0 + kT5Reads <= b.n_reads) {
+            const uint32_t o = lane * 128u;
+            if (o < kT5Reads * 4u) asm volatile("prefetch.global.L2 [%0];" ::"l"((const char*)(b.pos + i0) + o));
+            if (o < kT5Reads * 4u) asm volatile("prefetch.global.L2 [%0];" ::"l"((const char*)(b.cigar_off + i0) + o));
+            if (o < kT5Reads * 8u) asm volatile("prefetch.global.L2 [%0];" ::"l"((const char*)(b.seq_off + i0) + o));
+            if (o < kT5Reads * 2u) asm volatile("prefetch.global.L2 [%0];" ::"l"((const char*)(b.flag + i0) + o));
+            if (o < kT5Reads * 1u) asm volatile("prefetch.global.L2 [%0];" ::"l"((const char*)(b.mapq + i0) + o));
+            if (o < kT5Reads * 1u) asm volatile("prefetch.global.L2 [%0];" ::"l"((const char*)(b.keep + i0) + o));
+        }
+    }
+#endif
     uint32_t* sc = s_misc + 8;                                       // per-chunk scalars
     uint32_t* wc = s_misc + 32;                                      // runs per warp
     if (tid == 0) {
@@ -664,16 +679,19 @@ k_deposit_tile5(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
                         const int32_t col = col0 + lane;
                         uint32_t fresh = 0;
                         if (cnt4) {
-                            uint32_t ff[4];
+                            // the four first-seen ordinals of the column come with ONE 16-byte load (requested before
+                            // the reductions are issued)
                             const int64_t cell = (int64_t)col * 4;
+                            const uint4 ff = *reinterpret_cast<const uint4*>(first0 + cell);
 #pragma unroll
                             for (int c = 0; c < 4; ++c) {
                                 const uint32_t f = (cnt4 >> (8 * c)) & 255u;
-                                ff[c] = 0;
-                                if (f) { atomicAdd(&plane[cell + c], f); ff[c] = first0[cell + c]; }
+                                if (f) atomicAdd(&plane[cell + c], f);
                             }
-#pragma unroll
-                            for (int c = 0; c < 4; ++c) if (ff[c] > ord_lo) fresh |= 1u << c;
+                            if ((cnt4 & 0x000000FFu) && ff.x > ord_lo) fresh |= 1u;
+                            if ((cnt4 & 0x0000FF00u) && ff.y > ord_lo) fresh |= 2u;
+                            if ((cnt4 & 0x00FF0000u) && ff.z > ord_lo) fresh |= 4u;
+                            if ((cnt4 & 0xFF000000u) && ff.w > ord_lo) fresh |= 8u;
                         }
                         if (__any_sync(0xFFFFFFFFu, fresh != 0)) {
                             // exact first-seen ordinal for new (column, allele) pairs: scan the slab's candidate runs in

@@ -16,6 +16,7 @@
 #include "deposit_tile.cuh"
 #include "deposit_tile4.cuh"
 #include "deposit_tile5.cuh"
+#include "deposit_ont.cuh"
 #include "genotype.cuh"
 #include "overlap.hpp"
 
@@ -39,6 +40,8 @@ struct lvc_handle {
     bool own_stream = false;
     std::string err;
     int impl = 0;
+    int geno_lpp_wide = 1;                   // lanes per (position, slot) of the genotype pass for wide quality alphabets on short contigs (LVC_GENO_LPP)
+    int long_impl = 6;                       // what impl 0 picks for long-read batches (LVC_LONG_IMPL = 3 or 6)
     int tile_impl = 5;                       // what impl 0 (auto) picks for short-read batches (LVC_TILE_IMPL overrides)
     int sm_count = 148;
     uint64_t launches = 0;
@@ -57,6 +60,9 @@ struct lvc_handle {
     uint16_t* d_lut = nullptr;               // [kMaxKeys]
     uint32_t* d_dels = nullptr;
     int32_t* d_covdiff = nullptr;
+    uint32_t* d_seen = nullptr;              // first-seen hint nibbles (TableView::seen), 2 words of padding in front
+    size_t seen_words = 0;
+    bool seen_off = false;                   // someone took a raw pointer to a first-seen table: no hints any more
     uint32_t* d_first[4] = {nullptr, nullptr, nullptr, nullptr};
     uint32_t** d_first_arr = nullptr;        // [4] device copy of d_first
     uint32_t* d_newkeys = nullptr;           // [32]
@@ -145,6 +151,7 @@ static TableView table_view(lvc_handle* h) {
     for (int g = 0; g < 4; ++g) tv.first[g] = h->d_first[g];
     tv.newkeys = h->d_newkeys;
     tv.status = h->d_status;
+    tv.seen = (h->d_seen && !h->seen_off) ? h->d_seen + 2 : nullptr;
     return tv;
 }
 
@@ -194,6 +201,8 @@ int lvc_create(lvc_handle** out, int device, int64_t ref_len, const uint8_t* ref
     h->min_mq = min_mapping_quality;
     for (int k = 0; k < kMaxKeys; ++k) h->lut[k] = kNoPlane;
     if (const char* zc = getenv("LVC_ZERO_COPY")) h->zero_copy_ok = atoi(zc) != 0;
+    if (const char* gl = getenv("LVC_GENO_LPP")) { const int v = atoi(gl); if (v == 1 || v == 2 || v == 4 || v == 8) h->geno_lpp_wide = v; }
+    if (const char* li = getenv("LVC_LONG_IMPL")) { const int v = atoi(li); if (v == 3 || v == 6) h->long_impl = v; }
     if (const char* ti = getenv("LVC_TILE_IMPL")) { const int v = atoi(ti); if (v == 2 || v == 4 || v == 5) h->tile_impl = v; }
     auto body = [&]() -> int {
         CU(cudaSetDevice(device));
@@ -213,6 +222,9 @@ int lvc_create(lvc_handle** out, int device, int64_t ref_len, const uint8_t* ref
         CU(cudaMemsetAsync(h->d_dels, 0, (G + kRowSlack) * sizeof(uint32_t), h->stream));
         CU(cudaMalloc(&h->d_covdiff, (G + kRowSlack) * sizeof(int32_t)));
         CU(cudaMemsetAsync(h->d_covdiff, 0, (G + kRowSlack) * sizeof(int32_t), h->stream));
+        h->seen_words = (G + 7) / 8 + 8;
+        CU(cudaMalloc(&h->d_seen, h->seen_words * sizeof(uint32_t)));
+        CU(cudaMemsetAsync(h->d_seen, 0, h->seen_words * sizeof(uint32_t), h->stream));
         CU(cudaMalloc(&h->d_first_arr, 4 * sizeof(uint32_t*)));
         CU(cudaMemsetAsync(h->d_first_arr, 0, 4 * sizeof(uint32_t*), h->stream));
         CU(cudaMalloc(&h->d_newkeys, 32 * sizeof(uint32_t)));
@@ -257,7 +269,7 @@ void lvc_destroy(lvc_handle* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (auto p : h->planes) cudaFree(p);
     for (int g = 0; g < 4; ++g) cudaFree(h->d_first[g]);
-    cudaFree(h->d_ref); cudaFree(h->d_planes); cudaFree(h->d_lut); cudaFree(h->d_dels); cudaFree(h->d_covdiff);
+    cudaFree(h->d_ref); cudaFree(h->d_planes); cudaFree(h->d_lut); cudaFree(h->d_dels); cudaFree(h->d_covdiff); cudaFree(h->d_seen);
     cudaFree(h->d_first_arr); cudaFree(h->d_newkeys); cudaFree(h->d_replay); cudaFree(h->d_status); cudaFree(h->d_keymap);
     if (h->h_status) cudaFreeHost(h->h_status);
     if (h->h_sample) cudaFreeHost(h->h_sample);
@@ -290,7 +302,7 @@ int lvc_sync(lvc_handle* h) {
 }
 
 int lvc_set_impl(lvc_handle* h, int impl) {
-    if (!h || impl < 0 || impl > 5) return LVC_EINVAL;
+    if (!h || impl < 0 || impl > 6) return LVC_EINVAL;
     h->impl = impl;
     return LVC_OK;
 }
@@ -304,6 +316,7 @@ int lvc_reset(lvc_handle* h) {
         if (h->d_first[g]) CU(cudaMemsetAsync(h->d_first[g], 0xFF, G * 4 * sizeof(uint32_t), h->stream));
     CU(cudaMemsetAsync(h->d_dels, 0, G * sizeof(uint32_t), h->stream));
     CU(cudaMemsetAsync(h->d_covdiff, 0, (G + 1) * sizeof(int32_t), h->stream));
+    CU(cudaMemsetAsync(h->d_seen, 0, h->seen_words * sizeof(uint32_t), h->stream));
     CU(cudaMemsetAsync(h->d_out_depth, 0, G * sizeof(uint32_t), h->stream));
     CU(cudaMemsetAsync(h->d_out_ad, 0, G * 4 * sizeof(uint32_t), h->stream));
     CU(cudaMemsetAsync(h->d_out_lik, 0, G * 4 * sizeof(double), h->stream));
@@ -346,7 +359,7 @@ int lvc_admit_overlaps(uint32_t n, const int32_t* pos, const uint16_t* flag, con
 // ------------------------------------------------------------------------------------------------
 // deposit
 // ------------------------------------------------------------------------------------------------
-static int launch_deposit(lvc_handle* h, const BatchView& bv, int replay, uint64_t n_cigar_ops) {
+static int launch_deposit(lvc_handle* h, const BatchView& bv, int replay, uint64_t n_cigar_ops, uint64_t n_qual) {
     TableView tv = table_view(h);
     DepositParams dp;
     dp.min_bq = h->min_bq;
@@ -359,10 +372,25 @@ static int launch_deposit(lvc_handle* h, const BatchView& bv, int replay, uint64
     // auto: batches of long reads (many CIGAR ops per read: ONT) take the warp-per-read kernel, short-read batches
     // the tiled kernel
     const bool long_reads = n_cigar_ops > 4ull * n;
-    const int impl = h->impl == 0 ? (long_reads ? 3 : h->tile_impl) : h->impl;
+    // long reads: the CTA-cooperative kernel while the reads' ops fit its tables (<= 32 per read), else one warp per read
+    const int long_impl = (n_cigar_ops <= 40ull * n && !replay && h->long_impl == 6) ? 6 : 3;
+    const int impl = h->impl == 0 ? (long_reads ? long_impl : h->tile_impl) : h->impl;
     // the tiled kernels' byte arithmetic assumes a primary quality and a threshold below 128
     const bool tile_ok = h->qprim < 128 && h->min_bq <= 128 && h->lut[h->qprim] != kNoPlane;
-    if (impl == 3 || ((replay || !tile_ok) && impl != 1 && long_reads)) {
+    if (impl == 6 && !replay) {
+        // reads per CTA: as many as keep the CTA's unit list (16 query bases per unit) about three quarters full
+        const uint64_t avg_q = std::max<uint64_t>(n_qual / n, 1);
+        const uint32_t rpc = (uint32_t)std::min<uint64_t>(kOntMaxReads, std::max<uint64_t>(1, (uint64_t)kOntMaxUnits * 12 / avg_q));
+        { KernelTimer t(h, 1);
+          cudaLaunchConfig_t cfg = {};
+          cfg.gridDim = dim3((n + rpc - 1) / rpc); cfg.blockDim = dim3(kOntThreads); cfg.stream = h->stream;
+          cudaLaunchAttribute at[1];
+          at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+          at[0].val.programmaticStreamSerializationAllowed = 1;
+          cfg.attrs = at; cfg.numAttrs = 1;
+          CU(cudaLaunchKernelEx(&cfg, k_deposit_ont, bv, tv, dp, n, rpc)); }
+        h->launches++;
+    } else if (impl == 3 || impl == 6 || ((replay || !tile_ok) && impl != 1 && long_reads)) {
         { KernelTimer t(h, 1);
           cudaLaunchConfig_t cfg = {};
           const unsigned wpb = kWarpKernelThreads / 32;
@@ -395,6 +423,7 @@ static int launch_deposit(lvc_handle* h, const BatchView& bv, int replay, uint64
               at[0].val.programmaticStreamSerializationAllowed = 1;
               cfg.attrs = at; cfg.numAttrs = 1;
               if (impl == 5) {
+                  tp.n_chunks = (uint32_t)h->sm_count * (uint32_t)kTile5CtasPerSM;     // header prefetch distance: one wave
                   if (h->min_bq <= 0) CU(cudaLaunchKernelEx(&cfg, k_deposit_tile5<true>, bv, tv, dp, tp));
                   else CU(cudaLaunchKernelEx(&cfg, k_deposit_tile5<false>, bv, tv, dp, tp));
               } else if (h->min_bq <= 0) CU(cudaLaunchKernelEx(&cfg, k_deposit_tile4<true>, bv, tv, dp, tp));
@@ -409,11 +438,12 @@ static int launch_deposit(lvc_handle* h, const BatchView& bv, int replay, uint64
     return LVC_OK;
 }
 
-static int deposit_with_replay(lvc_handle* h, const BatchView& bv, uint64_t n_cigar_ops, const lvc_batch* account = nullptr) {
+static int deposit_with_replay(lvc_handle* h, const BatchView& bv, uint64_t n_cigar_ops, uint64_t n_qual,
+                               const lvc_batch* account = nullptr) {
     if ((uint64_t)h->ordinal + bv.n_reads >= 0xFFFFFFFFull)
         return fail(h, LVC_ERANGE, "first-seen ordinal space (2^32-1 reads per handle) exhausted");
     CU(cudaMemsetAsync(h->d_status, 0, ST_WORDS * sizeof(uint32_t), h->stream));
-    int rc = launch_deposit(h, bv, 0, n_cigar_ops);
+    int rc = launch_deposit(h, bv, 0, n_cigar_ops, n_qual);
     if (rc) return rc;
     CU(cudaMemcpyAsync(h->h_status, h->d_status, ST_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaMemcpyAsync(h->h_status + ST_WORDS, h->d_newkeys, 32 * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
@@ -453,7 +483,7 @@ static int deposit_with_replay(lvc_handle* h, const BatchView& bv, uint64_t n_ci
         CU(cudaMemcpyAsync(h->d_replay, h->d_newkeys, 32 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, h->stream));
         CU(cudaMemsetAsync(h->d_newkeys, 0, 32 * sizeof(uint32_t), h->stream));
         CU(cudaMemsetAsync(h->d_status, 0, ST_WORDS * sizeof(uint32_t), h->stream));
-        rc = launch_deposit(h, bv, 1, n_cigar_ops);
+        rc = launch_deposit(h, bv, 1, n_cigar_ops, n_qual);
         if (rc) return rc;
         CU(cudaStreamSynchronize(h->stream));
     }
@@ -577,7 +607,7 @@ int lvc_push_batch(lvc_handle* h, const lvc_batch* b) {
     bv.cigar_off = (const uint32_t*)h->b_coff.p; bv.cigar = (const uint32_t*)h->b_cig.p;
     bv.seq_off = (const uint64_t*)h->b_soff.p; bv.seq4 = dev_seq;
     bv.qual = dev_qual;
-    return deposit_with_replay(h, bv, b->n_cigar_ops, zero_copy ? b : nullptr);
+    return deposit_with_replay(h, bv, b->n_cigar_ops, b->n_qual_bytes, zero_copy ? b : nullptr);
 }
 
 int lvc_push_batch_device(lvc_handle* h, const lvc_batch* b) {
@@ -591,7 +621,7 @@ int lvc_push_batch_device(lvc_handle* h, const lvc_batch* b) {
     bv.cigar_off = b->cigar_off; bv.cigar = b->cigar; bv.seq_off = b->seq_off; bv.seq4 = b->seq4; bv.qual = b->qual;
     rc = premap_device(h, b);
     if (rc) return rc;
-    return deposit_with_replay(h, bv, b->n_cigar_ops);
+    return deposit_with_replay(h, bv, b->n_cigar_ops, b->n_qual_bytes);
 }
 
 int lvc_push_batch_device_async(lvc_handle* h, const lvc_batch* b) {
@@ -605,7 +635,7 @@ int lvc_push_batch_device_async(lvc_handle* h, const lvc_batch* b) {
     bv.n_reads = b->n_reads;
     bv.pos = b->pos; bv.flag = b->flag; bv.mapq = b->mapq; bv.keep = b->keep;
     bv.cigar_off = b->cigar_off; bv.cigar = b->cigar; bv.seq_off = b->seq_off; bv.seq4 = b->seq4; bv.qual = b->qual;
-    rc = launch_deposit(h, bv, 0, b->n_cigar_ops);
+    rc = launch_deposit(h, bv, 0, b->n_cigar_ops, b->n_qual_bytes);
     if (rc) return rc;
     h->ordinal += b->n_reads;
     return LVC_OK;
@@ -693,23 +723,26 @@ static int genotype_enqueue(lvc_handle* h, int64_t min_total_depth, int64_t min_
         tables_stale = true;
     }
     if (tables_stale && np > 0) {
-        // per plane: log2(e[q]) and log2(1 - e[q]) as double-doubles, from the caller's doubles in 80-bit arithmetic.
+        // per plane: log2(e[q]) and log2(1 - e[q]) split into exactly summable pieces, from the caller's doubles in 80-bit arithmetic.
         // A zero probability (1 - e at q = 0) becomes a huge finite negative logarithm: its products vanish.
         rc = ensure(h, h->g_pconst, (size_t)np * sizeof(PlaneConst));
         if (rc) return rc;
         CU(cudaStreamSynchronize(h->stream));                 // the staging vector may still feed an earlier copy
         h->pconst_host.resize((size_t)np);
-        auto split = [](double v, double& hi, double& lo) {
-            if (!(v > 0.0)) { hi = -1e290; lo = 0.0; return; }
+        // log2 of a probability in three pieces (genotype.cuh Acc3): multiples of 2^-10 and 2^-36 plus a remainder
+        auto split3 = [](double v, double& c1, double& c2, double& c3) {
+            if (!(v > 0.0)) { c1 = -1e290; c2 = 0.0; c3 = 0.0; return; }
             const long double l = log2l((long double)v);
-            hi = (double)l;
-            lo = (double)(l - (long double)hi);
+            const long double a = roundl(l * 1024.0L) / 1024.0L;
+            const long double r1 = l - a;
+            const long double bq = roundl(r1 * 68719476736.0L) / 68719476736.0L;      // 2^36
+            c1 = (double)a; c2 = (double)bq; c3 = (double)(r1 - bq);
         };
         for (int k = 0; k < np; ++k) {
             const uint32_t q = keys[(size_t)k] & 255u;
             PlaneConst& pc = h->pconst_host[(size_t)k];
-            split(e_lut[q], pc.le_h, pc.le_l);
-            split(om_lut[q], pc.lo_h, pc.lo_l);
+            split3(e_lut[q], pc.le1, pc.le2, pc.le3);
+            split3(om_lut[q], pc.lo1, pc.lo2, pc.lo3);
             pc.e = e_lut[q];
         }
         CU(cudaMemcpyAsync(h->g_pconst.p, h->pconst_host.data(), (size_t)np * sizeof(PlaneConst), cudaMemcpyHostToDevice,
@@ -720,10 +753,15 @@ static int genotype_enqueue(lvc_handle* h, int64_t min_total_depth, int64_t min_
     gp.min_ratio = min_ratio; gp.flags = flags; gp.n_planes = np; gp.cand_cap = h->cand_cap;
     for (int g = 0; g < 5; ++g) gp.grp_begin[g] = grp_begin[g];
     const int threads = kGenoThreads;
-    // wide quality alphabets (ONT: dozens of planes) on a short contig: 8 lanes share the planes of one (position, slot)
-    const int lpp = (grp_begin[1] - grp_begin[0] >= 16 && gp.p1 - gp.p0 <= (1 << 22)) ? 8 : 1;
+    // wide quality alphabets (ONT: dozens of planes) on a short contig: LPP lanes share the planes of one (position,
+    // slot) so that the grid still fills the GPU (a SARS-CoV-2 contig is only 120 k (position, slot) threads)
+    int lpp = 1;
+    if (grp_begin[1] - grp_begin[0] >= 16) {
+        const int64_t span = gp.p1 - gp.p0;
+        lpp = span <= (1 << 17) ? h->geno_lpp_wide : (span <= (1 << 19) ? 2 : 1);
+    }
     const int ppb = threads / (4 * lpp);                      // positions per block
-    const unsigned blocks = (unsigned)((gp.p1 - gp.p0 + ppb - 1) / ppb);
+    const unsigned blocks = (unsigned)((gp.p1 - (gp.p0 & ~7ll) + ppb - 1) / ppb);          // position 0 of a block is a multiple of 8
     if (gp.p1 <= gp.p0) { h->last_cand_count = 0; h->geno_pending = false; return LVC_OK; }
     {
         // Launched with programmatic stream serialization: its blocks may become resident while the deposit kernel
@@ -739,13 +777,20 @@ static int genotype_enqueue(lvc_handle* h, int64_t min_total_depth, int64_t min_
         at[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
         const bool other_groups = grp_begin[4] > grp_begin[1];
-        auto kern = lpp == 8 ? (other_groups ? k_genotype<8, 4> : k_genotype<8, 1>)
-                             : (other_groups ? k_genotype<1, 4> : k_genotype<1, 1>);
+        using GenoKernel = decltype(&k_genotype<1, 1>);
+        static const GenoKernel kerns[4][2] = {{k_genotype<1, 1>, k_genotype<1, 4>}, {k_genotype<2, 1>, k_genotype<2, 4>},
+                                               {k_genotype<4, 1>, k_genotype<4, 4>}, {k_genotype<8, 1>, k_genotype<8, 4>}};
+        const GenoKernel kern = kerns[lpp == 8 ? 3 : (lpp == 4 ? 2 : (lpp == 2 ? 1 : 0))][other_groups ? 1 : 0];
+        cfg.dynamicSmemBytes = (size_t)np * sizeof(PlaneConst);
+        if (cfg.dynamicSmemBytes > 48 * 1024) {        // > 877 planes: never seen, allowed (1024 keys x 56 B = 57 KB)
+            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kMaxKeys * sizeof(PlaneConst))));
+        }
         CU(cudaLaunchKernelEx(&cfg, kern, gp, (const uint32_t* const*)h->g_order_ptrs.p,
                               (const PlaneConst*)h->g_pconst.p, (const uint32_t*)h->d_dels, (const uint8_t*)h->d_ref,
                               (const uint32_t* const*)h->d_first_arr, h->d_out_depth, h->d_out_ad, h->d_out_lik,
                               (lvc_candidate*)h->g_cand.p, h->d_cand_count + h->cand_slot,
-                              h->d_cand_count + (h->cand_slot ^ 1)));
+                              h->d_cand_count + (h->cand_slot ^ 1),
+                              (lpp == 1 && h->d_seen && !h->seen_off) ? h->d_seen + 2 : (uint32_t*)nullptr));
     }
     h->launches++;
     CU(cudaGetLastError());
@@ -923,6 +968,7 @@ int lvc_import_first(lvc_handle* h, int group, const uint32_t* src) {
         CU(cudaMemsetAsync(h->d_first[group], 0xFF, bytes, h->stream));
         CU(cudaMemcpyAsync(h->d_first_arr + group, &h->d_first[group], sizeof(uint32_t*), cudaMemcpyHostToDevice, h->stream));
     }
+    CU(cudaMemsetAsync(h->d_seen, 0, h->seen_words * sizeof(uint32_t), h->stream));      // the hint describes the old table
     CU(cudaMemcpyAsync(h->d_first[group], src, (size_t)h->G * 16, cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return LVC_OK;
@@ -939,7 +985,11 @@ void* lvc_plane_devptr(lvc_handle* h, uint16_t key) {
 }
 void* lvc_dels_devptr(lvc_handle* h) { return h ? h->d_dels : nullptr; }
 void* lvc_covdiff_devptr(lvc_handle* h) { return h ? h->d_covdiff : nullptr; }
-void* lvc_first_devptr(lvc_handle* h, int group) { return (h && group >= 0 && group < 4) ? h->d_first[group] : nullptr; }
+void* lvc_first_devptr(lvc_handle* h, int group) {
+    if (!h || group < 0 || group > 3) return nullptr;
+    h->seen_off = true;       // the caller may write the table (halo exchange clears cells): no first-seen hints any more
+    return h->d_first[group];
+}
 uint64_t lvc_launch_count(lvc_handle* h) { return h ? h->launches : 0; }
 uint64_t lvc_h2d_payload_bytes(lvc_handle* h) { return h ? h->h2d_payload_bytes : 0; }
 

@@ -35,6 +35,9 @@ struct TableView {
     uint32_t* first[4];           // per group [G][4] (nullptr if the group has no plane yet)
     uint32_t* newkeys;            // [32] bitmap of keys seen without a plane
     uint32_t* status;             // [ST_WORDS]
+    const uint32_t* seen;         // hint, may be null: one nibble per column (8 columns per word), bit = "this A/C/G/T
+                                  // allele had a first-seen ordinal after an EARLIER batch" (written by k_genotype);
+                                  // readable from column -16 to G + 31
 };
 
 // One batch of reads, device pointers (mirrors lvc_batch in include/lvc.h).

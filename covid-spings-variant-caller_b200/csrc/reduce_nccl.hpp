@@ -145,6 +145,7 @@ int lvc_reduce_tables(lvc_handle* h, void* nccl_comm, int n_ranks, int rank, int
     NC(A->GroupEnd());
     h->launches++;
     if (mode == LVC_REDUCE_SCATTER) {
+        CU(cudaMemsetAsync(h->d_seen, 0, h->seen_words * sizeof(uint32_t), h->stream));   // first-seen cells outside the slice are cleared below
         // ---- (3) only the rank's own slice is complete: clear the rest (the next batch's deposits start from zero there)
         for (const Tab& t : tabs) {
             const size_t row_b = t.width * 4, lo = (size_t)rank * per, hi = (size_t)(rank + 1) * per;

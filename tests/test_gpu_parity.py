@@ -48,7 +48,7 @@ def _check_likelihoods(lvc, want_lik, what, depth_of):
     return n
 
 
-@pytest.mark.parametrize("impl", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("impl", [1, 2, 3, 4, 5, 6])
 @pytest.mark.parametrize("name", ["vc_config", "bq13", "all_zero", "bq13_dp3"])
 def test_reference_fixture(lib, golden_testfile, name, impl):
     """BASELINE configs[0]: test/testdata/testfile.sam through process_bam (SAM text in, like the server)."""
@@ -65,7 +65,7 @@ def test_reference_fixture(lib, golden_testfile, name, impl):
     lvc.close()
 
 
-@pytest.mark.parametrize("impl", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("impl", [1, 2, 3, 4, 5, 6])
 @pytest.mark.parametrize("scen", ["mixed_small", "ont_like", "deep_underflow", "amplicon_like", "maxdepth"])
 def test_synthetic_scenarios(lib, golden_synth, tmp_path, scen, impl):
     from lvc_b200 import packing
@@ -93,7 +93,7 @@ def test_synthetic_scenarios(lib, golden_synth, tmp_path, scen, impl):
         lvc.close()
 
 
-@pytest.mark.parametrize("impl", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("impl", [1, 2, 3, 4, 5, 6])
 def test_live_batches_accumulate(lib, golden_synth, tmp_path, impl):
     """incremental per-batch update: N process calls == the oracle fed the same batches (max_depth per call)."""
     from lvc_b200 import packing

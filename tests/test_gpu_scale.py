@@ -33,7 +33,7 @@ def device_tables(h):
     return ad, qsum, first, h.copy_dels(), np.cumsum(h.copy_covdiff()[:-1])
 
 
-def check_against_c_oracle(ref, batches, th, impl, max_depth=8000):
+def check_against_c_oracle(ref, batches, th, impl, max_depth=8000, geno_between=False):
     from lvc_b200 import capi, records
     from oracle.c_oracle import COracle
     e_lut, om_lut = records.phred_luts()
@@ -43,6 +43,8 @@ def check_against_c_oracle(ref, batches, th, impl, max_depth=8000):
     for b in batches:
         h.push_batch(b.as_capi())
         co.process(b)
+        if geno_between:                       # live mode: a genotype pass after every batch (it also writes the first-seen hints)
+            h.genotype(th["minDP"], th["minAD"], th["ratio"], e_lut, om_lut)
     ad, qsum, first, dels, cov = device_tables(h)
     assert np.array_equal(ad, co.ad.astype(np.uint64)), "allele depth tables differ"
     assert np.array_equal(qsum, co.qsum), "quality-sum checksum differs"
@@ -110,7 +112,7 @@ def test_live_batches_ont(lib):
     ref = synth.random_reference(6000, 3)
     batches = [synth.ont_batch(100 + k, ref, depth=40.0) for k in range(3)]
     th = dict(minBQ=13, minMQ=20, minDP=10, minAD=3, ratio=0.05)
-    for impl in (0, 1, 2, 3, 4, 5):          # 0 = auto: picks the warp-per-read kernel for these batches
+    for impl in (0, 1, 2, 3, 4, 5, 6):          # 0 = auto: picks the warp-per-read kernel for these batches
         check_against_c_oracle(ref, batches, th, impl)
 
 
@@ -181,6 +183,33 @@ def test_long_reads_with_many_cigar_ops(lib):
     b1 = synth.ont_batch_fast(501, ref, depth=40.0, ref_span=2400, n_runs=60)
     b2 = synth.ont_batch_fast(502, ref, depth=25.0, ref_span=6000, n_runs=200)
     assert b1.n_cigar == 121 * b1.n_reads and b2.n_cigar == 401 * b2.n_reads
-    for impl in (0, 3, 4, 5):
+    for impl in (0, 3, 4, 5, 6):
         check_against_c_oracle(ref, [b1, b2], dict(minBQ=20, minMQ=20, minDP=5, minAD=2, ratio=0.05), impl)
     check_against_c_oracle(ref, [b2, b1], dict(minBQ=0, minMQ=0, minDP=1, minAD=1, ratio=0.0), 0)
+
+
+def test_first_seen_hints_between_batches(lib):
+    """Live mode: the genotype pass after batch k tells the long-read kernel which alleles already have a first-seen
+    ordinal (TableView::seen), and the kernel then skips the first-seen test for them.  Shallow batches, so new
+    (column, allele) pairs keep appearing in later batches; ordinals must equal the oracle's, with and without a
+    genotype pass in between, and after a reset."""
+    from lvc_b200 import capi, records, synth
+    ref = synth.random_reference(5000, 11)
+    batches = [synth.ont_batch_fast(700 + k, ref, depth=3.0) for k in range(6)]
+    th = dict(minBQ=13, minMQ=20, minDP=2, minAD=1, ratio=0.0)
+    for impl in (6, 0, 3):
+        check_against_c_oracle(ref, batches, th, impl, geno_between=True)
+        check_against_c_oracle(ref, batches, th, impl, geno_between=False)
+    # reset clears the hints: the same handle, fed again, must give the first run's first-seen table
+    e_lut, om_lut = records.phred_luts()
+    h = capi.Handle(ref.encode("latin-1"), th["minBQ"], th["minMQ"], device=0)
+    h.set_impl(6)
+    runs = []
+    for _ in range(2):
+        for b in batches:
+            h.push_batch(b.as_capi())
+            h.genotype(th["minDP"], th["minAD"], th["ratio"], e_lut, om_lut)
+        runs.append(h.copy_first(0).copy())
+        h.reset()
+    assert np.array_equal(runs[0], runs[1])
+    h.close()

@@ -53,7 +53,7 @@ def test_vcqueue_process_with_dropin(lib, tmp_path, monkeypatch, relaxed):
     th = dict(minBQ=30, minMQ=20, minDP=10, minAD=5, ratio=0.10)       # config_util/vc.config as shipped
     if relaxed:
         # vc.config is configuration, not code: relaxed thresholds so that the fixture yields records
-        th = dict(minBQ=13, minMQ=0, minDP=3, minAD=2, ratio=0.05)
+        th = dict(minBQ=13, minMQ=0, minDP=1, minAD=1, ratio=0.0)           # golden set "bq13": 4 records
         cfg = (work / "config_util" / "vc.config").read_text()
         for k, v in (("MIN_EVIDENCE_DEPTH", th["minAD"]), ("MIN_EVIDENCE_RATIO", th["ratio"]), ("MIN_TOTAL_DEPTH", th["minDP"]),
                      ("MIN_MAPPING_QUALITY", th["minMQ"]), ("MIN_BASE_QUALITY", th["minBQ"])):

@@ -1,31 +1,56 @@
-"""Per-source-line instruction and stall-sample shares of one kernel from an ncu report (read on the CPU box).
+#!/usr/bin/env python
+"""Aggregate an `ncu -i X.ncu-rep --page source --csv --print-source cuda,sass` dump per CUDA source line:
+warp instructions executed, stall samples, shared-memory wavefronts.  Usage: ncu_lines.py dump.csv [top_n]"""
+import csv
+import sys
+from collections import defaultdict
 
-    python tools/ncu_lines.py report.ncu-rep k_deposit_tile4 [top]
-"""
-import csv, subprocess, sys, io
 
-def load(rep, kern):
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv", "-k",
-                          "regex:" + kern], capture_output=True, text=True).stdout
-    rows = list(csv.reader(io.StringIO(txt)))
-    cur, hdr, out = None, None, []
-    def num(s):
-        try: return int(s)
-        except Exception: return 0
-    for r in rows:
-        if not r: continue
-        if r[0] == 'File Path': cur = r[1].split('/')[-1]; continue
-        if r[0] == 'Line No': hdr = r; continue
-        if hdr and r[0].isdigit():
-            d = dict(zip(hdr, r))
-            out.append((cur, int(r[0]), r[1], num(d.get('Instructions Executed')), num(d.get('# Samples')), d))
-    return out
+def main():
+    path = sys.argv[1]
+    top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
+    cur_file, hdr = None, None
+    agg = defaultdict(lambda: [0, 0, 0, 0, ""])      # (file, line) -> inst, samples, smem wavefronts, excessive, text
+    line_no, line_src = None, ""
+    for row in csv.reader(open(path, newline="")):
+        if not row:
+            continue
+        if row[0] == "File Path":
+            cur_file = row[1].split("/")[-1]
+            continue
+        if row[0] == "Line No":
+            hdr = row
+            ix = {n: i for i, n in enumerate(hdr)}
+            continue
+        if row[0] == "Function Name" or hdr is None:
+            continue
+        if row[0] != "":
+            line_no, line_src = row[0], row[1]
+            continue
+        if row[2] == "...":
+            continue
+
+        def num(name):
+            try:
+                return int(float(row[ix[name]]))
+            except (ValueError, KeyError):
+                return 0
+        a = agg[(cur_file, int(line_no))]
+        a[0] += num("Instructions Executed")
+        a[1] += num("# Samples")
+        a[2] += num("L1 Wavefronts Shared")
+        a[3] += num("L1 Wavefronts Shared Excessive")
+        a[4] = line_src.strip()[:110]
+    tot_i = sum(a[0] for a in agg.values()) or 1
+    tot_s = sum(a[1] for a in agg.values()) or 1
+    print(f"total warp instructions {tot_i}, samples {tot_s}")
+    print("--- by instructions")
+    for (f, ln), a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+        print(f"{100*a[0]/tot_i:5.1f}% inst {100*a[1]/tot_s:5.1f}% smp  wf {a[2]:>9} exc {a[3]:>8}  {f}:{ln}  {a[4]}")
+    print("--- by stall samples")
+    for (f, ln), a in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
+        print(f"{100*a[1]/tot_s:5.1f}% smp {100*a[0]/tot_i:5.1f}% inst  {f}:{ln}  {a[4]}")
+
 
 if __name__ == "__main__":
-    rep, kern = sys.argv[1], sys.argv[2]
-    top = int(sys.argv[3]) if len(sys.argv) > 3 else 60
-    out = load(rep, kern)
-    tot = sum(o[3] for o in out) or 1; tots = sum(o[4] for o in out) or 1
-    print('total warp instructions', tot, 'samples', tots)
-    for o in sorted(out, key=lambda x: -x[3])[:top]:
-        print(f"{o[0][:20]:20s} {o[1]:4d} {100*o[3]/tot:5.1f}% s{100*o[4]/tots:5.1f}%  {o[2][:120]}")
+    main()
