@@ -35,19 +35,28 @@ constexpr int kOntMaxReads = 32;                // reads per CTA, at most (the l
 constexpr int kOntSlots = 32;                   // one slot per CIGAR op of a read: slot = lane (reads with more ops: warp path)
 constexpr uint32_t kOntMaxUnits = 2560;         // units per CTA (more: the remaining reads take the warp path)
 constexpr uint32_t kOntMaxWindow = 1u << 30;    // payload window of a CTA addressed with 32-bit offsets
+constexpr uint32_t kOntMaxSpan = 1u << 15;      // columns of a CTA addressed with 15 bits in an entry (more: warp path)
 constexpr uint32_t kOntDelUnit = 0x80000000u;   // unit flag: deletion / ref-skip entry instead of 16 bases of a match run
 constexpr uint32_t kOntNoQual = 0xFFFFFFFFu;    // deletion at the very end of the query: its quality is 0
+constexpr uint32_t kOntMaxEntries = kOntThreads * 16;    // passing bases of one step (one unit per thread)
 
 struct OntSmem {
     uint32_t run_q[kOntMaxReads * kOntSlots];   // match run: first byte, offset in the CTA's payload window; deletion: the NEXT query byte
     uint32_t run_len[kOntMaxReads * kOntSlots];
     int32_t run_ref[kOntMaxReads * kOntSlots];  // first reference column of the op
     uint32_t unit[kOntMaxUnits];                // slot | unit index inside the run << 16, or slot | kOntDelUnit
+    // per warp: the 32 units of a step as they were loaded, and the step's passing bases as (lane << 4 | byte)
+    uint4 st_q[kOntThreads];                    // 16 qualities
+    uint2 st_s[kOntThreads];                    // 16 bases (4 bit each, as packed in the batch)
+    uint2 st_n[kOntThreads];                    // "seen before" nibbles of the unit's 16 columns
+    uint32_t st_c[kOntThreads];                 // column of byte 0 - col_min + 16 | read << 16
+    uint16_t entry[kOntMaxEntries];
     uint32_t* plane[128];                       // group 0 (A,C,G,T) plane of quality q < 128, or nullptr
-    uint32_t hdr_c0[kOntMaxReads], hdr_nc[kOntMaxReads], hdr_so[kOntMaxReads];
+    uint32_t hdr_c0[kOntMaxReads], hdr_nc[kOntMaxReads], hdr_so[kOntMaxReads], hdr_rlen[kOntMaxReads];
     int32_t hdr_pos[kOntMaxReads];
     uint32_t deferred[kOntMaxReads];
     uint32_t n_deferred, n_units, n_valid;
+    int32_t col_min;
 };
 
 #ifndef LVC_ONT_CTAS
@@ -65,25 +74,44 @@ k_deposit_ont(const __grid_constant__ BatchView b, const __grid_constant__ Table
     const uint64_t win0 = b.seq_off[r0] & ~15ull;                        // 16-byte aligned
     const uint64_t win1 = b.seq_off[r0 + nr_cta];
     const bool window_ok = win1 - win0 < kOntMaxWindow;
-    if (tid == 0) { sm.n_deferred = 0; sm.n_units = 0; sm.n_valid = kOntMaxUnits; }
+#ifdef LVC_ONT_PREFETCH
+    {
+        // ask L2 for the CTA's payload now: the CIGAR phase hides the DRAM latency of the unit phase's first loads
+        const uint64_t q0 = win0, q1 = win1;
+        for (uint64_t a = q0 + (uint64_t)tid * 128u; a < q1; a += (uint64_t)kOntThreads * 128u)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(b.qual + a));
+        for (uint64_t a = (q0 >> 1) + (uint64_t)tid * 128u; a < ((q1 + 1) >> 1); a += (uint64_t)kOntThreads * 128u)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(b.seq4 + a));
+    }
+#endif
+    if (tid == 0) {
+        sm.n_deferred = 0; sm.n_units = 0; sm.n_valid = kOntMaxUnits; sm.col_min = INT32_MAX;
+    }
+    __syncthreads();
     if (tid < 128) {
         const uint16_t pl = tv.lut[tid];
         sm.plane[tid] = pl == kNoPlane ? nullptr : tv.planes[pl];
     } else if (tid - 128u < nr_cta) {
         // read headers, one read per thread: one round of loads for the whole CTA
         const uint32_t rl = tid - 128u, i = r0 + rl;
-        const bool ok = read_passes_filter(b.flag[i], b.mapq[i], b.keep[i], dp.min_mq);
+        const uint32_t keep = b.keep[i];
+        const bool ok = read_passes_filter(b.flag[i], b.mapq[i], keep, dp.min_mq);
         const uint32_t c0 = b.cigar_off[i];
+        const int32_t pos = b.pos[i];
         sm.hdr_c0[rl] = c0;
-        sm.hdr_nc[rl] = ok ? b.cigar_off[i + 1] - c0 : 0u;                // 0 ops: nothing to do for this read
+        // 0 ops: nothing to do for this read.  Reads without the "every base is A/C/G/T" hint (keep bit 1) take the
+        // warp path: the unit phase then never meets another base code (marked by 33+ ops here)
+        sm.hdr_nc[rl] = ok ? ((keep & 2u) ? b.cigar_off[i + 1] - c0 : max(b.cigar_off[i + 1] - c0, 33u)) : 0u;
         sm.hdr_so[rl] = (uint32_t)(b.seq_off[i] - win0);
-        sm.hdr_pos[rl] = b.pos[i];
+        sm.hdr_pos[rl] = pos;
+        sm.hdr_rlen[rl] = 0;                                              // > 0: coverage to deposit after the CIGAR phase
+        if (ok) atomicMin(&sm.col_min, pos);
     }
     __syncthreads();
-    // the tables may still be read by the previous kernel of the stream (programmatic stream serialization)
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const int32_t col_min = sm.col_min;
 
-    // ---- (1) CIGAR phase: warp w takes reads w, w + 8, ...; the next read's ops are requested before this one's are used
+    // ---- (1) CIGAR phase: warp w takes reads w, w + 8, ...; the next read's ops are requested before this one's are
+    //      used.  Nothing is written to the tables here, so the phase overlaps the previous kernel of the stream.
     auto load_ops = [&](uint32_t rl) -> uint32_t {
         return (rl < nr_cta && lane < min(sm.hdr_nc[rl], 32u)) ? b.cigar[sm.hdr_c0[rl] + lane] : 0u;   // padding: a match of length 0
     };
@@ -117,13 +145,14 @@ k_deposit_ont(const __grid_constant__ BatchView b, const __grid_constant__ Table
             if ((int)lane >= d) u_in += uu;
         }
         const uint32_t u_tot = __shfl_sync(0xFFFFFFFFu, u_in, 31);
-        // anything the tables cannot hold goes to the warp-per-read path (which does its own coverage / deletions)
-        bool big = nc > 32u || !window_ok || dp.replay || __any_sync(0xFFFFFFFFu, len >= (1u << 19)) || u_tot > kOntMaxUnits;
         const uint32_t rlen = __shfl_sync(0xFFFFFFFFu, r_in, 31), lq = __shfl_sync(0xFFFFFFFFu, q_in, 31);
+        // anything the tables cannot hold goes to the warp-per-read path (which does its own coverage / deletions)
+        bool big = nc > 32u || !window_ok || dp.replay || __any_sync(0xFFFFFFFFu, len >= (1u << 19)) || u_tot > kOntMaxUnits ||
+                   (uint64_t)(pos - col_min) + rlen >= kOntMaxSpan;
         if (!big) {
             if (rlen == 0) continue;         // no M/D/N/=/X op: htslib asserts on such records; skipped
             if (pos < 0 || pos + (int64_t)rlen > tv.G) {
-                if (lane == 0) atomicAdd(&tv.status[ST_RANGE_ERR], 1u);
+                if (lane == 0) sm.hdr_rlen[rl] = 0xFFFFFFFFu;                 // out of range: reported after the phase
                 continue;
             }
         }
@@ -140,10 +169,7 @@ k_deposit_ont(const __grid_constant__ BatchView b, const __grid_constant__ Table
             if (lane == 0) sm.deferred[atomicAdd(&sm.n_deferred, 1u)] = rl;
             continue;
         }
-        if (lane == 0) {
-            atomicAdd(&tv.covdiff[pos], 1);
-            atomicAdd(&tv.covdiff[pos + (int64_t)rlen], -1);
-        }
+        if (lane == 0) sm.hdr_rlen[rl] = rlen;
         if (my_units) {
             const uint32_t slot = rl * kOntSlots + lane;
             // deletion / ref-skip entries are kept iff the NEXT query base passes the quality rule (pysam
@@ -152,13 +178,35 @@ k_deposit_ont(const __grid_constant__ BatchView b, const __grid_constant__ Table
             sm.run_len[slot] = len;
             sm.run_ref[slot] = (int32_t)(pos + r_off);
             uint32_t* up = sm.unit + u_base + (u_in - my_units);
-            if (is_m) for (uint32_t k = 0; k < my_units; ++k) up[k] = slot | (k << 16);
-            else up[0] = slot | kOntDelUnit;
+            if (is_m) {
+                for (uint32_t k = 0; k < my_units; k += 4) {
+                    up[k] = slot | (k << 16);
+                    if (k + 1 < my_units) up[k + 1] = slot | ((k + 1) << 16);
+                    if (k + 2 < my_units) up[k + 2] = slot | ((k + 2) << 16);
+                    if (k + 3 < my_units) up[k + 3] = slot | ((k + 3) << 16);
+                }
+            } else up[0] = slot | kOntDelUnit;
         }
     }
     __syncthreads();
+    // the tables may still be read by the previous kernel of the stream (programmatic stream serialization)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (tid < nr_cta) {
+        // coverage difference array of the reads this CTA deposits itself
+        const uint32_t rlen = sm.hdr_rlen[tid];
+        if (rlen == 0xFFFFFFFFu) atomicAdd(&tv.status[ST_RANGE_ERR], 1u);
+        else if (rlen) {
+            const int64_t pos = sm.hdr_pos[tid];
+            atomicAdd(&tv.covdiff[pos], 1);
+            atomicAdd(&tv.covdiff[pos + (int64_t)rlen], -1);
+        }
+    }
 
-    // ---- (2) unit phase: the next unit's loads are in flight while this one is deposited
+    // ---- (2) unit phase.  Each warp works on its own: 32 units per step (one per lane): test, COMPACT the step's
+    //      passing bases into the warp's entry list (a short loop over the set bits of a 16-bit mask: two integer
+    //      instructions and a store per base), then deposit the list with every lane busy -- the quality, the base and
+    //      the column of an entry are read back from the warp's staging slots.  No CTA barrier; the next step's loads
+    //      are in flight while this one is processed.
     {
         const uint32_t n_units = min(sm.n_units, sm.n_valid);
         const uint8_t* qbase = b.qual + win0;
@@ -197,69 +245,104 @@ k_deposit_ont(const __grid_constant__ BatchView b, const __grid_constant__ Table
                 x.w0 = sw[0]; x.w1 = sw[1]; x.w2 = sw[2];
             }
         };
-        auto deposit = [&](const Unit& x) {
-            if (x.lo == INT32_MIN) {
-                // deletion / ref-skip entry: kept iff the NEXT query base passes the quality rule
-                if ((int)x.q4.x >= mbq) {
-                    uint32_t* d = tv.dels + x.col0;
-                    for (uint32_t j = 0; j < x.len; ++j) atomicAdd(d + j, 1u);
+        const uint32_t wbase = warp * 32u;                                      // the warp's staging slots
+        uint16_t* ent = sm.entry + warp * 512u;                                 // and its entry list (32 units x 16 bases)
+        const uint8_t* stq = reinterpret_cast<const uint8_t*>(sm.st_q + wbase);
+        const uint8_t* sts = reinterpret_cast<const uint8_t*>(sm.st_s + wbase);
+        const uint32_t* stn = reinterpret_cast<const uint32_t*>(sm.st_n + wbase);
+        Unit cur, nxt;
+        if (tid < n_units) fetch(tid, cur);
+        for (uint32_t ub = 0; ub + wbase < n_units; ub += kOntThreads) {
+            const bool have = ub + tid < n_units;
+            const bool have_n = ub + kOntThreads + tid < n_units;
+            if (have_n) fetch(ub + kOntThreads + tid, nxt);
+            uint32_t m16 = 0;
+            if (have) {
+                if (cur.lo == INT32_MIN) {
+                    // deletion / ref-skip entry: kept iff the NEXT query base passes the quality rule
+                    if ((int)cur.q4.x >= mbq) {
+                        uint32_t* d = tv.dels + cur.col0;
+                        for (uint32_t j = 0; j < cur.len; ++j) atomicAdd(d + j, 1u);
+                    }
+                } else {
+                    const uint32_t f0 = ge_flags4(cur.q4.x, mbq), f1 = ge_flags4(cur.q4.y, mbq), f2 = ge_flags4(cur.q4.z, mbq),
+                                   f3 = ge_flags4(cur.q4.w, mbq);
+                    // 0x80 per passing byte -> one bit per base
+                    m16 = ((((f0 >> 7) * 0x00204081u) >> 21) & 15u) | (((((f1 >> 7) * 0x00204081u) >> 21) & 15u) << 4) |
+                          (((((f2 >> 7) * 0x00204081u) >> 21) & 15u) << 8) | (((((f3 >> 7) * 0x00204081u) >> 21) & 15u) << 12);
+                    if (cur.lo > 0) m16 &= 0xFFFFu << cur.lo;
+                    if (cur.hi < 16) m16 &= 0xFFFFu >> (16 - cur.hi);
+                    if ((cur.q4.x | cur.q4.y | cur.q4.z | cur.q4.w) & 0x80808080u) {
+                        // a quality >= 128 (no real file): this unit's bases one by one, nothing to compact
+                        const uint32_t ord = dp.ord_base + r0 + cur.slot / kOntSlots;
+                        while (m16) {
+                            const uint32_t j = (uint32_t)__ffs(m16) - 1u;
+                            m16 &= m16 - 1u;
+                            const uint32_t qw = j < 8u ? (j < 4u ? cur.q4.x : cur.q4.y) : (j < 12u ? cur.q4.z : cur.q4.w);
+                            const uint32_t sw = j < 8u ? cur.sraw.x : cur.sraw.y;
+                            const uint32_t byte = (sw >> ((j & 6u) * 4u)) & 255u;
+                            deposit_base(tv, dp, (int64_t)cur.col0 + j, (j & 1u) ? (byte & 15u) : (byte >> 4),
+                                         (qw >> ((j & 3u) * 8u)) & 255u, ord);
+                        }
+                    }
                 }
-                return;
             }
-            const uint32_t f0 = ge_flags4(x.q4.x, mbq), f1 = ge_flags4(x.q4.y, mbq), f2 = ge_flags4(x.q4.z, mbq),
-                           f3 = ge_flags4(x.q4.w, mbq);
-            // 0x80 per passing byte -> one bit per base
-            uint32_t m16 = ((((f0 >> 7) * 0x00204081u) >> 21) & 15u) | (((((f1 >> 7) * 0x00204081u) >> 21) & 15u) << 4) |
-                           (((((f2 >> 7) * 0x00204081u) >> 21) & 15u) << 8) | (((((f3 >> 7) * 0x00204081u) >> 21) & 15u) << 12);
-            if (x.lo > 0) m16 &= 0xFFFFu << x.lo;
-            if (x.hi < 16) m16 &= 0xFFFFu >> (16 - x.hi);
-            if (!m16) return;
-            // base nibbles in little-endian nibble order (base j of the unit at bits 4j of s1:s0)
-            uint32_t s0, s1;
-            asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(s0) : "r"(x.sraw.x >> 4), "r"(x.sraw.x << 4), "r"(0x0F0F0F0Fu));
-            asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(s1) : "r"(x.sraw.y >> 4), "r"(x.sraw.y << 4), "r"(0x0F0F0F0Fu));
-            // seen nibbles of the unit's 16 columns, column j at bits 4j of n1:n0
-            const uint32_t sh = ((uint32_t)x.col0 & 7u) * 4u;
-            const uint32_t n0 = __funnelshift_r(x.w0, x.w1, sh), n1 = __funnelshift_r(x.w1, x.w2, sh);
-            const uint32_t ord = dp.ord_base + r0 + (x.slot / kOntSlots);
-            while (m16) {
-                const uint32_t j = (uint32_t)__ffs(m16) - 1u;
-                m16 &= m16 - 1u;
-                const uint32_t qw = j < 8u ? (j < 4u ? x.q4.x : x.q4.y) : (j < 12u ? x.q4.z : x.q4.w);
-                const uint32_t q = (qw >> ((j & 3u) * 8u)) & 255u;
-                const uint32_t jb = (j & 7u) * 4u;
-                const uint32_t nib = ((j < 8u ? s0 : s1) >> jb) & 15u;
-                const uint32_t sl = (uint32_t)__ffs(nib) - 1u;                   // A,C,G,T = 1,2,4,8 -> slot 0..3
-                uint32_t* pl = (q < 128u && (nib & (nib - 1u)) == 0u && nib) ? sm.plane[q] : nullptr;
-                const int64_t col = (int64_t)x.col0 + (int64_t)j;
+            if (m16) {
+                // stage what the deposit needs: qualities, bases, seen nibbles (column j at bits 4j of y:x), column, read
+                sm.st_q[tid] = cur.q4;
+                sm.st_s[tid] = cur.sraw;
+                const uint32_t sh = ((uint32_t)cur.col0 & 7u) * 4u;
+                sm.st_n[tid] = make_uint2(__funnelshift_r(cur.w0, cur.w1, sh), __funnelshift_r(cur.w1, cur.w2, sh));
+                sm.st_c[tid] = (uint32_t)(cur.col0 - col_min + 16) | ((cur.slot / kOntSlots) << 16);
+            }
+            // where this lane's entries go: warp scan of the counts
+            const uint32_t cnt = __popc(m16);
+            uint32_t c_in = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t uu = __shfl_up_sync(0xFFFFFFFFu, c_in, d);
+                if ((int)lane >= d) c_in += uu;
+            }
+            const uint32_t n_ent = __shfl_sync(0xFFFFFFFFu, c_in, 31);
+            {
+                uint16_t* ep = ent + (c_in - cnt);
+                const uint32_t tag = lane << 4;
+                while (m16) {
+                    *ep++ = (uint16_t)(tag | ((uint32_t)__ffs(m16) - 1u));
+                    m16 &= m16 - 1u;
+                }
+            }
+            __syncwarp();
+            for (uint32_t i = lane; i < n_ent; i += 32) {
+                const uint32_t e = ent[i];
+                const uint32_t t = e >> 4, j = e & 15u;
+                const uint32_t q = stq[t * 16u + j];                                      // < 128 (tested with the unit)
+                const uint32_t byte = sts[t * 8u + (j >> 1)];
+                const uint32_t nib = (j & 1u) ? (byte & 15u) : (byte >> 4);               // A,C,G,T = 1,2,4,8 (read hint)
+                const uint32_t sn = (stn[t * 2u + (j >> 3)] >> ((j & 7u) * 4u)) & nib;
+                const uint32_t uc = sm.st_c[wbase + t];
+                const uint32_t col = (uint32_t)col_min + (uc & 0xFFFFu) - 16u + j;
+                uint32_t* pl = sm.plane[q];
                 if (pl) {
-                    const int64_t cell = col * 4 + sl;
-                    atomicAdd(&pl[cell], 1u);
-                    // First-seen ordinal.  An allele the genotype pass found present after an earlier batch cannot get
-                    // a smaller ordinal from this one: its nibble bit in `seen` is set and nothing is read.  Otherwise
-                    // test before reducing (all quality planes of a group share the cell; a stale L1 line is safe:
-                    // the cell only decreases).
-                    if (!(((j < 8u ? n0 : n1) >> jb) & nib)) {
+                    const uint32_t cell = col * 4u + ((nib >> 1) - (nib >> 3));           // slot 0..3
+                    atomicAdd(pl + cell, 1u);
+                    // First-seen ordinal.  An allele the genotype pass found present after an earlier batch cannot get a
+                    // smaller ordinal from this one: its bit in `seen` is set and nothing is read.  Otherwise test before
+                    // reducing (all quality planes of a group share the cell; a stale L1 line is safe: it only decreases).
+                    if (!sn) {
+                        const uint32_t ord = dp.ord_base + r0 + (uc >> 16);
                         uint32_t* f = first0 + cell;
                         if (*f > ord) atomicMin(f, ord);
                     }
                 } else {
-                    deposit_base(tv, dp, col, nib, q, ord);         // other allele groups, new keys
+                    deposit_base(tv, dp, (int64_t)col, nib, q, dp.ord_base + r0 + (uc >> 16));   // a quality without a plane yet
                 }
             }
-        };
-        uint32_t u = tid;
-        Unit cur, nxt;
-        bool have = u < n_units;
-        if (have) fetch(u, cur);
-        while (have) {
-            const uint32_t un = u + kOntThreads;
-            const bool have_n = un < n_units;
-            if (have_n) fetch(un, nxt);
-            deposit(cur);
-            cur = nxt; u = un; have = have_n;
+            __syncwarp();
+            cur = nxt;
         }
     }
+    __syncthreads();
     // ---- reads the tables could not hold: the warp-per-read path, one warp each
     const uint32_t n_def = sm.n_deferred;
     for (uint32_t d = warp; d < n_def; d += kOntWarps) deposit_read_warp(b, tv, dp, r0 + sm.deferred[d], lane);

@@ -373,11 +373,12 @@ static int launch_deposit(lvc_handle* h, const BatchView& bv, int replay, uint64
     // the tiled kernel
     const bool long_reads = n_cigar_ops > 4ull * n;
     // long reads: the CTA-cooperative kernel while the reads' ops fit its tables (<= 32 per read), else one warp per read
-    const int long_impl = (n_cigar_ops <= 40ull * n && !replay && h->long_impl == 6) ? 6 : 3;
+    // (its cell indices are 32-bit: contigs below 2^30 columns)
+    const int long_impl = (n_cigar_ops <= 40ull * n && !replay && h->long_impl == 6 && h->G < (1ll << 30)) ? 6 : 3;
     const int impl = h->impl == 0 ? (long_reads ? long_impl : h->tile_impl) : h->impl;
     // the tiled kernels' byte arithmetic assumes a primary quality and a threshold below 128
     const bool tile_ok = h->qprim < 128 && h->min_bq <= 128 && h->lut[h->qprim] != kNoPlane;
-    if (impl == 6 && !replay) {
+    if (impl == 6 && !replay && h->G < (1ll << 30)) {
         // reads per CTA: as many as keep the CTA's unit list (16 query bases per unit) about three quarters full
         const uint64_t avg_q = std::max<uint64_t>(n_qual / n, 1);
         const uint32_t rpc = (uint32_t)std::min<uint64_t>(kOntMaxReads, std::max<uint64_t>(1, (uint64_t)kOntMaxUnits * 12 / avg_q));
@@ -755,11 +756,11 @@ static int genotype_enqueue(lvc_handle* h, int64_t min_total_depth, int64_t min_
     const int threads = kGenoThreads;
     // wide quality alphabets (ONT: dozens of planes) on a short contig: LPP lanes share the planes of one (position,
     // slot) so that the grid still fills the GPU (a SARS-CoV-2 contig is only 120 k (position, slot) threads)
+    // wide quality alphabets (ONT: dozens of planes) on a short contig: one lane per (position, slot) measured best on
+    // B200 (config 3, 61 planes: 19 us; 2 / 4 / 8 lanes sharing the planes of a slot: 23 / 27 / 36 us; the 4 warps of a
+    // block sharing 8 positions: 23 us) -- the pass is bound by its fixed latency chain, not by loads in flight
     int lpp = 1;
-    if (grp_begin[1] - grp_begin[0] >= 16) {
-        const int64_t span = gp.p1 - gp.p0;
-        lpp = span <= (1 << 17) ? h->geno_lpp_wide : (span <= (1 << 19) ? 2 : 1);
-    }
+    if (grp_begin[1] - grp_begin[0] >= 16 && gp.p1 - gp.p0 <= (1 << 19)) lpp = h->geno_lpp_wide;
     const int ppb = threads / (4 * lpp);                      // positions per block
     const unsigned blocks = (unsigned)((gp.p1 - (gp.p0 & ~7ll) + ppb - 1) / ppb);          // position 0 of a block is a multiple of 8
     if (gp.p1 <= gp.p0) { h->last_cand_count = 0; h->geno_pending = false; return LVC_OK; }
