@@ -74,16 +74,6 @@ k_deposit_ont(const __grid_constant__ BatchView b, const __grid_constant__ Table
     const uint64_t win0 = b.seq_off[r0] & ~15ull;                        // 16-byte aligned
     const uint64_t win1 = b.seq_off[r0 + nr_cta];
     const bool window_ok = win1 - win0 < kOntMaxWindow;
-#ifdef LVC_ONT_PREFETCH
-    {
-        // ask L2 for the CTA's payload now: the CIGAR phase hides the DRAM latency of the unit phase's first loads
-        const uint64_t q0 = win0, q1 = win1;
-        for (uint64_t a = q0 + (uint64_t)tid * 128u; a < q1; a += (uint64_t)kOntThreads * 128u)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(b.qual + a));
-        for (uint64_t a = (q0 >> 1) + (uint64_t)tid * 128u; a < ((q1 + 1) >> 1); a += (uint64_t)kOntThreads * 128u)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(b.seq4 + a));
-    }
-#endif
     if (tid == 0) {
         sm.n_deferred = 0; sm.n_units = 0; sm.n_valid = kOntMaxUnits; sm.col_min = INT32_MAX;
     }

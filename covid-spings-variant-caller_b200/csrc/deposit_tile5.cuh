@@ -127,27 +127,15 @@ k_deposit_tile5(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
     ReadHdr hd;
     uint64_t so0;
     hdr_load1<kT5Reads>(b, cur, tid, hd, so0);
-#ifdef LVC5_HDR_PREFETCH
-    if (warp == 0) {
-        // the chunk that will run in this CTA slot about one wave from now: ask L2 for its header lines
-        const uint64_t i0 = ((uint64_t)cur + tp.n_chunks /* = prefetch distance, see launch */) * kT5Reads;
-        if (i0 + kT5Reads <= b.n_reads) {
-            const uint32_t o = lane * 128u;
-            if (o < kT5Reads * 4u) asm volatile("prefetch.global.L2 [%0];" ::"l"((const char*)(b.pos + i0) + o));
-            if (o < kT5Reads * 4u) asm volatile("prefetch.global.L2 [%0];" ::"l"((const char*)(b.cigar_off + i0) + o));
-            if (o < kT5Reads * 8u) asm volatile("prefetch.global.L2 [%0];" ::"l"((const char*)(b.seq_off + i0) + o));
-            if (o < kT5Reads * 2u) asm volatile("prefetch.global.L2 [%0];" ::"l"((const char*)(b.flag + i0) + o));
-            if (o < kT5Reads * 1u) asm volatile("prefetch.global.L2 [%0];" ::"l"((const char*)(b.mapq + i0) + o));
-            if (o < kT5Reads * 1u) asm volatile("prefetch.global.L2 [%0];" ::"l"((const char*)(b.keep + i0) + o));
-        }
-    }
-#endif
     uint32_t* sc = s_misc + 8;                                       // per-chunk scalars
     uint32_t* wc = s_misc + 32;                                      // runs per warp
     if (tid == 0) {
         s_misc[6] = 0;
         sc[0] = 0xFFFFFFFFu; sc[1] = 0; sc[2] = 0; sc[3] = 0;
     }
+    // a chunk in which the host admission (htslib max_depth) dropped every read ends here, after ONE load per thread:
+    // nothing else of its headers is waited for
+    if (!__syncthreads_or(hd.keep & 1u)) return;
     if (tid < 66) {
         // edge masks of a 32-column unit, one nibble per column: [0][n] keeps the columns >= n, [1][n] the columns < n
         const uint32_t n = tid < 33 ? (uint32_t)tid : (uint32_t)tid - 33u;
@@ -161,7 +149,7 @@ k_deposit_tile5(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
         s_lut[tid] = make_uint4(m[0], m[1], m[2], m[3]);
     }
     hdr_load2(b, hd, dp.min_mq);       // CIGAR ops, only for reads that pass the read-level filter
-    // a chunk in which no read passes the read-level filter (everything dropped by the depth cap) ends here
+    // a chunk in which no read passes the read-level filter ends here
     if (!__syncthreads_or(read_passes_filter(hd.flag, hd.mapq, hd.keep, dp.min_mq))) return;
     // Up to here only the batch was read.  The tables may still be in use by the previous kernel of the stream (this
     // kernel is launched with programmatic stream serialization): wait for it before the first table access.

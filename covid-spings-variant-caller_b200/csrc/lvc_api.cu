@@ -424,7 +424,6 @@ static int launch_deposit(lvc_handle* h, const BatchView& bv, int replay, uint64
               at[0].val.programmaticStreamSerializationAllowed = 1;
               cfg.attrs = at; cfg.numAttrs = 1;
               if (impl == 5) {
-                  tp.n_chunks = (uint32_t)h->sm_count * (uint32_t)kTile5CtasPerSM;     // header prefetch distance: one wave
                   if (h->min_bq <= 0) CU(cudaLaunchKernelEx(&cfg, k_deposit_tile5<true>, bv, tv, dp, tp));
                   else CU(cudaLaunchKernelEx(&cfg, k_deposit_tile5<false>, bv, tv, dp, tp));
               } else if (h->min_bq <= 0) CU(cudaLaunchKernelEx(&cfg, k_deposit_tile4<true>, bv, tv, dp, tp));
