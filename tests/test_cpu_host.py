@@ -172,6 +172,13 @@ def test_vcf_text_layout():
           {"DP": 70, "AD": 5, "GL": 0, "PL": 0, "SCORE": 0}}]
     txt = records.format_vcf(v, [("NC_045512.2", 29903)])
     assert txt == po.format_vcf(v, [("NC_045512.2", 29903)])
+    # the whole file against a LITERAL fixture (tests/golden/expected_two_records.vcf): reviewed by hand against the VCF 4.2
+    # text htslib writes for a default pysam.VariantHeader() + the five add_meta calls of live_variant_caller.py:237-272 +
+    # contigs.add (:274-278) + new_record without contig / filter (:287-295) -- header order, PASS filter line, "." in
+    # ID and FILTER, kputd floats.  [EXT]: not produced by pysam (absent from this image); tests/test_pysam_crosscheck.py
+    # compares with the real writer wherever pysam imports.
+    with open(os.path.join(GOLD, "expected_two_records.vcf")) as fh:
+        assert txt == fh.read()
     lines = txt.strip().split("\n")
     assert lines[0] == "##fileformat=VCFv4.2" and lines[-3].startswith("#CHROM")
     assert lines[-2] == "NC_045512.2\t10\t.\tA\tT\t0.001\t.\tDP=70;AD=5;GL=0;PL=0;SCORE=0"
