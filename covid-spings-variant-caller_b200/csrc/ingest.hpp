@@ -581,6 +581,7 @@ extern "C" {
 
 int lvc_read_alignments_ex(const char* path, const char* contig, int min_mapq, int max_depth, int n_threads,
                            int overlap_model, lvc_reads** out, char* errbuf, int errlen) {
+    NvtxRange nvtx_range("lvc_read_alignments");
     ingest::PhaseTimer timer;                                    // per call: the entry point is re-entrant
     auto seterr = [&](const std::string& s) { if (errbuf && errlen > 0) snprintf(errbuf, (size_t)errlen, "%s", s.c_str()); };
     if (!path || !out || overlap_model < LVC_OVERLAP_OFF || overlap_model > LVC_OVERLAP_HTSLIB_1_13) { seterr("bad arguments"); return LVC_EINVAL; }

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>          // header-only NVTX 3: ranges cost nothing unless a tool injects itself
 
 #include "../../include/lvc.h"
 #include "lvc_common.cuh"
@@ -19,6 +20,15 @@
 #include "deposit_ont.cuh"
 #include "genotype.cuh"
 #include "overlap.hpp"
+
+// NVTX range around the host side of an entry point (ingest / push / genotype / exchange show up
+// as named ranges in Nsight Systems).
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 using namespace lvc;
 
@@ -541,6 +551,7 @@ static int validate_batch(lvc_handle* h, const lvc_batch* b) {
 }
 
 int lvc_push_batch(lvc_handle* h, const lvc_batch* b) {
+    NvtxRange nvtx_range("lvc_push_batch");
     int rc = validate_batch(h, b);
     if (rc) return rc;
     if (b->n_reads == 0) return LVC_OK;
@@ -611,6 +622,7 @@ int lvc_push_batch(lvc_handle* h, const lvc_batch* b) {
 }
 
 int lvc_push_batch_device(lvc_handle* h, const lvc_batch* b) {
+    NvtxRange nvtx_range("lvc_push_batch_device");
     int rc = validate_batch(h, b);
     if (rc) return rc;
     if (b->n_reads == 0) return LVC_OK;
@@ -625,6 +637,7 @@ int lvc_push_batch_device(lvc_handle* h, const lvc_batch* b) {
 }
 
 int lvc_push_batch_device_async(lvc_handle* h, const lvc_batch* b) {
+    NvtxRange nvtx_range("lvc_push_batch_device_async");
     int rc = validate_batch(h, b);
     if (rc) return rc;
     if (b->n_reads == 0) return LVC_OK;
@@ -808,6 +821,7 @@ static int genotype_read_count(lvc_handle* h) {
 
 int lvc_genotype_device(lvc_handle* h, int64_t min_total_depth, int64_t min_allele_depth, double min_ratio,
                         const double* e_lut, const double* om_lut, uint32_t flags) {
+    NvtxRange nvtx_range("lvc_genotype_device");
     if (!h || !e_lut || !om_lut) return LVC_EINVAL;
     CU(cudaSetDevice(h->device));
     for (int attempt = 0; attempt < 2; ++attempt) {
@@ -826,6 +840,7 @@ int lvc_genotype_device(lvc_handle* h, int64_t min_total_depth, int64_t min_alle
 
 int lvc_genotype_device_async(lvc_handle* h, int64_t min_total_depth, int64_t min_allele_depth, double min_ratio,
                               const double* e_lut, const double* om_lut, uint32_t flags) {
+    NvtxRange nvtx_range("lvc_genotype_device_async");
     if (!h || !e_lut || !om_lut) return LVC_EINVAL;
     CU(cudaSetDevice(h->device));
     return genotype_enqueue(h, min_total_depth, min_allele_depth, min_ratio, e_lut, om_lut, flags);
@@ -855,6 +870,7 @@ int lvc_fetch_candidates(lvc_handle* h, lvc_candidate* out, uint32_t cap, uint32
 
 int lvc_genotype(lvc_handle* h, int64_t min_total_depth, int64_t min_allele_depth, double min_ratio, const double* e_lut,
                  const double* om_lut, uint32_t flags, lvc_candidate* out, uint32_t cap, uint32_t* n_out) {
+    NvtxRange nvtx_range("lvc_genotype");
     int rc = lvc_genotype_device(h, min_total_depth, min_allele_depth, min_ratio, e_lut, om_lut, flags);
     if (rc) return rc;
     return lvc_fetch_candidates(h, out, cap, n_out);

@@ -101,6 +101,7 @@ int lvc_position_slice(const lvc_handle* h, int n_ranks, int rank, int64_t* p0, 
 }
 
 int lvc_reduce_tables(lvc_handle* h, void* nccl_comm, int n_ranks, int rank, int mode) {
+    NvtxRange nvtx_range("lvc_reduce_tables");
     if (!h || !nccl_comm || n_ranks < 1 || rank < 0 || rank >= n_ranks || (mode != LVC_REDUCE_ALL && mode != LVC_REDUCE_SCATTER))
         return LVC_EINVAL;
     if (n_ranks > kRowSlack - 2) return fail(h, LVC_EINVAL, "lvc_reduce_tables: at most %d ranks", kRowSlack - 2);

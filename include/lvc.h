@@ -152,10 +152,16 @@ void lvc_reads_free(lvc_reads* r);
 /* ---- deposit: process_bam / process_pileup_column / process_svn (live_variant_caller.py:54-103) ----
  * Walks every kept read's CIGAR on the device and adds its bases/qualities to the persistent
  * per-position tables.  Accumulates across calls (live batches).  `impl`: 0 = auto (the tiled kernel for short-read
- * batches, 3 for batches averaging more than 4 CIGAR ops per read), 1 = general kernel only (one thread per read),
- * 2 = tiled kernel staging the raw payload with TMA, 3 = long-read kernel (wide quality alphabets), 4 = tiled kernel
- * staging 4-bit keys with SWAR counters, 5 = tiled kernel with bit-sliced counters and per-task flush (the tiled
- * kernels use the warp path for the reads they cannot take). */
+ * batches, the long-read kernel 6 for batches averaging more than 4 CIGAR ops per read -- 3 if they average more than
+ * 40), 1 = general kernel only (one thread per read), 2 = tiled kernel staging the raw payload with TMA, 3 = one warp
+ * per read (any record, wide quality alphabets), 4 = tiled kernel staging 4-bit keys with SWAR counters, 5 = tiled
+ * kernel with bit-sliced counters and per-task flush, 6 = long-read kernel (CTA of up to 32 reads: run units, compacted
+ * passing bases, first-seen hints from the genotype pass).  The fast kernels use the warp path for the reads they cannot
+ * take.  Device-resident batches (lvc_push_batch_device*): the kernels read `seq4` and `qual` in aligned 16-byte
+ * groups, so both arrays must be READABLE up to the next 16-byte boundary past their last byte (any cudaMalloc
+ * allocation is; a sub-allocation that ends exactly at the end of a mapped range is not).  NVTX ranges named after the
+ * entry points (lvc_read_alignments, lvc_push_batch*, lvc_genotype*, lvc_reduce_tables) are emitted when a tool is
+ * attached. */
 int lvc_push_batch(lvc_handle* h, const lvc_batch* host_batch);
 int lvc_push_batch_device(lvc_handle* h, const lvc_batch* device_batch);
 int lvc_set_impl(lvc_handle* h, int impl);
