@@ -32,7 +32,9 @@ namespace lvc {
 constexpr int kOntThreads = 256;
 constexpr int kOntWarps = kOntThreads / 32;
 constexpr int kOntMaxReads = 32;                // reads per CTA, at most (the launch picks fewer for longer reads)
-constexpr int kOntSlots = 32;                   // one slot per CIGAR op of a read: slot = lane (reads with more ops: warp path)
+constexpr int kOntSlots = 32;                   // one slot per CIGAR op of a read (reads with more ops: warp path)
+constexpr int kOntSlotStride = 33;              // slots of consecutive reads are 33 words apart: the 32 threads of the CIGAR
+                                                // phase write the same op index of 32 reads without bank conflicts
 constexpr uint32_t kOntMaxUnits = 2560;         // units per CTA (more: the remaining reads take the warp path)
 constexpr uint32_t kOntMaxWindow = 1u << 30;    // payload window of a CTA addressed with 32-bit offsets
 constexpr uint32_t kOntMaxSpan = 1u << 15;      // columns of a CTA addressed with 15 bits in an entry (more: warp path)
@@ -41,9 +43,9 @@ constexpr uint32_t kOntNoQual = 0xFFFFFFFFu;    // deletion at the very end of t
 constexpr uint32_t kOntMaxEntries = kOntThreads * 16;    // passing bases of one step (one unit per thread)
 
 struct OntSmem {
-    uint32_t run_q[kOntMaxReads * kOntSlots];   // match run: first byte, offset in the CTA's payload window; deletion: the NEXT query byte
-    uint32_t run_len[kOntMaxReads * kOntSlots];
-    int32_t run_ref[kOntMaxReads * kOntSlots];  // first reference column of the op
+    uint32_t run_q[kOntMaxReads * kOntSlotStride];   // match run: first byte, offset in the CTA's payload window; deletion: the NEXT query byte
+    uint32_t run_len[kOntMaxReads * kOntSlotStride];
+    int32_t run_ref[kOntMaxReads * kOntSlotStride];  // first reference column of the op
     uint32_t unit[kOntMaxUnits];                // slot | unit index inside the run << 16, or slot | kOntDelUnit
     // per warp: the 32 units of a step as they were loaded, and the step's passing bases as (lane << 4 | byte)
     uint4 st_q[kOntThreads];                    // 16 qualities
@@ -100,82 +102,104 @@ k_deposit_ont(const __grid_constant__ BatchView b, const __grid_constant__ Table
     __syncthreads();
     const int32_t col_min = sm.col_min;
 
-    // ---- (1) CIGAR phase: warp w takes reads w, w + 8, ...; the next read's ops are requested before this one's are
-    //      used.  Nothing is written to the tables here, so the phase overlaps the previous kernel of the stream.
-    auto load_ops = [&](uint32_t rl) -> uint32_t {
-        return (rl < nr_cta && lane < min(sm.hdr_nc[rl], 32u)) ? b.cigar[sm.hdr_c0[rl] + lane] : 0u;   // padding: a match of length 0
-    };
-    uint32_t cg_next = load_ops(warp);
-    for (uint32_t rl = warp; rl < nr_cta; rl += kOntWarps) {
-        const uint32_t cg = cg_next;
-        cg_next = load_ops(rl + kOntWarps);
-        const uint32_t nc = sm.hdr_nc[rl];
-        if (nc == 0) continue;
-        const uint32_t so = sm.hdr_so[rl];
-        const int64_t pos = sm.hdr_pos[rl];
-        const uint32_t op = cg & 15u, len = cg >> 4;
-        const bool is_m = len != 0 && op_is_match(op);
-        const bool is_d = len != 0 && (op == 2 || op == 3);
-        uint32_t r_in = op_consumes_ref(op) ? len : 0u, q_in = op_consumes_query(op) ? len : 0u;
-        const uint32_t rlen1 = r_in, qlen1 = q_in;
+    // ---- (1) CIGAR phase: EIGHT THREADS PER READ, four ops each: the CTA's 32 reads are walked in one pass by all
+    //      256 threads (~45 warp instructions per read where a warp per read with lane = op spent 200, and no warp
+    //      idles as with a thread per read).  Each thread sums the reference / query lengths of its four ops, a 3-level
+    //      scan over the read's 8 lanes gives the offsets, a second one the unit counts; then every thread writes the
+    //      run records and the unit-list entries of its own ops.  Nothing is written to the tables here, so the phase
+    //      overlaps the previous kernel of the stream.
+    {
+        static_assert(kOntThreads == 8 * kOntMaxReads && kOntSlots == 32, "8 threads x 4 ops per read");
+        const uint32_t rl = tid >> 3, part = tid & 7u;
+        const uint32_t nc = rl < nr_cta ? sm.hdr_nc[rl] : 0u;
+        const bool fits = nc != 0 && nc <= (uint32_t)kOntSlots && window_ok && !dp.replay;   // the same for the read's 8 lanes
+        const uint32_t c0 = sm.hdr_c0[rl < nr_cta ? rl : 0], so = sm.hdr_so[rl < nr_cta ? rl : 0];
+        const int64_t pos = sm.hdr_pos[rl < nr_cta ? rl : 0];
+        uint32_t cg[4];
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t ur = __shfl_up_sync(0xFFFFFFFFu, r_in, d);
-            const uint32_t uq = __shfl_up_sync(0xFFFFFFFFu, q_in, d);
-            if ((int)lane >= d) { r_in += ur; q_in += uq; }
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t k = part * 4u + j;
+            cg[j] = (fits && k < nc) ? b.cigar[c0 + k] : 0u;                  // padding: a match of length 0
         }
-        const uint32_t r_off = r_in - rlen1, q_off = q_in - qlen1;
-        // units of this lane's op: a match run touches some aligned 16-byte groups of the window; a deletion is one unit
-        const uint32_t rq = so + q_off;
-        const uint32_t my_units = is_m ? (((rq & 15u) + len + 15u) >> 4) : (is_d ? 1u : 0u);
-        uint32_t u_in = my_units;
+        uint32_t r4 = 0, q4 = 0;
+        bool huge = false;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t uu = __shfl_up_sync(0xFFFFFFFFu, u_in, d);
-            if ((int)lane >= d) u_in += uu;
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t op = cg[j] & 15u, len = cg[j] >> 4;
+            r4 += op_consumes_ref(op) ? len : 0u;
+            q4 += op_consumes_query(op) ? len : 0u;
+            huge |= len >= (1u << 19);
         }
-        const uint32_t u_tot = __shfl_sync(0xFFFFFFFFu, u_in, 31);
-        const uint32_t rlen = __shfl_sync(0xFFFFFFFFu, r_in, 31), lq = __shfl_sync(0xFFFFFFFFu, q_in, 31);
-        // anything the tables cannot hold goes to the warp-per-read path (which does its own coverage / deletions)
-        bool big = nc > 32u || !window_ok || dp.replay || __any_sync(0xFFFFFFFFu, len >= (1u << 19)) || u_tot > kOntMaxUnits ||
-                   (uint64_t)(pos - col_min) + rlen >= kOntMaxSpan;
-        if (!big) {
-            if (rlen == 0) continue;         // no M/D/N/=/X op: htslib asserts on such records; skipped
-            if (pos < 0 || pos + (int64_t)rlen > tv.G) {
-                if (lane == 0) sm.hdr_rlen[rl] = 0xFFFFFFFFu;                 // out of range: reported after the phase
-                continue;
-            }
+        uint32_t r_in = r4, q_in = q4;
+#pragma unroll
+        for (int d = 1; d < 8; d <<= 1) {
+            const uint32_t ur = __shfl_up_sync(0xFFFFFFFFu, r_in, d, 8);
+            const uint32_t uq = __shfl_up_sync(0xFFFFFFFFu, q_in, d, 8);
+            if ((int)part >= d) { r_in += ur; q_in += uq; }
         }
-        uint32_t u_base = 0;
-        if (!big) {
-            if (lane == 0) u_base = atomicAdd(&sm.n_units, u_tot);
-            u_base = __shfl_sync(0xFFFFFFFFu, u_base, 0);
-            if (u_base + u_tot > kOntMaxUnits) {                              // list full: this read and every later one
-                if (lane == 0) atomicMin(&sm.n_valid, u_base);
-                big = true;
-            }
-        }
-        if (big) {
-            if (lane == 0) sm.deferred[atomicAdd(&sm.n_deferred, 1u)] = rl;
-            continue;
-        }
-        if (lane == 0) sm.hdr_rlen[rl] = rlen;
-        if (my_units) {
-            const uint32_t slot = rl * kOntSlots + lane;
-            // deletion / ref-skip entries are kept iff the NEXT query base passes the quality rule (pysam
-            // pileup_base_qual_skip on qpos = y; quality 0 if qpos >= l_qseq) -- SURVEY B3; tested in the unit phase
-            sm.run_q[slot] = is_m ? rq : (q_off < lq ? rq : kOntNoQual);
-            sm.run_len[slot] = len;
-            sm.run_ref[slot] = (int32_t)(pos + r_off);
-            uint32_t* up = sm.unit + u_base + (u_in - my_units);
-            if (is_m) {
-                for (uint32_t k = 0; k < my_units; k += 4) {
-                    up[k] = slot | (k << 16);
-                    if (k + 1 < my_units) up[k + 1] = slot | ((k + 1) << 16);
-                    if (k + 2 < my_units) up[k + 2] = slot | ((k + 2) << 16);
-                    if (k + 3 < my_units) up[k + 3] = slot | ((k + 3) << 16);
+        const uint32_t rlen = __shfl_sync(0xFFFFFFFFu, r_in, 7, 8), lq = __shfl_sync(0xFFFFFFFFu, q_in, 7, 8);
+        // units of this thread's ops: a match run touches some aligned 16-byte groups of the window; a deletion is one
+        uint32_t u4 = 0;
+        {
+            uint32_t qo = q_in - q4;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t op = cg[j] & 15u, len = cg[j] >> 4;
+                if (len != 0) {
+                    if (op_is_match(op)) u4 += (((so + qo) & 15u) + len + 15u) >> 4;
+                    else if (op == 2 || op == 3) u4 += 1u;
                 }
-            } else up[0] = slot | kOntDelUnit;
+                qo += op_consumes_query(op) ? len : 0u;
+            }
+        }
+        uint32_t u_in = u4;
+#pragma unroll
+        for (int d = 1; d < 8; d <<= 1) {
+            const uint32_t uu = __shfl_up_sync(0xFFFFFFFFu, u_in, d, 8);
+            if ((int)part >= d) u_in += uu;
+        }
+        const uint32_t u_tot = __shfl_sync(0xFFFFFFFFu, u_in, 7, 8);
+        const bool any_huge = ((__ballot_sync(0xFFFFFFFFu, huge) >> (lane & 24u)) & 255u) != 0u;
+        // anything the tables cannot hold goes to the warp-per-read path (which does its own coverage / deletions)
+        const bool big = nc != 0 && (!fits || any_huge || u_tot > kOntMaxUnits || (uint64_t)(pos - col_min) + rlen >= kOntMaxSpan);
+        // rlen == 0: no M/D/N/=/X op: htslib asserts on such records; skipped
+        const bool ok = nc != 0 && !big && rlen != 0;
+        const bool range_err = ok && (pos < 0 || pos + (int64_t)rlen > tv.G);
+        uint32_t u_base = 0;
+        if (ok && !range_err && part == 0) u_base = atomicAdd(&sm.n_units, u_tot);
+        u_base = __shfl_sync(0xFFFFFFFFu, u_base, 0, 8);
+        const bool full = ok && !range_err && u_base + u_tot > kOntMaxUnits;   // list full: this read and every later one
+        if (part == 0) {
+            if (full) atomicMin(&sm.n_valid, u_base);
+            if (big || full) sm.deferred[atomicAdd(&sm.n_deferred, 1u)] = rl;
+            else if (range_err) sm.hdr_rlen[rl] = 0xFFFFFFFFu;                 // out of range: reported after the phase
+            else if (ok) sm.hdr_rlen[rl] = rlen;
+        }
+        if (ok && !range_err && !full) {
+            uint32_t* up = sm.unit + u_base + (u_in - u4);
+            uint32_t r_off = r_in - r4, q_off = q_in - q4;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t op = cg[j] & 15u, len = cg[j] >> 4;
+                const uint32_t slot = rl * kOntSlotStride + part * 4u + j;
+                if (len != 0 && op_is_match(op)) {
+                    const uint32_t rq = so + q_off;
+                    sm.run_q[slot] = rq;
+                    sm.run_len[slot] = len;
+                    sm.run_ref[slot] = (int32_t)(pos + r_off);
+                    const uint32_t n_u = ((rq & 15u) + len + 15u) >> 4;
+                    for (uint32_t k = 0; k < n_u; ++k) *up++ = slot | (k << 16);
+                } else if (len != 0 && (op == 2 || op == 3)) {
+                    // deletion / ref-skip entries are kept iff the NEXT query base passes the quality rule (pysam
+                    // pileup_base_qual_skip on qpos = y; quality 0 if qpos >= l_qseq) -- SURVEY B3; tested in the unit phase
+                    sm.run_q[slot] = q_off < lq ? so + q_off : kOntNoQual;
+                    sm.run_len[slot] = len;
+                    sm.run_ref[slot] = (int32_t)(pos + r_off);
+                    *up++ = slot | kOntDelUnit;
+                }
+                r_off += op_consumes_ref(op) ? len : 0u;
+                q_off += op_consumes_query(op) ? len : 0u;
+            }
         }
     }
     __syncthreads();
@@ -264,7 +288,7 @@ k_deposit_ont(const __grid_constant__ BatchView b, const __grid_constant__ Table
                     if (cur.hi < 16) m16 &= 0xFFFFu >> (16 - cur.hi);
                     if ((cur.q4.x | cur.q4.y | cur.q4.z | cur.q4.w) & 0x80808080u) {
                         // a quality >= 128 (no real file): this unit's bases one by one, nothing to compact
-                        const uint32_t ord = dp.ord_base + r0 + cur.slot / kOntSlots;
+                        const uint32_t ord = dp.ord_base + r0 + cur.slot / kOntSlotStride;
                         while (m16) {
                             const uint32_t j = (uint32_t)__ffs(m16) - 1u;
                             m16 &= m16 - 1u;
@@ -283,7 +307,7 @@ k_deposit_ont(const __grid_constant__ BatchView b, const __grid_constant__ Table
                 sm.st_s[tid] = cur.sraw;
                 const uint32_t sh = ((uint32_t)cur.col0 & 7u) * 4u;
                 sm.st_n[tid] = make_uint2(__funnelshift_r(cur.w0, cur.w1, sh), __funnelshift_r(cur.w1, cur.w2, sh));
-                sm.st_c[tid] = (uint32_t)(cur.col0 - col_min + 16) | ((cur.slot / kOntSlots) << 16);
+                sm.st_c[tid] = (uint32_t)(cur.col0 - col_min + 16) | ((cur.slot / kOntSlotStride) << 16);
             }
             // where this lane's entries go: warp scan of the counts
             const uint32_t cnt = __popc(m16);
