@@ -5,23 +5,25 @@
 // htslib CIGAR walk behind it.  The warp-per-read kernel (deposit_general.cuh: k_deposit_warp) spends ~1,100 warp
 // instructions per 520-base read: a CIGAR scan with 21 of 32 lanes busy, a quality test over the whole query
 // (soft clips included), a ring of passing bases and a shuffle binary search per passing base to find its op.
-// Here nothing is searched.  A CTA owns `reads_per_cta` consecutive (coordinate-sorted) reads and works in two phases
-// (DESIGN.md section 3.5):
-//   (1) CIGAR phase, one warp per read in turn: lane = op, warp scan of the reference / query offsets (no dependent
-//       global load per op); coverage and deletion entries are deposited; every MATCH op becomes a run record
-//       (payload offset, length, first column) in a per-read slot table in shared memory, and the lane that holds the
-//       op appends the run's UNITS -- the aligned 16-byte pieces of the quality array it touches -- to a CTA-wide
-//       unit list;
-//   (2) unit phase, all threads, one unit per thread per step: one aligned 16-byte load of qualities + one 8-byte
-//       load of bases, byte-parallel threshold test, bytes outside the run masked off, then one RED per PASSING
-//       base (~16 % at minBQ 30) straight into the plane of its quality -- the unit knows its run, so the column is
-//       an addition.  Soft clips and insertions are never looked at.
-// Per read: ~35 units = 1.1 warp steps instead of 5 test steps + 3 resolve-and-deposit steps with a 6-level shuffle
-// search each.  The (column, allele, quality) histogram of a CTA is sparse (a 64-read CTA puts ~30 passing bases on
-// a column, spread over 61 quality planes x 4 alleles), so a shared-memory count tile would merge almost nothing:
-// the reductions go to L2 directly, and the first-seen ordinal is tested in L1 before it is reduced.
-// Counts stay exact for any input: reads with more ops / runs / units than the tables hold take the warp-per-read path
-// inside the same CTA; unknown (group, quality) keys are recorded for the replay exactly as in the other kernels.
+// Here nothing is searched.  A CTA (128 threads) owns up to 16 consecutive (coordinate-sorted) reads and works in two
+// phases ("k_deposit_ont"):
+//   (1) CIGAR phase, EIGHT THREADS PER READ, four ops each, the whole CTA in one pass: per-thread sums of the
+//       reference / query lengths, a 3-level scan over the read's 8 lanes for the offsets, a second one for the unit
+//       counts.  Every MATCH op becomes a run record (payload offset, length, first column) in a per-read slot table
+//       in shared memory and appends the run's UNITS -- the aligned 16-byte pieces of the quality array it touches --
+//       to a CTA-wide unit list; deletion / ref-skip ops go to a list of their own.  Nothing is written to the tables,
+//       so the phase runs before griddepcontrol.wait and overlaps the previous kernel of the stream;
+//   (2) unit phase, every warp on its own, 32 units per step: one aligned 16-byte load of qualities + one 8-byte load
+//       of bases per lane (the next step's loads in flight), byte-parallel threshold test, bytes outside the run masked
+//       off; the step's PASSING bases (~16 % at minBQ 30) are compacted into the warp's entry list and deposited with
+//       every lane busy: one RED into the plane of the base's quality -- the unit knows its run, so the column is an
+//       addition.  Soft clips and insertions are never looked at.  First-seen ordinals are tested only for alleles
+//       the genotype pass has not yet marked as seen (TableView::seen).
+// The (column, allele, quality) histogram of a CTA is sparse (16 reads put ~6 passing bases on a column, spread over
+// 61 quality planes x 4 alleles), so a shared-memory count tile would merge almost nothing: the reductions go to L2.
+// Counts stay exact for any input: reads with more than 32 ops, other base codes than A/C/G/T, or more units / columns
+// than the tables hold take the warp-per-read path inside the same CTA; unknown (group, quality) keys are recorded for
+// the replay exactly as in the other kernels.
 #pragma once
 #include "lvc_common.cuh"
 #include "deposit_general.cuh"
@@ -29,16 +31,18 @@
 
 namespace lvc {
 
-constexpr int kOntThreads = 256;
+#ifndef LVC_ONT_THREADS
+#define LVC_ONT_THREADS 128
+#endif
+constexpr int kOntThreads = LVC_ONT_THREADS;
 constexpr int kOntWarps = kOntThreads / 32;
-constexpr int kOntMaxReads = 32;                // reads per CTA, at most (the launch picks fewer for longer reads)
+constexpr int kOntMaxReads = kOntThreads / 8;   // reads per CTA, at most (the launch picks fewer for longer reads)
 constexpr int kOntSlots = 32;                   // one slot per CIGAR op of a read (reads with more ops: warp path)
 constexpr int kOntSlotStride = 33;              // slots of consecutive reads are 33 words apart: the 32 threads of the CIGAR
                                                 // phase write the same op index of 32 reads without bank conflicts
-constexpr uint32_t kOntMaxUnits = 2560;         // units per CTA (more: the remaining reads take the warp path)
+constexpr uint32_t kOntMaxUnits = kOntThreads * 10;   // units per CTA (more: the remaining reads take the warp path)
 constexpr uint32_t kOntMaxWindow = 1u << 30;    // payload window of a CTA addressed with 32-bit offsets
 constexpr uint32_t kOntMaxSpan = 1u << 15;      // columns of a CTA addressed with 15 bits in an entry (more: warp path)
-constexpr uint32_t kOntDelUnit = 0x80000000u;   // unit flag: deletion / ref-skip entry instead of 16 bases of a match run
 constexpr uint32_t kOntNoQual = 0xFFFFFFFFu;    // deletion at the very end of the query: its quality is 0
 constexpr uint32_t kOntMaxEntries = kOntThreads * 16;    // passing bases of one step (one unit per thread)
 
@@ -46,7 +50,8 @@ struct OntSmem {
     uint32_t run_q[kOntMaxReads * kOntSlotStride];   // match run: first byte, offset in the CTA's payload window; deletion: the NEXT query byte
     uint32_t run_len[kOntMaxReads * kOntSlotStride];
     int32_t run_ref[kOntMaxReads * kOntSlotStride];  // first reference column of the op
-    uint32_t unit[kOntMaxUnits];                // slot | unit index inside the run << 16, or slot | kOntDelUnit
+    uint32_t unit[kOntMaxUnits];                // match runs: slot | unit index inside the run << 16
+    uint16_t del_list[kOntMaxReads * kOntSlots];  // deletion / ref-skip ops: slot (one entry per op: cannot overflow)
     // per warp: the 32 units of a step as they were loaded, and the step's passing bases as (lane << 4 | byte)
     uint4 st_q[kOntThreads];                    // 16 qualities
     uint2 st_s[kOntThreads];                    // 16 bases (4 bit each, as packed in the batch)
@@ -57,12 +62,12 @@ struct OntSmem {
     uint32_t hdr_c0[kOntMaxReads], hdr_nc[kOntMaxReads], hdr_so[kOntMaxReads], hdr_rlen[kOntMaxReads];
     int32_t hdr_pos[kOntMaxReads];
     uint32_t deferred[kOntMaxReads];
-    uint32_t n_deferred, n_units, n_valid;
+    uint32_t n_deferred, n_units, n_valid, n_dels;
     int32_t col_min;
 };
 
 #ifndef LVC_ONT_CTAS
-#define LVC_ONT_CTAS 4
+#define LVC_ONT_CTAS 8
 #endif
 __global__ void __launch_bounds__(kOntThreads, LVC_ONT_CTAS)
 k_deposit_ont(const __grid_constant__ BatchView b, const __grid_constant__ TableView tv,
@@ -77,15 +82,16 @@ k_deposit_ont(const __grid_constant__ BatchView b, const __grid_constant__ Table
     const uint64_t win1 = b.seq_off[r0 + nr_cta];
     const bool window_ok = win1 - win0 < kOntMaxWindow;
     if (tid == 0) {
-        sm.n_deferred = 0; sm.n_units = 0; sm.n_valid = kOntMaxUnits; sm.col_min = INT32_MAX;
+        sm.n_deferred = 0; sm.n_units = 0; sm.n_valid = kOntMaxUnits; sm.n_dels = 0; sm.col_min = INT32_MAX;
     }
     __syncthreads();
-    if (tid < 128) {
-        const uint16_t pl = tv.lut[tid];
-        sm.plane[tid] = pl == kNoPlane ? nullptr : tv.planes[pl];
-    } else if (tid - 128u < nr_cta) {
+    for (uint32_t q = tid; q < 128u; q += kOntThreads) {
+        const uint16_t pl = tv.lut[q];
+        sm.plane[q] = pl == kNoPlane ? nullptr : tv.planes[pl];
+    }
+    if (tid < nr_cta) {
         // read headers, one read per thread: one round of loads for the whole CTA
-        const uint32_t rl = tid - 128u, i = r0 + rl;
+        const uint32_t rl = tid, i = r0 + rl;
         const uint32_t keep = b.keep[i];
         const bool ok = read_passes_filter(b.flag[i], b.mapq[i], keep, dp.min_mq);
         const uint32_t c0 = b.cigar_off[i];
@@ -147,7 +153,7 @@ k_deposit_ont(const __grid_constant__ BatchView b, const __grid_constant__ Table
                 const uint32_t op = cg[j] & 15u, len = cg[j] >> 4;
                 if (len != 0) {
                     if (op_is_match(op)) u4 += (((so + qo) & 15u) + len + 15u) >> 4;
-                    else if (op == 2 || op == 3) u4 += 1u;
+                    else if (op == 2 || op == 3) u4 += 1u << 16;                 // deletions counted in the high half
                 }
                 qo += op_consumes_query(op) ? len : 0u;
             }
@@ -158,16 +164,18 @@ k_deposit_ont(const __grid_constant__ BatchView b, const __grid_constant__ Table
             const uint32_t uu = __shfl_up_sync(0xFFFFFFFFu, u_in, d, 8);
             if ((int)part >= d) u_in += uu;
         }
-        const uint32_t u_tot = __shfl_sync(0xFFFFFFFFu, u_in, 7, 8);
+        const uint32_t ud_tot = __shfl_sync(0xFFFFFFFFu, u_in, 7, 8);
+        const uint32_t u_tot = ud_tot & 0xFFFFu, d_tot = ud_tot >> 16;
         const bool any_huge = ((__ballot_sync(0xFFFFFFFFu, huge) >> (lane & 24u)) & 255u) != 0u;
         // anything the tables cannot hold goes to the warp-per-read path (which does its own coverage / deletions)
         const bool big = nc != 0 && (!fits || any_huge || u_tot > kOntMaxUnits || (uint64_t)(pos - col_min) + rlen >= kOntMaxSpan);
         // rlen == 0: no M/D/N/=/X op: htslib asserts on such records; skipped
         const bool ok = nc != 0 && !big && rlen != 0;
         const bool range_err = ok && (pos < 0 || pos + (int64_t)rlen > tv.G);
-        uint32_t u_base = 0;
-        if (ok && !range_err && part == 0) u_base = atomicAdd(&sm.n_units, u_tot);
+        uint32_t u_base = 0, d_base = 0;
+        if (ok && !range_err && part == 0) { u_base = atomicAdd(&sm.n_units, u_tot); d_base = atomicAdd(&sm.n_dels, d_tot); }
         u_base = __shfl_sync(0xFFFFFFFFu, u_base, 0, 8);
+        d_base = __shfl_sync(0xFFFFFFFFu, d_base, 0, 8);
         const bool full = ok && !range_err && u_base + u_tot > kOntMaxUnits;   // list full: this read and every later one
         if (part == 0) {
             if (full) atomicMin(&sm.n_valid, u_base);
@@ -175,14 +183,15 @@ k_deposit_ont(const __grid_constant__ BatchView b, const __grid_constant__ Table
             else if (range_err) sm.hdr_rlen[rl] = 0xFFFFFFFFu;                 // out of range: reported after the phase
             else if (ok) sm.hdr_rlen[rl] = rlen;
         }
-        if (ok && !range_err && !full) {
-            uint32_t* up = sm.unit + u_base + (u_in - u4);
+        if (ok && !range_err) {
+            uint32_t* up = sm.unit + u_base + ((u_in - u4) & 0xFFFFu);
+            uint16_t* dl = sm.del_list + d_base + ((u_in - u4) >> 16);
             uint32_t r_off = r_in - r4, q_off = q_in - q4;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const uint32_t op = cg[j] & 15u, len = cg[j] >> 4;
                 const uint32_t slot = rl * kOntSlotStride + part * 4u + j;
-                if (len != 0 && op_is_match(op)) {
+                if (len != 0 && op_is_match(op) && !full) {
                     const uint32_t rq = so + q_off;
                     sm.run_q[slot] = rq;
                     sm.run_len[slot] = len;
@@ -191,11 +200,12 @@ k_deposit_ont(const __grid_constant__ BatchView b, const __grid_constant__ Table
                     for (uint32_t k = 0; k < n_u; ++k) *up++ = slot | (k << 16);
                 } else if (len != 0 && (op == 2 || op == 3)) {
                     // deletion / ref-skip entries are kept iff the NEXT query base passes the quality rule (pysam
-                    // pileup_base_qual_skip on qpos = y; quality 0 if qpos >= l_qseq) -- SURVEY B3; tested in the unit phase
+                    // pileup_base_qual_skip on qpos = y; quality 0 if qpos >= l_qseq) -- SURVEY B3; tested after the unit
+                    // phase.  (A read the unit list could not take leaves its reserved entries empty.)
                     sm.run_q[slot] = q_off < lq ? so + q_off : kOntNoQual;
                     sm.run_len[slot] = len;
                     sm.run_ref[slot] = (int32_t)(pos + r_off);
-                    *up++ = slot | kOntDelUnit;
+                    *dl++ = full ? (uint16_t)0xFFFFu : (uint16_t)slot;
                 }
                 r_off += op_consumes_ref(op) ? len : 0u;
                 q_off += op_consumes_query(op) ? len : 0u;
@@ -229,12 +239,12 @@ k_deposit_ont(const __grid_constant__ BatchView b, const __grid_constant__ Table
         const uint32_t* seen = tv.seen;
         const int mbq = dp.min_bq;
         struct Unit {
-            uint4 q4;            // 16 qualities (deletion unit: x = the one quality that decides)
+            uint4 q4;            // 16 qualities
             uint2 sraw;          // 16 bases, 4 bit each
             uint32_t w0, w1, w2; // "allele seen in an earlier batch" nibbles of the columns around the unit
             uint32_t slot, len;
-            int32_t lo, hi;      // bytes [lo, hi) of the unit belong to the run; lo = INT_MIN marks a deletion unit
-            int32_t col0;        // column of the unit's byte 0 (deletion unit: first column)
+            int32_t lo, hi;      // bytes [lo, hi) of the unit belong to the run
+            int32_t col0;        // column of the unit's byte 0
         };
         auto fetch = [&](uint32_t u, Unit& x) {
             const uint32_t e = sm.unit[u];
@@ -242,11 +252,6 @@ k_deposit_ont(const __grid_constant__ BatchView b, const __grid_constant__ Table
             const uint32_t rq = sm.run_q[x.slot];
             x.len = sm.run_len[x.slot];
             const int32_t ref0 = sm.run_ref[x.slot];
-            if (e & kOntDelUnit) {
-                x.lo = INT32_MIN; x.hi = 0; x.col0 = ref0;
-                x.q4.x = rq == kOntNoQual ? 0u : (uint32_t)qbase[rq];
-                return;
-            }
             const uint32_t A = (rq & ~15u) + ((e >> 16) << 4);                  // window offset of the unit's byte 0
             x.q4 = __ldcs(reinterpret_cast<const uint4*>(qbase + A));
             x.sraw = __ldcs(reinterpret_cast<const uint2*>(sbase + (A >> 1)));
@@ -264,6 +269,14 @@ k_deposit_ont(const __grid_constant__ BatchView b, const __grid_constant__ Table
         const uint8_t* stq = reinterpret_cast<const uint8_t*>(sm.st_q + wbase);
         const uint8_t* sts = reinterpret_cast<const uint8_t*>(sm.st_s + wbase);
         const uint32_t* stn = reinterpret_cast<const uint32_t*>(sm.st_n + wbase);
+        // deletion / ref-skip entries: the one quality that decides each of them is requested now and used after the unit
+        // loop (its latency is hidden; the first 256 entries cover a CTA of 520-base ONT reads)
+        const uint32_t n_dels = sm.n_dels;
+        uint32_t d_slot = 0xFFFFu, d_q = 0;
+        if (tid < n_dels) {
+            d_slot = sm.del_list[tid];
+            if (d_slot != 0xFFFFu) { const uint32_t rq = sm.run_q[d_slot]; d_q = rq == kOntNoQual ? 0u : (uint32_t)qbase[rq]; }
+        }
         Unit cur, nxt;
         if (tid < n_units) fetch(tid, cur);
         for (uint32_t ub = 0; ub + wbase < n_units; ub += kOntThreads) {
@@ -272,13 +285,7 @@ k_deposit_ont(const __grid_constant__ BatchView b, const __grid_constant__ Table
             if (have_n) fetch(ub + kOntThreads + tid, nxt);
             uint32_t m16 = 0;
             if (have) {
-                if (cur.lo == INT32_MIN) {
-                    // deletion / ref-skip entry: kept iff the NEXT query base passes the quality rule
-                    if ((int)cur.q4.x >= mbq) {
-                        uint32_t* d = tv.dels + cur.col0;
-                        for (uint32_t j = 0; j < cur.len; ++j) atomicAdd(d + j, 1u);
-                    }
-                } else {
+                {
                     const uint32_t f0 = ge_flags4(cur.q4.x, mbq), f1 = ge_flags4(cur.q4.y, mbq), f2 = ge_flags4(cur.q4.z, mbq),
                                    f3 = ge_flags4(cur.q4.w, mbq);
                     // 0x80 per passing byte -> one bit per base
@@ -354,6 +361,18 @@ k_deposit_ont(const __grid_constant__ BatchView b, const __grid_constant__ Table
             }
             __syncwarp();
             cur = nxt;
+        }
+        for (uint32_t i = tid; i < n_dels; i += kOntThreads) {
+            if (i != tid) {
+                d_slot = sm.del_list[i];
+                if (d_slot != 0xFFFFu) { const uint32_t rq = sm.run_q[d_slot]; d_q = rq == kOntNoQual ? 0u : (uint32_t)qbase[rq]; }
+            }
+            // kept iff the NEXT query base passes the quality rule
+            if (d_slot != 0xFFFFu && (int)d_q >= mbq) {
+                uint32_t* d = tv.dels + sm.run_ref[d_slot];
+                const uint32_t len = sm.run_len[d_slot];
+                for (uint32_t j = 0; j < len; ++j) atomicAdd(d + j, 1u);
+            }
         }
     }
     __syncthreads();
