@@ -375,8 +375,8 @@ k_deposit_ont(const __grid_constant__ BatchView b, const __grid_constant__ Table
             }
         }
     }
-    __syncthreads();
-    // ---- reads the tables could not hold: the warp-per-read path, one warp each
+    // ---- reads the tables could not hold: the warp-per-read path, one warp each (the list is complete since the barrier
+    //      after the CIGAR phase: no barrier here, a warp that is done with its units leaves)
     const uint32_t n_def = sm.n_deferred;
     for (uint32_t d = warp; d < n_def; d += kOntWarps) deposit_read_warp(b, tv, dp, r0 + sm.deferred[d], lane);
 }
