@@ -60,7 +60,10 @@ struct GenoParams {
 };
 
 constexpr int kGenoThreads = 128;            // 32 positions x 4 allele slots (LPP = 1)
-constexpr int kGenoBatch = 8;                // plane counts requested together
+#ifndef LVC_GENO_BATCH
+#define LVC_GENO_BATCH 8
+#endif
+constexpr int kGenoBatch = LVC_GENO_BATCH;                // plane counts requested together
 
 // Exact accumulation without double-double arithmetic in the loop.  Each logarithm c is split ON THE HOST into
 //   c = c1 + c2 + c3,   c1 a multiple of 2^-10 (|c1| < 2^8),  c2 a multiple of 2^-36 (|c2| <= 2^-11),  |c3| <= 2^-37,
@@ -117,15 +120,17 @@ __global__ void __launch_bounds__(kGenoThreads) k_genotype(GenoParams gp, const 
     // per-plane constants in shared memory: every lane of a warp (LPP = 1) or every LPP-th lane reads the same entry
     extern __shared__ __align__(16) unsigned char geno_smem[];
     PlaneConst* s_pc = reinterpret_cast<PlaneConst*>(geno_smem);
-    // everything below reads tables written by the deposit kernel launched before this one
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;");        // the next deposit kernel may start reading its batch
+    // the per-plane constants were uploaded by a copy that precedes the previous kernel of the stream (or this launch,
+    // which a copy node serialises fully): they can be staged while that kernel drains
     {
         const double* src = reinterpret_cast<const double*>(pconst);
         double* dst = reinterpret_cast<double*>(geno_smem);
         const int nd = gp.n_planes * (int)(sizeof(PlaneConst) / sizeof(double));
         for (int k = tid; k < nd; k += kGenoThreads) dst[k] = src[k];
     }
+    // everything below reads tables written by the deposit kernel launched before this one
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;");        // the next deposit kernel may start reading its batch
     if (blockIdx.x == 0 && tid == 0) *cand_count_next = 0;
     const int slot = tid & 3;
     const int sub = (tid >> 2) & (LPP - 1);
@@ -133,6 +138,10 @@ __global__ void __launch_bounds__(kGenoThreads) k_genotype(GenoParams gp, const 
     const int64_t p = (gp.p0 & ~7ll) + (int64_t)blockIdx.x * (kGenoThreads / (4 * LPP)) + (tid / (4 * LPP));
     const bool live = p >= gp.p0 && p < gp.p1;
     const int64_t pc = p < gp.p0 ? gp.p0 : (p < gp.p1 ? p : gp.p1 - 1);   // clamp: every lane takes part in the shuffles
+    // requested now, used after the plane loop: deletion entries of the position and (for the hint) the first-seen cell
+    const uint32_t dels_p = dels[pc];
+    uint32_t first_p = kUnsetOrdinal;
+    if (LPP == 1 && seen && first[0]) first_p = first[0][pc * 4 + slot];
     __syncthreads();
 
     AlleleStat st[NG];
@@ -186,7 +195,7 @@ __global__ void __launch_bounds__(kGenoThreads) k_genotype(GenoParams gp, const 
     tot = dd_add(tot, dd_shfl_xor(tot, 2));
     uint32_t dsum = own_ad + __shfl_xor_sync(0xFFFFFFFFu, own_ad, 1);
     dsum += __shfl_xor_sync(0xFFFFFFFFu, dsum, 2);
-    const uint64_t depth = (uint64_t)dels[pc] + dsum;
+    const uint64_t depth = (uint64_t)dels_p + dsum;
     // L(a) = prod(1-e | a) * prod over b != a of prod(e | b)      (utils.py:16-24)
     double L[NG];
     double Ssum = 0.0;
@@ -204,8 +213,7 @@ __global__ void __launch_bounds__(kGenoThreads) k_genotype(GenoParams gp, const 
     if (LPP == 1 && seen) {
         // hint for the deposit kernels (TableView::seen): which A/C/G/T alleles of these 8 positions have a first-seen
         // ordinal now -- no later batch can lower it.  Lane = position * 4 + slot is exactly the nibble layout.
-        const uint32_t* f0 = first[0];
-        const bool has = live && f0 && f0[pc * 4 + slot] != kUnsetOrdinal;
+        const bool has = live && first_p != kUnsetOrdinal;
         const uint32_t word = __ballot_sync(0xFFFFFFFFu, has);
         if ((tid & 31) == 0) seen[p >> 3] = word;
     }
