@@ -385,7 +385,8 @@ def leg_config5_sharded(torch, dist, capi, records, stream, dev, world, rank, st
     """ONE sample, contiguous chunks of the coordinate-sorted reads per rank, then the ONE
     exchange of the integer tables over NCCL, then each rank genotypes its slice of positions.  Three exchange modes
     are timed with the same deposit: reduce-scatter and all-reduce through the C-ABI (lvc_reduce_tables, one grouped
-    NCCL call on the device tables) and the halo-only send/recv of lvc_b200.dist."""
+    NCCL call on the device tables), the halo-only send/recv of lvc_b200.dist, and "peer": position ownership over NVLink
+    peer memory (lvc_peer_attach), where the deposit kernel reduces into the owner's tables and the exchange is a barrier."""
     from lvc_b200 import dist as ldist
     e_lut, om_lut = records.phred_luts()
     ref, batch = config5_workload()             # the keep mask was computed over the WHOLE batch
@@ -405,6 +406,16 @@ def leg_config5_sharded(torch, dist, capi, records, stream, dev, world, rank, st
         h = capi.Handle(ref.encode("latin-1"), THRESH["minBQ"], THRESH["minMQ"], device=dev.index, stream=stream.cuda_stream)
         touched = ldist.touched_ranges(batch, shards)
         tabs = None
+        if mode == "peer":
+            # position ownership over NVLink peer memory: fix the plane set, map every rank's tables, then deposit
+            for k in ldist.key_union(ldist.batch_keys(mine, THRESH["minBQ"])):
+                h.ensure_plane(k)
+            h.sync()
+            blobs = [None] * world
+            dist.all_gather_object(blobs, h.peer_export())
+            h.peer_attach(rank, blobs)
+            h.stream_barrier(comm)
+            h.sync()
         t_dep, t_exc, t_gen, t_step, nbytes = [], [], [], [], 0
         for it in range(steps + 2):
             if mode == "all_reduce" and rank != 0 and it > 0:
@@ -415,12 +426,18 @@ def leg_config5_sharded(torch, dist, capi, records, stream, dev, world, rank, st
             dist.barrier()
             torch.cuda.synchronize()
             e[0].record(stream)
-            if it == 0:
+            if mode == "peer":
+                h.stream_barrier(comm)                       # the previous genotype pass is complete on every rank
+                h.push_batch_device_async(db)                # remote columns are reduced into their owner's tables
+            elif it == 0:
                 h.push_batch_device(db)                      # synchronous first push: creates the quality planes
             else:
                 h.push_batch_device_async(db)
             e[1].record(stream)
-            if mode == "halo":
+            if mode == "peer":
+                h.stream_barrier(comm)                       # every rank's reductions have landed
+                nbytes = 0
+            elif mode == "halo":
                 if tabs is None:
                     h.sync()
                     for k in ldist.key_union([int(k) for k in h.plane_keys()]):
@@ -449,13 +466,16 @@ def leg_config5_sharded(torch, dist, capi, records, stream, dev, world, rank, st
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         nb = torch.tensor([nbytes, n_cand], device=dev, dtype=torch.int64)
         dist.all_reduce(nb, op=dist.ReduceOp.SUM)
+        if mode == "peer":
+            h.peer_detach()                                  # nobody frees tables another rank still has mapped
+            dist.barrier()
         h.close()
         dep, exc, gen, step = [float(x) for x in t.tolist()]
         return {"deposit_ms": dep, "exchange_ms": exc, "genotype_slice_ms": gen, "step_ms": step,
                 "exchange_bytes_all_ranks": int(nb[0].item()), "records_all_ranks": int(nb[1].item()),
                 "value": batch.aligned_bases() / (step * 1e-3), "unit": UNIT}
 
-    for mode in ("reduce_scatter", "all_reduce", "halo"):
+    for mode in ("reduce_scatter", "all_reduce", "halo", "peer"):
         try:
             res[mode] = run_mode(mode)
         except Exception as ex:  # a leg must never take the headline line down

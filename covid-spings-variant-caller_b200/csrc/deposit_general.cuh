@@ -14,7 +14,10 @@ __device__ __forceinline__ void mark_unmapped(const TableView& tv, uint32_t key)
     atomicAdd(&tv.status[ST_UNMAPPED], 1u);
 }
 
-// deposit one passing base (nibble `nib`, quality `q`) of read ordinal `ord` at reference column r
+// deposit one passing base (nibble `nib`, quality `q`) of read ordinal `ord` at reference column r.
+// PEER = true: peer tables are attached (lvc_peer_attach) and the cell is looked up at the rank that owns the column;
+// the PEER = false instantiations contain no routing code.
+template <bool PEER = false>
 __device__ __forceinline__ void deposit_base(const TableView& tv, const DepositParams& dp, int64_t r, uint32_t nib,
                                              uint32_t q, uint32_t ord) {
     const uint32_t gs = nibble_gs(nib);
@@ -25,18 +28,18 @@ __device__ __forceinline__ void deposit_base(const TableView& tv, const DepositP
         if (!dp.replay) mark_unmapped(tv, key);
         return;
     }
-    const int64_t cell = r * 4 + (gs & 3u);
-    atomicAdd(&tv.planes[pl][cell], 1u);
+    atomicAdd((PEER ? plane_row(tv, pl, r) : tv.planes[pl] + r * 4) + (gs & 3u), 1u);
     // first-seen ordinal.  Every quality plane of a group shares ONE first-seen cell per (column, allele): at depth d
     // an unconditional RED.MIN would put d same-address atomics per batch on it (they serialise in L2), so test first;
     // after the first reads of a column the test fails and nothing is written.  The test may read a STALE line from L1:
     // the cell only ever decreases, so a stale value is >= the current one and can only cause a redundant atomicMin,
     // never a missed one (and the reads of a CTA share a few hundred columns, so the test mostly hits L1).
-    uint32_t* f = tv.first[gs >> 2] + cell;
+    uint32_t* f = (PEER ? first_row(tv, gs >> 2, r) : tv.first[gs >> 2] + r * 4) + (gs & 3u);
     if (*f > ord) atomicMin(f, ord);
 }
 
 // Walk one read (one thread).
+template <bool PEER = false>
 __device__ __forceinline__ void deposit_read_general(const BatchView& b, const TableView& tv, const DepositParams& dp,
                                                      uint32_t i) {
     const uint32_t flag = b.flag[i];
@@ -57,8 +60,8 @@ __device__ __forceinline__ void deposit_read_general(const BatchView& b, const T
         return;
     }
     if (!dp.replay) {
-        atomicAdd(&tv.covdiff[pos], 1);
-        atomicAdd(&tv.covdiff[pos + rlen], -1);
+        atomicAdd(PEER ? covdiff_cell(tv, pos) : tv.covdiff + pos, 1);
+        atomicAdd(PEER ? covdiff_cell(tv, pos + rlen) : tv.covdiff + pos + rlen, -1);
     }
     const uint64_t qb = b.seq_off[i];
     const uint8_t* qual = b.qual + qb;
@@ -74,14 +77,14 @@ __device__ __forceinline__ void deposit_read_general(const BatchView& b, const T
                 if ((int)q < dp.min_bq) continue;
                 const uint32_t byte = seq[qi >> 1];
                 const uint32_t nib = (qi & 1u) ? (byte & 15u) : (byte >> 4);
-                deposit_base(tv, dp, r, nib, q, ord);
+                deposit_base<PEER>(tv, dp, r, nib, q, ord);
             }
         } else if (op == 2 || op == 3) {
             // deletion / ref-skip entries are kept iff the NEXT query base passes the quality rule
             // (pysam pileup_base_qual_skip on qpos = y; 0 if qpos >= l_qseq) -- SURVEY B3
             const uint32_t q = (qi < lq) ? (uint32_t)qual[qi] : 0u;
             if (!dp.replay && (int)q >= dp.min_bq) {
-                for (uint32_t j = 0; j < len; ++j) atomicAdd(&tv.dels[r + j], 1u);
+                for (uint32_t j = 0; j < len; ++j) atomicAdd(PEER ? dels_cell(tv, r + j) : tv.dels + r + j, 1u);
             }
             r += len;
         } else if (op == 1 || op == 4) {
@@ -116,7 +119,7 @@ __device__ __forceinline__ uint32_t ge_flags4(uint32_t w, int min_bq) {
     return f;
 }
 
-template <bool COMPACT>
+template <bool COMPACT, bool PEER = false>
 __device__ __forceinline__ void deposit_read_warp_impl(const BatchView& b, const TableView& tv, const DepositParams& dp,
                                                        uint32_t i, uint32_t lane, WarpRing* ring = nullptr) {
     if (!read_passes_filter(b.flag[i], b.mapq[i], b.keep[i], dp.min_mq)) return;
@@ -161,8 +164,8 @@ __device__ __forceinline__ void deposit_read_warp_impl(const BatchView& b, const
     }
     const uint32_t lq = (uint32_t)lq64;
     if (!dp.replay && lane == 0) {
-        atomicAdd(&tv.covdiff[pos], 1);
-        atomicAdd(&tv.covdiff[pos + (int64_t)rlen], -1);
+        atomicAdd(PEER ? covdiff_cell(tv, pos) : tv.covdiff + pos, 1);
+        atomicAdd(PEER ? covdiff_cell(tv, pos + (int64_t)rlen) : tv.covdiff + pos + (int64_t)rlen, -1);
     }
     const uint8_t* qual = b.qual + qb;
     const uint8_t* seq = b.seq4 + (qb >> 1);
@@ -197,7 +200,7 @@ __device__ __forceinline__ void deposit_read_warp_impl(const BatchView& b, const
             // passes the quality rule (pysam pileup_base_qual_skip on qpos = y; 0 if qpos >= l_qseq) -- SURVEY B3
             const uint32_t q = (q_off < lq) ? (uint32_t)qual[q_off] : 0u;
             if ((int)q >= dp.min_bq)
-                for (uint32_t j = 0; j < len; ++j) atomicAdd(&tv.dels[pos + r_off + j], 1u);
+                for (uint32_t j = 0; j < len; ++j) atomicAdd(PEER ? dels_cell(tv, pos + r_off + j) : tv.dels + pos + r_off + j, 1u);
         }
         // without the word-parallel path: the ops with something to deposit, one after the other
         uint32_t work = __ballot_sync(0xFFFFFFFFu, !wide && len != 0 && (op_is_match(op) || op == 2 || op == 3));
@@ -214,14 +217,14 @@ __device__ __forceinline__ void deposit_read_warp_impl(const BatchView& b, const
                     if ((int)q < dp.min_bq) continue;
                     const uint32_t byte = seq[(qi + j) >> 1];
                     const uint32_t nib = ((qi + j) & 1u) ? (byte & 15u) : (byte >> 4);
-                    deposit_base(tv, dp, r + j, nib, q, ord);
+                    deposit_base<PEER>(tv, dp, r + j, nib, q, ord);
                 }
             } else if (!dp.replay) {
                 // deletion / ref-skip entries are kept iff the NEXT query base passes the quality rule
                 // (pysam pileup_base_qual_skip on qpos = y; 0 if qpos >= l_qseq) -- SURVEY B3
                 const uint32_t q = (qi < lq) ? (uint32_t)qual[qi] : 0u;
                 if ((int)q >= dp.min_bq)
-                    for (uint32_t j = lane; j < lenk; j += 32) atomicAdd(&tv.dels[r + j], 1u);
+                    for (uint32_t j = lane; j < lenk; j += 32) atomicAdd(PEER ? dels_cell(tv, r + j) : tv.dels + r + j, 1u);
             }
         }
         const uint32_t r_tot = __shfl_sync(0xFFFFFFFFu, r_in, 31), q_tot = __shfl_sync(0xFFFFFFFFu, q_in, 31);
@@ -248,7 +251,7 @@ __device__ __forceinline__ void deposit_read_warp_impl(const BatchView& b, const
                 const uint32_t qo = __shfl_sync(0xFFFFFFFFu, q_off, ko), ro = __shfl_sync(0xFFFFFFFFu, r_off, ko);
                 if (lane < cnt && op_is_match(co & 15u)) {
                     const uint32_t byte = seq[x >> 1];
-                    deposit_base(tv, dp, pos + (int64_t)ro + (x - qo), (x & 1u) ? (byte & 15u) : (byte >> 4), q, ord);
+                    deposit_base<PEER>(tv, dp, pos + (int64_t)ro + (x - qo), (x & 1u) ? (byte & 15u) : (byte >> 4), q, ord);
                 }
                 ring_head = (ring_head + cnt) & (kRingEntries - 1);
                 ring_n -= cnt;
@@ -298,20 +301,27 @@ __device__ __forceinline__ void deposit_read_warp_impl(const BatchView& b, const
 // out of line: what the tiled kernels call for the few reads they hand over
 __device__ __noinline__ void deposit_read_warp(const BatchView& b, const TableView& tv, const DepositParams& dp,
                                                uint32_t i, uint32_t lane) {
-    deposit_read_warp_impl<false>(b, tv, dp, i, lane);
+    deposit_read_warp_impl<false, false>(b, tv, dp, i, lane);
+}
+// the same with peer tables attached (columns of other ranks are reduced into their tables)
+__device__ __noinline__ void deposit_read_warp_peer(const BatchView& b, const TableView& tv, const DepositParams& dp,
+                                                    uint32_t i, uint32_t lane) {
+    deposit_read_warp_impl<false, true>(b, tv, dp, i, lane);
 }
 
 // one thread per read of the batch
+template <bool PEER>
 __global__ void __launch_bounds__(128) k_deposit_general(const __grid_constant__ BatchView b,
                                                          const __grid_constant__ TableView tv,
                                                          const __grid_constant__ DepositParams dp, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) deposit_read_general(b, tv, dp, i);
+    if (i < n) deposit_read_general<PEER>(b, tv, dp, i);
 }
 
 // one WARP per read of the batch: long reads with many CIGAR ops and a wide quality alphabet (ONT), where neither a
 // primary quality nor a short run table exists.  Every read of the batch is in flight at once.
 constexpr int kWarpKernelThreads = 256;
+template <bool PEER>
 __global__ void __launch_bounds__(kWarpKernelThreads) k_deposit_warp(const __grid_constant__ BatchView b,
                                                                      const __grid_constant__ TableView tv,
                                                                      const __grid_constant__ DepositParams dp, uint32_t n) {
@@ -319,7 +329,7 @@ __global__ void __launch_bounds__(kWarpKernelThreads) k_deposit_warp(const __gri
     asm volatile("griddepcontrol.wait;" ::: "memory");     // the tables may still be read by the previous kernel
     __shared__ WarpRing rings[kWarpKernelThreads / 32];
     const uint32_t i = blockIdx.x * (kWarpKernelThreads / 32) + (threadIdx.x >> 5);
-    if (i < n) deposit_read_warp_impl<true>(b, tv, dp, i, threadIdx.x & 31u, &rings[threadIdx.x >> 5]);
+    if (i < n) deposit_read_warp_impl<true, PEER>(b, tv, dp, i, threadIdx.x & 31u, &rings[threadIdx.x >> 5]);
 }
 
 }  // namespace lvc

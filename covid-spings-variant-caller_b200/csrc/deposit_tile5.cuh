@@ -91,7 +91,8 @@ __device__ __forceinline__ void bs_add(const uint32_t (&a)[N], const uint32_t (&
 
 // kernel parameters stay in the constant bank even where their address is taken (the warp-per-read helper takes
 // the views by reference): without this every thread copies them to local memory first
-template <bool GE_ALL>
+// PEER: lvc_peer_attach is active -- columns another rank owns are reduced into that rank's tables (lvc_common.cuh)
+template <bool GE_ALL, bool PEER>
 __global__ void __launch_bounds__(kT5Threads, kTile5CtasPerSM)
 k_deposit_tile5(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp, LVC_GC TileParams tp) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -176,7 +177,7 @@ k_deposit_tile5(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
         }
         __syncthreads();
         const uint32_t n_def = s_misc[6];
-        for (uint32_t d = warp; d < n_def; d += kT5Warps) deposit_read_warp(b, tv, dp, cur * kT5Reads + s_dlist[d], lane);
+        for (uint32_t d = warp; d < n_def; d += kT5Warps) (PEER ? deposit_read_warp_peer : deposit_read_warp)(b, tv, dp, cur * kT5Reads + s_dlist[d], lane);
         return;
     }
     // staging base: 16-byte aligned start of the first such read
@@ -372,14 +373,14 @@ k_deposit_tile5(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
             // coverage difference array: one atomic per distinct start / end among the warp's reads
             const int32_t ks = active ? hd.pos : (int32_t)(0x80000000u + lane);
             const uint32_t ms = __match_any_sync(0xFFFFFFFFu, ks);
-            if (active && lane == __ffs(ms) - 1) atomicAdd(&tv.covdiff[hd.pos], (int32_t)__popc(ms));
+            if (active && lane == __ffs(ms) - 1) atomicAdd(PEER ? covdiff_cell(tv, hd.pos) : tv.covdiff + hd.pos, (int32_t)__popc(ms));
             const int32_t ke = active ? (int32_t)(hd.pos + rspan) : (int32_t)(0x80000000u + lane);
             const uint32_t me = __match_any_sync(0xFFFFFFFFu, ke);
-            if (active && lane == __ffs(me) - 1) atomicAdd(&tv.covdiff[hd.pos + rspan], -(int32_t)__popc(me));
+            if (active && lane == __ffs(me) - 1) atomicAdd(PEER ? covdiff_cell(tv, (int64_t)hd.pos + rspan) : tv.covdiff + hd.pos + rspan, -(int32_t)__popc(me));
 #pragma unroll
             for (int k = 0; k < kMaxDelsPerRead; ++k)
                 if ((uint32_t)k < nd && (int)del_q[k] >= dp.min_bq)
-                    for (uint32_t j = 0; j < del_len[k]; ++j) atomicAdd(&tv.dels[del_pos[k] + j], 1u);
+                    for (uint32_t j = 0; j < del_len[k]; ++j) atomicAdd(PEER ? dels_cell(tv, (int64_t)del_pos[k] + j) : tv.dels + del_pos[k] + j, 1u);
         }
         if (n_runs) {
             if (nr) {
@@ -514,7 +515,7 @@ k_deposit_tile5(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
                                     if (lo > a0) {
                                         const uint32_t r = lo - 1, d = x_rel - s_qo[r];
                                         if (d < (uint32_t)s_len[r])
-                                            deposit_base(tv, dp, (int64_t)s_pos[r] + d, (sx >> (4 * bb)) & 15u,
+                                            deposit_base<PEER>(tv, dp, (int64_t)s_pos[r] + d, (sx >> (4 * bb)) & 15u,
                                                          (qv >> (8 * bb)) & 255u, chunk_ord + (s_rix[r] & 255u));
                                     }
                                 }
@@ -670,11 +671,17 @@ k_deposit_tile5(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
                             // the four first-seen ordinals of the column come with ONE 16-byte load (requested before
                             // the reductions are issued)
                             const int64_t cell = (int64_t)col * 4;
-                            const uint4 ff = *reinterpret_cast<const uint4*>(first0 + cell);
+                            uint32_t* prow = plane + cell;
+                            const uint32_t* frow = first0 + cell;
+                            if (PEER && peer_remote(tv.peer, col)) {       // a column another rank owns: its tables, over NVLink
+                                prow = plane_row(tv, tp.prim_plane, col);
+                                frow = first_row(tv, 0, col);
+                            }
+                            const uint4 ff = *reinterpret_cast<const uint4*>(frow);
 #pragma unroll
                             for (int c = 0; c < 4; ++c) {
                                 const uint32_t f = (cnt4 >> (8 * c)) & 255u;
-                                if (f) atomicAdd(&plane[cell + c], f);
+                                if (f) atomicAdd(prow + c, f);
                             }
                             if ((cnt4 & 0x000000FFu) && ff.x > ord_lo) fresh |= 1u;
                             if ((cnt4 & 0x0000FF00u) && ff.y > ord_lo) fresh |= 2u;
@@ -706,7 +713,7 @@ k_deposit_tile5(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
                                         const uint32_t hb = __ballot_sync(0xFFFFFFFFu, hit);
                                         if (hb) {
                                             if (lane == 0)
-                                                atomicMin(&first0[(int64_t)icol * 4 + c],
+                                                atomicMin((PEER ? first_row(tv, 0, icol) : first0 + (int64_t)icol * 4) + c,
                                                           chunk_ord0 + (s_rix[q0 + (__ffs(hb) - 1)] & 255u));
                                             break;
                                         }
@@ -723,7 +730,7 @@ k_deposit_tile5(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
         // ---- reads the tiled path could not take (many runs, long, exotic base codes): general path, one warp each
         __syncthreads();
         const uint32_t n_def = s_misc[6];
-        for (uint32_t d = warp; d < n_def; d += kT5Warps) deposit_read_warp(b, tv, dp, chunk0 + s_dlist[d], lane);
+        for (uint32_t d = warp; d < n_def; d += kT5Warps) (PEER ? deposit_read_warp_peer : deposit_read_warp)(b, tv, dp, chunk0 + s_dlist[d], lane);
     }
 }
 

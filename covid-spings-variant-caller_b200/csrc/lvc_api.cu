@@ -70,6 +70,11 @@ struct lvc_handle {
     uint16_t* d_lut = nullptr;               // [kMaxKeys]
     uint32_t* d_dels = nullptr;
     int32_t* d_covdiff = nullptr;
+    PeerView* d_peer = nullptr;              // lvc_peer_attach: tables of the other ranks (peer.hpp)
+    uint32_t** d_peer_planes = nullptr;
+    std::vector<void*> peer_opened;
+    int peer_ranks = 0;
+    size_t peer_planes_at_attach = 0;
     uint32_t* d_seen = nullptr;              // first-seen hint nibbles (TableView::seen), 2 words of padding in front
     size_t seen_words = 0;
     bool seen_off = false;                   // someone took a raw pointer to a first-seen table: no hints any more
@@ -162,6 +167,7 @@ static TableView table_view(lvc_handle* h) {
     tv.newkeys = h->d_newkeys;
     tv.status = h->d_status;
     tv.seen = (h->d_seen && !h->seen_off) ? h->d_seen + 2 : nullptr;
+    tv.peer = h->peer_ranks > 1 ? h->d_peer : nullptr;
     return tv;
 }
 
@@ -258,8 +264,10 @@ int lvc_create(lvc_handle** out, int device, int64_t ref_len, const uint8_t* ref
         CU(cudaFuncSetAttribute(k_deposit_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes));
         CU(cudaFuncSetAttribute(k_deposit_tile4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTile4SmemBytes));
         CU(cudaFuncSetAttribute(k_deposit_tile4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTile4SmemBytes));
-        CU(cudaFuncSetAttribute(k_deposit_tile5<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTile5SmemBytes));
-        CU(cudaFuncSetAttribute(k_deposit_tile5<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTile5SmemBytes));
+        CU(cudaFuncSetAttribute(k_deposit_tile5<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTile5SmemBytes));
+        CU(cudaFuncSetAttribute(k_deposit_tile5<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTile5SmemBytes));
+        CU(cudaFuncSetAttribute(k_deposit_tile5<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTile5SmemBytes));
+        CU(cudaFuncSetAttribute(k_deposit_tile5<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTile5SmemBytes));
         CU(cudaStreamSynchronize(h->stream));
         return LVC_OK;
     };
@@ -279,7 +287,9 @@ void lvc_destroy(lvc_handle* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (auto p : h->planes) cudaFree(p);
     for (int g = 0; g < 4; ++g) cudaFree(h->d_first[g]);
-    cudaFree(h->d_ref); cudaFree(h->d_planes); cudaFree(h->d_lut); cudaFree(h->d_dels); cudaFree(h->d_covdiff); cudaFree(h->d_seen);
+    cudaFree(h->d_ref); cudaFree(h->d_planes); cudaFree(h->d_lut); cudaFree(h->d_dels); for (void* q : h->peer_opened) cudaIpcCloseMemHandle(q);
+    cudaFree(h->d_peer); cudaFree(h->d_peer_planes);
+    cudaFree(h->d_covdiff); cudaFree(h->d_seen);
     cudaFree(h->d_first_arr); cudaFree(h->d_newkeys); cudaFree(h->d_replay); cudaFree(h->d_status); cudaFree(h->d_keymap);
     if (h->h_status) cudaFreeHost(h->h_status);
     if (h->h_sample) cudaFreeHost(h->h_sample);
@@ -385,7 +395,13 @@ static int launch_deposit(lvc_handle* h, const BatchView& bv, int replay, uint64
     // long reads: the CTA-cooperative kernel while the reads' ops fit its tables (<= 32 per read), else one warp per read
     // (its cell indices are 32-bit: contigs below 2^30 columns)
     const int long_impl = (n_cigar_ops <= 40ull * n && !replay && h->long_impl == 6 && h->G < (1ll << 30)) ? 6 : 3;
-    const int impl = h->impl == 0 ? (long_reads ? long_impl : h->tile_impl) : h->impl;
+    int impl = h->impl == 0 ? (long_reads ? long_impl : h->tile_impl) : h->impl;
+    if (h->peer_ranks > 1) {
+        // peer tables: only the generation-5 tiled kernel and the any-record kernels route their reductions
+        if (h->planes.size() != h->peer_planes_at_attach)
+            return fail(h, LVC_EINVAL, "a plane was added after lvc_peer_attach: export and attach again");
+        impl = (impl == 5 || (h->impl == 0 && !long_reads)) ? 5 : (long_reads ? 3 : 1);
+    }
     // the tiled kernels' byte arithmetic assumes a primary quality and a threshold below 128
     const bool tile_ok = h->qprim < 128 && h->min_bq <= 128 && h->lut[h->qprim] != kNoPlane;
     if (impl == 6 && !replay && h->G < (1ll << 30)) {
@@ -410,11 +426,13 @@ static int launch_deposit(lvc_handle* h, const BatchView& bv, int replay, uint64
           at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
           at[0].val.programmaticStreamSerializationAllowed = 1;
           cfg.attrs = at; cfg.numAttrs = 1;
-          CU(cudaLaunchKernelEx(&cfg, k_deposit_warp, bv, tv, dp, n)); }
+          if (h->peer_ranks > 1) CU(cudaLaunchKernelEx(&cfg, k_deposit_warp<true>, bv, tv, dp, n));
+          else CU(cudaLaunchKernelEx(&cfg, k_deposit_warp<false>, bv, tv, dp, n)); }
         h->launches++;
     } else if (impl == 1 || replay || !tile_ok) {
         { KernelTimer t(h, 1);
-          k_deposit_general<<<(n + 127) / 128, 128, 0, h->stream>>>(bv, tv, dp, n); }
+          if (h->peer_ranks > 1) k_deposit_general<true><<<(n + 127) / 128, 128, 0, h->stream>>>(bv, tv, dp, n);
+          else k_deposit_general<false><<<(n + 127) / 128, 128, 0, h->stream>>>(bv, tv, dp, n); }
         h->launches++;
     } else {
         TileParams tp = make_tile_params(n, h->sm_count);
@@ -434,8 +452,10 @@ static int launch_deposit(lvc_handle* h, const BatchView& bv, int replay, uint64
               at[0].val.programmaticStreamSerializationAllowed = 1;
               cfg.attrs = at; cfg.numAttrs = 1;
               if (impl == 5) {
-                  if (h->min_bq <= 0) CU(cudaLaunchKernelEx(&cfg, k_deposit_tile5<true>, bv, tv, dp, tp));
-                  else CU(cudaLaunchKernelEx(&cfg, k_deposit_tile5<false>, bv, tv, dp, tp));
+                  using T5 = decltype(&k_deposit_tile5<false, false>);
+                  static const T5 t5[2][2] = {{k_deposit_tile5<false, false>, k_deposit_tile5<false, true>},
+                                              {k_deposit_tile5<true, false>, k_deposit_tile5<true, true>}};
+                  CU(cudaLaunchKernelEx(&cfg, t5[h->min_bq <= 0 ? 1 : 0][h->peer_ranks > 1 ? 1 : 0], bv, tv, dp, tp));
               } else if (h->min_bq <= 0) CU(cudaLaunchKernelEx(&cfg, k_deposit_tile4<true>, bv, tv, dp, tp));
               else CU(cudaLaunchKernelEx(&cfg, k_deposit_tile4<false>, bv, tv, dp, tp));
           } else if (h->min_bq <= 0)
@@ -648,6 +668,12 @@ int lvc_push_batch_device_async(lvc_handle* h, const lvc_batch* b) {
     bv.n_reads = b->n_reads;
     bv.pos = b->pos; bv.flag = b->flag; bv.mapq = b->mapq; bv.keep = b->keep;
     bv.cigar_off = b->cigar_off; bv.cigar = b->cigar; bv.seq_off = b->seq_off; bv.seq4 = b->seq4; bv.qual = b->qual;
+    if (h->qprim == 255) {
+        // the first push of this handle is an asynchronous one (peer tables: nothing may be deposited before the tables
+        // are mapped): elect the tiled kernel's primary quality now (one small copy + stream synchronisation)
+        rc = premap_device(h, b);
+        if (rc) return rc;
+    }
     rc = launch_deposit(h, bv, 0, b->n_cigar_ops, b->n_qual_bytes);
     if (rc) return rc;
     h->ordinal += b->n_reads;
@@ -1012,4 +1038,5 @@ uint64_t lvc_h2d_payload_bytes(lvc_handle* h) { return h ? h->h2d_payload_bytes 
 }  // extern "C"
 
 #include "reduce_nccl.hpp"
+#include "peer.hpp"
 #include "ingest.hpp"

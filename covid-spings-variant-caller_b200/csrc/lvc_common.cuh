@@ -25,6 +25,21 @@ __host__ __device__ __forceinline__ uint32_t gs_nibble(uint32_t gs) {
     return (uint32_t)(inv >> (gs * 4)) & 0xFu;
 }
 
+// Position ownership over NVLink peer memory (lvc_peer_attach): rank r owns the columns [r*per, (r+1)*per) and its tables
+// hold the history of those columns only.  A deposit into a column owned by another rank is reduced directly into THAT
+// rank's table through its peer-mapped pointer (a RED that travels over NVLink / NVSwitch and is resolved in the owner's
+// L2): the exchange step of the read-chunk sharding disappears into the deposit kernel.
+constexpr int kMaxPeers = 8;
+struct PeerView {
+    int32_t n_ranks, rank;
+    int64_t per;                              // columns per rank (lvc_position_slice)
+    int64_t lo, hi;                           // this rank's columns [lo, hi)
+    uint32_t* dels[kMaxPeers];                // [rank] -> that rank's table ([rank] of this rank = its own pointer)
+    int32_t* covdiff[kMaxPeers];
+    uint32_t* first[kMaxPeers][4];
+    uint32_t* const* planes[kMaxPeers];       // [rank] -> device array indexed by THIS rank's plane id
+};
+
 // Persistent per-handle tables as the kernels see them.
 struct TableView {
     int64_t G;                    // reference length
@@ -38,6 +53,7 @@ struct TableView {
     const uint32_t* seen;         // hint, may be null: one nibble per column (8 columns per word), bit = "this A/C/G/T
                                   // allele had a first-seen ordinal after an EARLIER batch" (written by k_genotype);
                                   // readable from column -16 to G + 31
+    const PeerView* peer;         // null unless lvc_peer_attach was called (device memory)
 };
 
 // One batch of reads, device pointers (mirrors lvc_batch in include/lvc.h).
@@ -61,6 +77,32 @@ struct DepositParams {
     int replay;                   // 0: normal pass; 1: deposit only keys in `replay_keys`, no dels/cov
     const uint32_t* replay_keys;  // [32] bitmap (device) when replay
 };
+
+// ---- table cells by column, routed to the owning rank when peer tables are attached (the local slice takes the first branch)
+__device__ __forceinline__ int peer_owner(const PeerView* pv, int64_t col) {
+    const uint32_t r = (uint32_t)col / (uint32_t)pv->per;
+    return (int)(r < (uint32_t)pv->n_ranks ? r : (uint32_t)pv->n_ranks - 1u);
+}
+__device__ __forceinline__ bool peer_remote(const PeerView* pv, int64_t col) { return pv && (col < pv->lo || col >= pv->hi); }
+// covdiff has G + 1 entries; entry i belongs to the owner of column min(i, G - 1)
+__device__ __forceinline__ int32_t* covdiff_cell(const TableView& tv, int64_t i) {
+    const int64_t c = i < tv.G ? i : tv.G - 1;
+    if (peer_remote(tv.peer, c)) return tv.peer->covdiff[peer_owner(tv.peer, c)] + i;
+    return tv.covdiff + i;
+}
+__device__ __forceinline__ uint32_t* dels_cell(const TableView& tv, int64_t col) {
+    if (peer_remote(tv.peer, col)) return tv.peer->dels[peer_owner(tv.peer, col)] + col;
+    return tv.dels + col;
+}
+// row (4 cells) of plane `pl` / of the first-seen table of `group` at column col
+__device__ __forceinline__ uint32_t* plane_row(const TableView& tv, uint32_t pl, int64_t col) {
+    if (peer_remote(tv.peer, col)) return tv.peer->planes[peer_owner(tv.peer, col)][pl] + col * 4;
+    return tv.planes[pl] + col * 4;
+}
+__device__ __forceinline__ uint32_t* first_row(const TableView& tv, uint32_t group, int64_t col) {
+    if (peer_remote(tv.peer, col)) return tv.peer->first[peer_owner(tv.peer, col)][group] + col * 4;
+    return tv.first[group] + col * 4;
+}
 
 __device__ __forceinline__ bool read_passes_filter(uint32_t flag, uint32_t mapq, uint32_t keep, int min_mq) {
     // pysam stepper "samtools": flag filter, mapq, ignore_orphans + host admission bit

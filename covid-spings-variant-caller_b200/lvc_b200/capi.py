@@ -114,6 +114,10 @@ SIGNATURES = [
     ("lvc_position_slice", C.c_int, [_H, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     ("lvc_reduce_tables", C.c_int, [_H, C.c_void_p, C.c_int, C.c_int, C.c_int]),
     ("lvc_last_exchange_bytes", C.c_uint64, [_H]),
+    ("lvc_peer_export", C.c_int, [_H, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    ("lvc_peer_attach", C.c_int, [_H, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    ("lvc_peer_detach", C.c_int, [_H]),
+    ("lvc_stream_barrier", C.c_int, [_H, C.c_void_p]),
     ("lvc_launch_count", C.c_uint64, [_H]),
     ("lvc_h2d_payload_bytes", C.c_uint64, [_H]),
 ]
@@ -407,6 +411,30 @@ class Handle:
         """the one exchange step of the read-chunk sharding (lvc_reduce_tables); returns the bytes fed in"""
         self._check(self.lib.lvc_reduce_tables(self.h, comm.c, comm.n_ranks, comm.rank, int(mode)))
         return int(self.lib.lvc_last_exchange_bytes(self.h))
+
+    def peer_export(self) -> bytes:
+        """CUDA IPC blob of this handle's tables (lvc_peer_export) for the other ranks' peer_attach"""
+        n = C.c_size_t(0)
+        self._check(self.lib.lvc_peer_export(self.h, None, 0, C.byref(n)))
+        buf = C.create_string_buffer(n.value)
+        self._check(self.lib.lvc_peer_export(self.h, buf, n.value, C.byref(n)))
+        return buf.raw[:n.value]
+
+    def peer_attach(self, rank: int, blobs) -> None:
+        """map the other ranks' tables (blobs[r] = rank r's peer_export(); blobs[rank] is ignored): from now on the
+        deposit kernels reduce into the owner's tables over NVLink and this handle genotypes its own position slice"""
+        n = len(blobs)
+        keep = [C.create_string_buffer(b, len(b)) if b is not None else None for b in blobs]
+        ptrs = (C.c_void_p * n)(*[C.cast(k, C.c_void_p) if k is not None else None for k in keep])
+        lens = (C.c_size_t * n)(*[len(b) if b is not None else 0 for b in blobs])
+        self._check(self.lib.lvc_peer_attach(self.h, int(rank), n, ptrs, lens))
+
+    def peer_detach(self) -> None:
+        self._check(self.lib.lvc_peer_detach(self.h))
+
+    def stream_barrier(self, comm: "NcclComm") -> None:
+        """stream-ordered barrier over the ranks of `comm` (lvc_stream_barrier)"""
+        self._check(self.lib.lvc_stream_barrier(self.h, comm.c))
 
     def position_slice(self, n_ranks: int, rank: int):
         p0, p1 = C.c_int64(0), C.c_int64(0)

@@ -331,6 +331,55 @@ def process_batch_library(caller, batch: ReadBatch, comm, mode: str = "scatter")
     return n
 
 
+_NIBBLE_TO_GS = 0xFEDCBA9387625104          # lvc_common.cuh kNibbleToGS: BAM nibble -> (allele group << 2 | slot)
+
+
+def batch_keys(batch: ReadBatch, min_base_quality: int) -> List[int]:
+    """the (allele group << 8 | quality) plane keys a batch can deposit into (a superset: every stored base is looked at,
+    soft clips and padding included) -- what peer_setup needs BEFORE the first deposit"""
+    q = np.asarray(batch.qual, dtype=np.uint8)
+    s = np.asarray(batch.seq4, dtype=np.uint8)
+    n = min(len(q), 2 * len(s))
+    nib = np.empty(2 * len(s), dtype=np.uint8)
+    nib[0::2], nib[1::2] = s >> 4, s & 15
+    group = np.array([((_NIBBLE_TO_GS >> (4 * k)) & 15) >> 2 for k in range(16)], dtype=np.uint16)[nib[:n]]
+    keep = q[:n].astype(np.int32) >= int(min_base_quality)
+    return sorted(int(k) for k in np.unique((group[keep] << 8) | q[:n][keep].astype(np.uint16)))
+
+
+def peer_setup(caller, comm, keys=None, group=None) -> None:
+    """Position ownership over NVLink peer memory (lvc_peer_attach): make the plane set identical on every rank (the
+    union of the ranks' keys and of `keys`), exchange the CUDA IPC blobs of the tables over torch.distributed and map
+    the other ranks' tables.  Call once per caller (and again if a batch brings a quality never seen before)."""
+    import torch.distributed as dist
+    h = caller._handle
+    for k in key_union(sorted(set(int(k) for k in h.plane_keys()) | set(int(k) for k in (keys or []))), group):
+        h.ensure_plane(k)
+    h.sync()
+    blobs = [None] * comm.n_ranks
+    dist.all_gather_object(blobs, h.peer_export(), group=group)
+    h.peer_attach(comm.rank, blobs)
+    h.stream_barrier(comm)                      # nobody deposits before everybody has mapped everybody
+    h.sync()
+
+
+def process_batch_peer(caller, batch: ReadBatch, comm) -> None:
+    """One sample, read-chunk sharding with position ownership and NO exchange step: every rank deposits its contiguous
+    chunk of the coordinate-sorted batch; bases of columns another rank owns are reduced into that rank's tables over
+    NVLink by the deposit kernel itself (peer_setup must have been called).  Two stream-ordered barriers frame the
+    deposit; each rank then genotypes the slice it owns (gather_variants merges the records)."""
+    h = caller._handle
+    world, rank = comm.n_ranks, comm.rank
+    base = h.ordinal
+    a, b = shard_reads(batch, world)[rank]
+    h.ordinal = base + a                      # first-seen ordinals are global read indices
+    h.stream_barrier(comm)                    # the previous batch's genotype pass is complete on every rank
+    if b > a:
+        h.push_batch(batch.slice(a, b).as_capi())
+    h.ordinal = base + batch.n_reads
+    h.stream_barrier(comm)                    # every rank's reductions have landed
+
+
 def gather_variants(caller, group=None) -> List[dict]:
     """records of every rank's position slice, merged in position order on every rank"""
     import torch.distributed as dist

@@ -243,6 +243,28 @@ int lvc_position_slice(const lvc_handle* h, int n_ranks, int rank, int64_t* p0, 
 int lvc_reduce_tables(lvc_handle* h, void* nccl_comm, int n_ranks, int rank, int mode);
 uint64_t lvc_last_exchange_bytes(lvc_handle* h);    /* bytes this rank fed into the last lvc_reduce_tables */
 
+/* ---- multi-GPU without an exchange step: position ownership over NVLink peer memory -------------------------------
+ * Rank r owns the columns lvc_position_slice(h, n, r) and its tables hold the history of those columns only.  After
+ * lvc_peer_attach the deposit kernels reduce a base of column c directly into the tables of the rank that OWNS c,
+ * through that rank's peer-mapped pointers (CUDA IPC, one process per GPU): a RED that crosses NVLink / NVSwitch and is
+ * resolved in the owner's L2.  A rank's chunk of a coordinate-sorted batch lies almost entirely inside its own slice,
+ * so only the reads that straddle a slice border pay the link.  Per batch: every rank calls lvc_set_ordinal(base +
+ * first read index of its chunk) and lvc_push_batch*, then lvc_stream_barrier (all ranks' reductions are complete),
+ * then lvc_genotype* (its own slice; the range is set by lvc_peer_attach), then lvc_stream_barrier again before the
+ * next batch (nobody deposits into tables a slower rank is still genotyping).
+ *   lvc_peer_export  writes the handle's IPC blob (call with blob = NULL to get the size).  The (allele group, quality)
+ *                    plane set must be identical on all ranks (ensure the union first); a plane added later makes
+ *                    lvc_push_batch* fail with LVC_EINVAL until a new export / attach round.
+ *   lvc_peer_attach  blobs[r] / lens[r] = rank r's blob (blobs[rank] is ignored).  At most 8 ranks.  Short-read batches
+ *                    run the generation-5 tiled kernel, everything else the any-record kernels.
+ *   lvc_peer_detach  closes the peer mappings (also done by lvc_destroy).
+ * [EXT] the reference is one process (client_server/vc_queue.py:99); this replaces its in-order dict update
+ * (live_variant_caller.py:77-103) for one sample spread over several GPUs. */
+int lvc_peer_export(lvc_handle* h, void* blob, size_t cap, size_t* len);
+int lvc_peer_attach(lvc_handle* h, int rank, int n_ranks, const void* const* blobs, const size_t* lens);
+int lvc_peer_detach(lvc_handle* h);
+int lvc_stream_barrier(lvc_handle* h, void* nccl_comm);
+
 /* ---- introspection ---------------------------------------------------------------------------- */
 /* number of kernels this library has launched on the handle since creation (bench gpu_launches) */
 uint64_t lvc_launch_count(lvc_handle* h);

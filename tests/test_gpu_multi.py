@@ -39,11 +39,17 @@ def _worker(rank, world, port, rows, ref, q, mode="full"):
     th = dict(minBQ=13, minMQ=0, minDP=3, minAD=2, ratio=0.05)
     lvc = LiveVariantCaller(fa, th["minBQ"], th["minMQ"], th["minDP"], th["minAD"], th["ratio"], 1, device=rank)
     out = []
-    comm = ldist.make_library_comm(rank) if mode in ("lib_scatter", "lib_all") else None
+    comm = ldist.make_library_comm(rank) if mode in ("lib_scatter", "lib_all", "peer") else None
+    if mode == "peer":
+        # position ownership over NVLink peer memory: the plane set is fixed and the tables are mapped BEFORE the first deposit
+        allb = packing.pack_reads(r2t(rows), th["minMQ"])
+        ldist.peer_setup(lvc, comm, keys=ldist.batch_keys(allb, th["minBQ"]))
     for k in range(3):                                   # three live batches
         sel = list(range(k, len(rows), 3))
         batch = packing.pack_reads(r2t([rows[i] for i in sel]), th["minMQ"])
-        if comm is not None:
+        if mode == "peer":
+            ldist.process_batch_peer(lvc, batch, comm)
+        elif comm is not None:
             nbytes = ldist.process_batch_library(lvc, batch, comm, "scatter" if mode == "lib_scatter" else "all")
             assert nbytes > 0
         elif mode == "halo":
@@ -53,7 +59,7 @@ def _worker(rank, world, port, rows, ref, q, mode="full"):
             ldist.process_batch_sharded(lvc, batch)
         out.append(ldist.gather_variants(lvc))
     lvc._handle.set_genotype_range(0, -1)
-    if mode in ("halo", "lib_scatter"):
+    if mode in ("halo", "lib_scatter", "peer"):
         # every rank keeps the history of its own slice of positions only
         p0, p1 = ldist.position_slice(len(ref), world, rank)
         lvc._candidates()                                  # genotype pass over all positions: fills the dense outputs
@@ -66,6 +72,8 @@ def _worker(rank, world, port, rows, ref, q, mode="full"):
         mem = memory_tables(lvc.memory)
     if rank == 0:
         q.put((out, mem))
+    if mode == "peer":
+        lvc._handle.peer_detach()                          # nobody frees tables another rank still has mapped
     dist.barrier()
     lvc.close()
     if comm is not None:
@@ -144,9 +152,10 @@ def test_two_ranks_halo_exchange_equal_one(lib, golden_synth, tmp_path):
     one.close()
 
 
-@pytest.mark.parametrize("mode", ["lib_scatter", "lib_all"])
+@pytest.mark.parametrize("mode", ["lib_scatter", "lib_all", "peer"])
 def test_two_ranks_library_exchange_equal_one(lib, golden_synth, tmp_path, mode):
-    """lvc_reduce_tables (the C-ABI exchange: one grouped NCCL reduce-scatter / all-reduce over the device tables):
+    """mode "peer": lvc_peer_attach (position ownership, the deposit kernel reduces into the owner's tables over NVLink, no
+    exchange step).  Otherwise lvc_reduce_tables (the C-ABI exchange: one grouped NCCL reduce-scatter / all-reduce over the device tables):
     records of every live batch and the tables must equal the single-GPU run"""
     import torch
     if torch.cuda.device_count() < 2:
