@@ -230,3 +230,26 @@ def test_ont_batch_fast_is_deterministic_and_well_formed(lib):
     from lvc_b200.dist import ref_lengths
     assert (ref_lengths(a) == 400).all()
     assert int(a.qual[:a.n_qual].max()) <= 90 and (a.keep[:n] & 2).all()
+
+
+def test_batch_keys_cover_every_deposited_key(lib, golden_synth):
+    """peer tables fix the plane set before the first deposit: dist.batch_keys must name every (allele group, quality)
+    key the oracle deposits into (a superset is fine), and the owner of a column follows lvc_position_slice"""
+    from lvc_b200 import packing, dist as ldist
+    for scen in ("mixed_small", "ont_like", "amplicon_like"):
+        g = golden_synth[scen]
+        batch = packing.pack_reads(rows_to_tuples(g["reads"]), 0)
+        for mbq in (0, 13, 30):
+            keys = set(ldist.batch_keys(batch, mbq))
+            oc = po.OracleCaller(g["ref"], mbq, 0, 1, 1, 0.0)
+            oc.process_reads(synth_small.rows_to_reads(g["reads"]))
+            nib = {c: k for k, c in enumerate("=ACMGRSVTWYHKDBN")}
+            gs = [((0xFEDCBA9387625104 >> (4 * k)) & 15) for k in range(16)]
+            for site in oc.memory.values():
+                for allele, quals in site["snvs"].items():
+                    for q in quals:
+                        assert ((gs[nib[allele]] >> 2) << 8 | int(q)) in keys, (scen, mbq, allele, q)
+    G, world = 1000, 3
+    per = (G + 1 + world - 1) // world
+    for r in range(world):
+        assert ldist.position_slice(G, world, r) == (min(r * per, G), min((r + 1) * per, G))
