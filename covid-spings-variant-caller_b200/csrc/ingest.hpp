@@ -286,16 +286,18 @@ static std::string pack(lvc_reads* r, const std::vector<Rec>& recs, int min_mapq
         mpos.resize(n); tlen.resize(n); mref.resize(n);
         for (size_t i = 0; i < n; ++i) { mpos[i] = recs[i].next_pos; tlen[i] = recs[i].tlen; mref[i] = recs[i].next_ref; }
     }
+    timer.mark("mate arrays");
     auto name = [&](uint32_t i) { return lvc_overlap::NameKey{recs[i].name, recs[i].l_name}; };
     const int rc = lvc_overlap::admit_core((uint32_t)n, r->pos, r->flag, r->mapq, r->cigar_off, r->cigar, r->seq_off, r->seq4,
                                            r->qual, name, any_pair ? mpos.data() : nullptr, any_pair ? mref.data() : nullptr,
                                            any_pair ? tlen.data() : nullptr, min_mapq, max_depth,
                                            any_pair ? overlap_model : LVC_OVERLAP_OFF, adm.data(), &r->overlap_pairs,
                                            &r->overlap_bases);
+    timer.mark("admit + overlaps");
     if (rc == LVC_EUNSORTED) return fail("reads are not coordinate sorted");
     if (rc) return fail("admission failed (%d)", rc);
     for (size_t i = 0; i < n; ++i) r->keep[i] |= adm[i];
-    timer.mark("admit + overlaps");
+    timer.mark("keep bits");
     return "";
 }
 
