@@ -213,3 +213,37 @@ def test_first_seen_hints_between_batches(lib):
         h.reset()
     assert np.array_equal(runs[0], runs[1])
     h.close()
+
+
+@pytest.mark.parametrize("impl", [1, 3, 4, 5, 6])
+def test_read_leaving_the_reference_is_reported_and_not_deposited(lib, impl):
+    """a read whose reference span ends past the contig: every kernel reports LVC_ERANGE (the reference would raise
+    inside pysam) and deposits nothing of it; the other reads of the batch are deposited exactly"""
+    from lvc_b200 import capi, packing, synth
+    ref = synth.random_reference(600, 5)
+    G = len(ref)
+    q = [40] * 100
+
+    def rd(pos, ops):
+        lq = sum(l for o, l in ops if o in (0, 1, 4))
+        return (0, pos, 60, ops, ref[pos:pos + lq] if pos + lq <= G else (ref[pos:] + "A" * lq)[:lq], [40] * lq)
+    long_ops = [(4, 5), (0, 20), (1, 2), (0, 20), (2, 3), (0, 30), (4, 4)]        # S M I M D M S: 7 ops (long-read path)
+    good = [rd(10, [(0, 100)]), rd(50, long_ops), rd(300, [(0, 60), (2, 2), (0, 40)])]
+    bad = rd(G - 50, [(0, 100)])                                                  # 50 columns past the end
+    bad_long = rd(G - 40, long_ops)                                               # 73 reference columns from G - 40
+    th = dict(minBQ=20, minMQ=0)
+    href = capi.Handle(ref.encode("latin-1"), th["minBQ"], th["minMQ"], device=0)
+    href.set_impl(1)
+    href.push_batch(packing.pack_reads(good, 0).as_capi())
+    want = device_tables(href)
+    href.close()
+    for extra in (bad, bad_long):
+        h = capi.Handle(ref.encode("latin-1"), th["minBQ"], th["minMQ"], device=0)
+        h.set_impl(impl)
+        with pytest.raises(capi.LvcError) as ei:
+            h.push_batch(packing.pack_reads(good + [extra], 0).as_capi())
+        assert ei.value.code == -5                                                # LVC_ERANGE
+        got = device_tables(h)
+        for a, b_, what in zip(got, want, ("ad", "qsum", "first", "dels", "cov")):
+            assert np.array_equal(a, b_), (impl, what)
+        h.close()
