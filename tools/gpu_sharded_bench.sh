@@ -1,3 +1,4 @@
+# config-5 read-chunk sharding at N GPUs (run: gpurun --gpus N -- bash tools/gpu_sharded_bench.sh N)
 N=$1
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 5 --legs config5 --no-cpu-baseline --e2e-steps 2 > gpurun_out/q_bench$N.json 2> gpurun_out/q_bench$N.err; echo "bench rc=$?"
 python - <<PY

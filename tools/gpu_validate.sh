@@ -1,3 +1,4 @@
+# full GPU validation of a commit on one B200: pytest -m gpu, bench.py (all legs), the reference arm, ncu launch lists (run: gpurun -- bash tools/gpu_validate.sh)
 python -m pytest tests -m gpu -x -q > gpurun_out/o_tests.log 2>&1; echo "rc=$?" >> gpurun_out/o_tests.log
 python bench.py > gpurun_out/o_bench.json 2> gpurun_out/o_bench.err; echo "bench rc=$?"
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/o_ref.json 2> gpurun_out/o_ref.err; echo "ref rc=$?"
