@@ -90,9 +90,26 @@ def live_bytes(batch) -> int:
     return int((20 + 4 * nc[live] + (lq[live] + 1) // 2 + lq[live]).sum()), int(live.sum())
 
 
+QUALITY_FORM = "codes"      # --quality-form: what the short-read legs ship (codes = lvc_batch.qual_bits 2 where a batch qualifies)
+
+
+def in_form(batch):
+    """the batch in the quality form the run was asked for (2-bit codes only where the batch qualifies)"""
+    return batch.with_quality_codes() if QUALITY_FORM == "codes" else batch.without_quality_codes()
+
+
+def form_of(batch) -> str:
+    return "2-bit quality codes (lvc_batch.qual_bits = 2), 0.75 B per base" if batch.qcode is not None else \
+        "phred bytes, 1.5 B per base"
+
+
 def to_device(torch, capi, batch, dev):
-    keep = {name: torch.from_numpy(getattr(batch, name).view(np.uint8).reshape(-1)).to(dev) for name in BATCH_FIELDS}
-    db = capi.Handle.make_batch(batch.n_reads, batch.n_cigar, batch.n_qual, *[keep[k].data_ptr() for k in BATCH_FIELDS])
+    keep = {name: torch.from_numpy(getattr(batch, name).view(np.uint8).reshape(-1)).to(dev) for name in BATCH_FIELDS
+            if not (name == "qual" and batch.qcode is not None)}
+    if batch.qcode is not None:
+        keep["qual"] = torch.from_numpy(batch.qcode.view(np.uint8).reshape(-1)).to(dev)
+    db = capi.Handle.make_batch(batch.n_reads, batch.n_cigar, batch.n_qual, *[keep[k].data_ptr() for k in BATCH_FIELDS],
+                                qual_dict=batch.qdict if batch.qcode is not None else None)
     return db, keep
 
 
@@ -231,7 +248,7 @@ def main_config(batch, G, bases, alg_bytes, world):
             "(independent samples, no communication)",
             "reads_per_step_per_gpu": batch.n_reads, "aligned_bases_per_step_per_gpu": bases,
             "algorithmic_bytes_per_step_per_gpu": alg_bytes, "ref_len": G, "thresholds": THRESH,
-            "l2": "inputs (0.50 GB/step) larger than L2 (126 MB); no flush needed"}
+            "l2": "inputs (0.50 GB/step; 0.27 GB when the batch ships 2-bit quality codes) larger than L2 (126 MB); no flush needed"}
 
 
 def run_reference(args):
@@ -342,6 +359,7 @@ def leg_config5_single(torch, capi, records, stream, dev, steps=10):
     every read is live here, so the formula fraction IS the live-bytes fraction)."""
     e_lut, om_lut = records.phred_luts()
     ref, batch = config5_workload()
+    batch = in_form(batch)
     h = capi.Handle(ref.encode("latin-1"), THRESH["minBQ"], THRESH["minMQ"], device=dev.index, stream=stream.cuda_stream)
     db, keep = to_device(torch, capi, batch, dev)
 
@@ -375,6 +393,7 @@ def leg_config5_single(torch, capi, records, stream, dev, steps=10):
                        f"{batch.n_reads} reads, seed 20260400", "value": batch.aligned_bases() / (ms * 1e-3), "unit": UNIT,
            "ms_per_step": ms, "algorithmic_bytes": int(byts), "step_frac": byts / (ms * 1e-3) / 1e9 / peak,
            "deposit_kernel_ms": tile_ms / max(tile_n, 1), "live_reads": n_live, "live_bytes": lb,
+           "quality_form": form_of(batch),
            "frac_live": (lb / (tile_ms / max(tile_n, 1) * 1e-3) / 1e9 / peak) if tile_n else None, "steps": steps}
     h.close()
     del keep
@@ -498,6 +517,7 @@ def leg_config4(torch, dist, capi, records, stream, dev, world, rank, n_samples=
     t0 = time.time()
     data = [_cached(f"/tmp/lvc_bench_cfg4_{20260300 + s}.npz",
                     lambda s=s: synth.amplicon_sample(seed=20260300 + s, n_pairs=N_PAIRS // 2)) for s in gen]
+    data = [(r, in_form(b)) for r, b in data]
     gen_s = time.time() - t0
     dbs = [to_device(torch, capi, b, dev) for _, b in data]
     handles = []
@@ -608,7 +628,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--legs", default="all", help="all | main | comma list of: config3,config4,config5,e2e_api")
     ap.add_argument("--no-numa", action="store_true")
+    ap.add_argument("--quality-form", default="codes", choices=["codes", "bytes"],
+                    help="codes: batches whose qualities take <= 4 values ship 2-bit codes (what process_bam does); bytes: one phred byte per base")
     args = ap.parse_args()
+    global QUALITY_FORM
+    QUALITY_FORM = args.quality_form
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
@@ -634,6 +658,7 @@ def main():
 
     # every rank owns an independent sample of the same geometry (rank 0 = the canonical config-2 seed)
     ref, batch = make_workload(20260101 + 1000 * rank, args.n_pairs)
+    batch = in_form(batch)
     G = len(ref)
     bases = batch.aligned_bases()
     alg_bytes = batch.algorithmic_bytes(G)
@@ -818,10 +843,13 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms / args.e2e_steps, "steps": args.e2e_steps,
                     "api": "LiveVariantCaller.process_batch(pinned SoA, admitted at pack time) + prepare_variants()",
+                    "batch_form": form_of(batch),
                     "admit_ms": admit_ms,
                     "h2d_note": "small per-read arrays copied in full + payload read in place over PCIe: the 16-byte "
                                 "groups of each chunk's staged extent, counted by the library"},
             "e2e_api": e2e_api,
+            "batch_form": form_of(batch) + "; the algorithmic bytes of the roofline are SURVEY 8d's (1.5 B per base) "
+                          "whatever the form; --quality-form bytes ships one phred byte per base",
             "configs": configs,
             "numa": numa,
             "gpu_launches": int(launches),

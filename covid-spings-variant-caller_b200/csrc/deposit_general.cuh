@@ -64,7 +64,6 @@ __device__ __forceinline__ void deposit_read_general(const BatchView& b, const T
         atomicAdd(PEER ? covdiff_cell(tv, pos + rlen) : tv.covdiff + pos + rlen, -1);
     }
     const uint64_t qb = b.seq_off[i];
-    const uint8_t* qual = b.qual + qb;
     const uint8_t* seq = b.seq4 + (qb >> 1);
     const uint32_t ord = dp.ord_base + i;
     int64_t r = pos;
@@ -73,7 +72,7 @@ __device__ __forceinline__ void deposit_read_general(const BatchView& b, const T
         const uint32_t c = b.cigar[k], op = c & 15u, len = c >> 4;
         if (op_is_match(op)) {
             for (uint32_t j = 0; j < len; ++j, ++qi, ++r) {
-                const uint32_t q = qual[qi];
+                const uint32_t q = batch_qual(b, qb + qi);
                 if ((int)q < dp.min_bq) continue;
                 const uint32_t byte = seq[qi >> 1];
                 const uint32_t nib = (qi & 1u) ? (byte & 15u) : (byte >> 4);
@@ -82,7 +81,7 @@ __device__ __forceinline__ void deposit_read_general(const BatchView& b, const T
         } else if (op == 2 || op == 3) {
             // deletion / ref-skip entries are kept iff the NEXT query base passes the quality rule
             // (pysam pileup_base_qual_skip on qpos = y; 0 if qpos >= l_qseq) -- SURVEY B3
-            const uint32_t q = (qi < lq) ? (uint32_t)qual[qi] : 0u;
+            const uint32_t q = (qi < lq) ? batch_qual(b, qb + qi) : 0u;
             if (!dp.replay && (int)q >= dp.min_bq) {
                 for (uint32_t j = 0; j < len; ++j) atomicAdd(PEER ? dels_cell(tv, r + j) : tv.dels + r + j, 1u);
             }
@@ -167,12 +166,13 @@ __device__ __forceinline__ void deposit_read_warp_impl(const BatchView& b, const
         atomicAdd(PEER ? covdiff_cell(tv, pos) : tv.covdiff + pos, 1);
         atomicAdd(PEER ? covdiff_cell(tv, pos + (int64_t)rlen) : tv.covdiff + pos + (int64_t)rlen, -1);
     }
-    const uint8_t* qual = b.qual + qb;
+    // (byte form; a quality-code batch keeps its codes at a quarter of the offset and is read through batch_qual)
+    const uint8_t* qual = b.qual + (b.qbits == 2u ? (qb >> 2) : qb);
     const uint8_t* seq = b.seq4 + (qb >> 1);
     // request the read's whole payload now (one line per lane): the per-run loads below then hit L1 instead of
     // paying a DRAM latency per run
     for (uint32_t off = lane * 128u; off < lq; off += 32u * 128u) {
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(qual + off));
+        if (b.qbits != 2u || off < (lq + 3) / 4) asm volatile("prefetch.global.L1 [%0];" ::"l"(qual + off));
         if (off < (lq + 1) / 2) asm volatile("prefetch.global.L1 [%0];" ::"l"(seq + off));
     }
     const uint32_t ord = dp.ord_base + i;
@@ -198,7 +198,7 @@ __device__ __forceinline__ void deposit_read_warp_impl(const BatchView& b, const
         if (wide && !dp.replay && len != 0 && (op == 2 || op == 3)) {
             // deletion / ref-skip entries, every such op of the group in its own lane: kept iff the NEXT query base
             // passes the quality rule (pysam pileup_base_qual_skip on qpos = y; 0 if qpos >= l_qseq) -- SURVEY B3
-            const uint32_t q = (q_off < lq) ? (uint32_t)qual[q_off] : 0u;
+            const uint32_t q = (q_off < lq) ? batch_qual(b, qb + q_off) : 0u;
             if ((int)q >= dp.min_bq)
                 for (uint32_t j = 0; j < len; ++j) atomicAdd(PEER ? dels_cell(tv, pos + r_off + j) : tv.dels + pos + r_off + j, 1u);
         }
@@ -213,7 +213,7 @@ __device__ __forceinline__ void deposit_read_warp_impl(const BatchView& b, const
             const uint32_t opk = ck & 15u, lenk = ck >> 4;
             if (op_is_match(opk)) {
                 for (uint32_t j = lane; j < lenk; j += 32) {
-                    const uint32_t q = qual[qi + j];
+                    const uint32_t q = batch_qual(b, qb + qi + j);
                     if ((int)q < dp.min_bq) continue;
                     const uint32_t byte = seq[(qi + j) >> 1];
                     const uint32_t nib = ((qi + j) & 1u) ? (byte & 15u) : (byte >> 4);
@@ -222,7 +222,7 @@ __device__ __forceinline__ void deposit_read_warp_impl(const BatchView& b, const
             } else if (!dp.replay) {
                 // deletion / ref-skip entries are kept iff the NEXT query base passes the quality rule
                 // (pysam pileup_base_qual_skip on qpos = y; 0 if qpos >= l_qseq) -- SURVEY B3
-                const uint32_t q = (qi < lq) ? (uint32_t)qual[qi] : 0u;
+                const uint32_t q = (qi < lq) ? batch_qual(b, qb + qi) : 0u;
                 if ((int)q >= dp.min_bq)
                     for (uint32_t j = lane; j < lenk; j += 32) atomicAdd(PEER ? dels_cell(tv, r + j) : tv.dels + r + j, 1u);
             }

@@ -76,6 +76,8 @@ struct TileParams {
     uint32_t n_chunks;
     uint32_t qprim;        // primary quality (255 = none)
     uint32_t prim_plane;   // plane id of (group 0, qprim)
+    uint32_t qc_pcode;     // quality-code batches: the code of qprim (0..3)
+    uint32_t qc_cold;      // quality-code batches: bit c = code c passes the base-quality threshold and is not qc_pcode
 };
 
 inline TileParams make_tile_params(uint32_t n_reads, int sm_count) {
@@ -85,6 +87,8 @@ inline TileParams make_tile_params(uint32_t n_reads, int sm_count) {
     (void)sm_count;
     tp.qprim = 255;
     tp.prim_plane = 0;
+    tp.qc_pcode = 0;
+    tp.qc_cold = 0;
     return tp;
 }
 

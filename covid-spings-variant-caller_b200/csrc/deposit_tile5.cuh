@@ -18,6 +18,7 @@
 // Launched with programmatic stream serialization: everything before `griddepcontrol.wait` only reads the batch.
 #pragma once
 #include "deposit_tile4.cuh"
+#include "qcode.hpp"
 
 namespace lvc {
 
@@ -92,7 +93,10 @@ __device__ __forceinline__ void bs_add(const uint32_t (&a)[N], const uint32_t (&
 // kernel parameters stay in the constant bank even where their address is taken (the warp-per-read helper takes
 // the views by reference): without this every thread copies them to local memory first
 // PEER: lvc_peer_attach is active -- columns another rank owns are reduced into that rank's tables (lvc_common.cuh)
-template <bool GE_ALL, bool PEER>
+// QC: quality-code batch (lvc_batch::qual_bits == 2): `b.qual` holds 2-bit codes, 16 bases per 32-bit word; a group of
+//     16 bases is staged from ONE code word + 8 sequence bytes (0.75 bytes per base instead of 1.5); the key transform is
+//     qc_keys16 (qcode.hpp).  Everything after the keys are staged is the same code.
+template <bool GE_ALL, bool PEER, bool QC = false>
 __global__ void __launch_bounds__(kT5Threads, kTile5CtasPerSM)
 k_deposit_tile5(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp, LVC_GC TileParams tp) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -127,7 +131,10 @@ k_deposit_tile5(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
     const uint32_t cur = blockIdx.x;
     ReadHdr hd;
     uint64_t so0;
-    hdr_load1<kT5Reads>(b, cur, tid, hd, so0);
+    if (b.hdr_lazy) {
+        const uint32_t i = cur * kT5Reads + (uint32_t)tid;
+        hd.keep = i < b.n_reads ? (uint32_t)b.keep[i] : 0u;
+    } else hdr_load1<kT5Reads>(b, cur, tid, hd, so0);
     uint32_t* sc = s_misc + 8;                                       // per-chunk scalars
     uint32_t* wc = s_misc + 32;                                      // runs per warp
     if (tid == 0) {
@@ -137,6 +144,7 @@ k_deposit_tile5(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
     // a chunk in which the host admission (htslib max_depth) dropped every read ends here, after ONE load per thread:
     // nothing else of its headers is waited for
     if (!__syncthreads_or(hd.keep & 1u)) return;
+    if (b.hdr_lazy) hdr_load1<kT5Reads>(b, cur, tid, hd, so0);
     if (tid < 66) {
         // edge masks of a 32-column unit, one nibble per column: [0][n] keeps the columns >= n, [1][n] the columns < n
         const uint32_t n = tid < 33 ? (uint32_t)tid : (uint32_t)tid - 33u;
@@ -187,6 +195,10 @@ k_deposit_tile5(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
         // ask L2 for the chunk's payload now: classification and the run table hide the DRAM latency of the staging
         // loads (measured on config 5: 0.524 -> 0.498 ms)
         const uint64_t q0 = base_abs, q1 = so0 + max_rel;
+        if (QC) {
+            for (uint64_t a = (q0 >> 2) + (uint64_t)tid * 128u; a < ((q1 + 3) >> 2); a += (uint64_t)kT5Threads * 128u)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(b.qual + a));
+        } else
         for (uint64_t a = q0 + (uint64_t)tid * 128u; a < q1; a += (uint64_t)kT5Threads * 128u)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(b.qual + a));
         for (uint64_t a = (q0 >> 1) + (uint64_t)tid * 128u; a < ((q1 + 1) >> 1); a += (uint64_t)kT5Threads * 128u)
@@ -242,16 +254,17 @@ k_deposit_tile5(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
                 const uint32_t ndel = (uint32_t)d0 + (uint32_t)d1 + (uint32_t)d2;
                 bool tileable = ndel <= (uint32_t)kMaxDelsPerRead;
                 if (tileable && ndel) {
-                    const uint8_t* qrd = b.qual + so0 + so_rel;
-                    if (d0) { del_pos[0] = hd.pos; del_len[0] = n0; del_q[0] = 0u < lq ? (uint32_t)qrd[0] : 0u; nd = 1; }
+                    const uint64_t qrd0 = so0 + so_rel;
+                    auto qrd = [&](uint32_t k) -> uint32_t { return QC ? batch_qual(b, qrd0 + k) : (uint32_t)b.qual[qrd0 + k]; };
+                    if (d0) { del_pos[0] = hd.pos; del_len[0] = n0; del_q[0] = 0u < lq ? qrd(0) : 0u; nd = 1; }
                     if (d1) {
-                        const uint32_t qv = qo1 < lq ? (uint32_t)qrd[qo1] : 0u;
+                        const uint32_t qv = qo1 < lq ? qrd(qo1) : 0u;
                         if (nd == 0) { del_pos[0] = hd.pos + (int32_t)ro1; del_len[0] = n1; del_q[0] = qv; }
                         else { del_pos[1] = hd.pos + (int32_t)ro1; del_len[1] = n1; del_q[1] = qv; }
                         ++nd;
                     }
                     if (d2) {
-                        const uint32_t qv = qo2 < lq ? (uint32_t)qrd[qo2] : 0u;
+                        const uint32_t qv = qo2 < lq ? qrd(qo2) : 0u;
                         if (nd == 0) { del_pos[0] = hd.pos + (int32_t)ro2; del_len[0] = n2; del_q[0] = qv; }
                         else { del_pos[1] = hd.pos + (int32_t)ro2; del_len[1] = n2; del_q[1] = qv; }
                         ++nd;
@@ -304,7 +317,7 @@ k_deposit_tile5(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
                             // so its latency does not hold up the chunk
                             if (nd == (uint32_t)kMaxDelsPerRead) tileable = false;
                             else {
-                                const uint32_t q = qi < lq ? (uint32_t)b.qual[so0 + so_rel + qi] : 0u;
+                                const uint32_t q = qi < lq ? (QC ? batch_qual(b, so0 + so_rel + qi) : (uint32_t)b.qual[so0 + so_rel + qi]) : 0u;
                                 if (nd == 0) { del_pos[0] = r; del_len[0] = l; del_q[0] = q; }
                                 else { del_pos[1] = r; del_len[1] = l; del_q[1] = q; }
                                 ++nd;
@@ -526,7 +539,46 @@ k_deposit_tile5(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
                     // two groups per iteration, loaded then reduced.  (A software-pipelined version with the next two
                     // groups in flight costs 12 more live registers under the 48-register cap and measured 4 % slower:
                     // with 5 CTAs per SM the load latency is covered by the other CTAs.  One group per iteration is 8 % slower.)
+                    // the same for a quality-code batch: one word of 16 codes + 8 sequence bytes -> 16 keys
+                    auto stage_group_qc = [&](uint32_t gg, uint32_t w, const uint2& sraw) {
+                        const uint32_t s0 = bitsel(sraw.x >> 4, sraw.x << 4, 0x0F0F0F0Fu);
+                        const uint32_t s1 = bitsel(sraw.y >> 4, sraw.y << 4, 0x0F0F0F0Fu);
+                        uint32_t k0, k1;
+                        qc_keys16(s0, s1, w, tp.qc_pcode, k0, k1);
+                        if (tp.qc_cold) {
+                            // some code other than the primary one passes the threshold (uniform over the grid): its bases
+                            // are deposited individually, exactly as in the byte form
+                            uint32_t cold = qc_cold_flags(w, tp.qc_cold);
+                            while (cold) {
+                                const uint32_t bb = (uint32_t)(__ffs(cold) - 1) >> 1;          // base 0..15 of the group
+                                cold &= cold - 1;
+                                const uint32_t x_rel = w_rel + 16u * gg + bb;
+                                uint32_t lo = a0, hi = a1;             // last run with s_qo <= x_rel
+                                while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if (s_qo[m] <= x_rel) lo = m + 1; else hi = m; }
+                                if (lo > a0) {
+                                    const uint32_t r = lo - 1, d = x_rel - s_qo[r];
+                                    if (d < (uint32_t)s_len[r])
+                                        deposit_base<PEER>(tv, dp, (int64_t)s_pos[r] + d, ((bb < 8u ? s0 : s1) >> (4u * (bb & 7u))) & 15u,
+                                                           (b.qdict >> (8u * ((w >> (2u * bb)) & 3u))) & 255u, chunk_ord + (s_rix[r] & 255u));
+                                }
+                            }
+                        }
+                        asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(k_smem + 8u * gg), "r"(k0), "r"(k1) : "memory");
+                    };
                     if (warp == 0 && cmin < cmax) slab_setup(cmin);
+                    if (QC) {
+                        const uint32_t* gc = reinterpret_cast<const uint32_t*>(b.qual + (qbeg >> 2));
+                        for (uint32_t g = tid; g < n_grp; g += 2 * kT5Threads) {
+                            const bool hasB = g + kT5Threads < n_grp;
+                            const uint32_t wA = __ldcs(gc + g);
+                            const uint2 sA = __ldcs(gs + g);
+                            uint32_t wB = 0;
+                            uint2 sB = make_uint2(0, 0);
+                            if (hasB) { wB = __ldcs(gc + g + kT5Threads); sB = __ldcs(gs + g + kT5Threads); }
+                            stage_group_qc(g, wA, sA);
+                            if (hasB) stage_group_qc(g + kT5Threads, wB, sB);
+                        }
+                    } else
                     for (uint32_t g = tid; g < n_grp; g += 2 * kT5Threads) {
                         const bool hasB = g + kT5Threads < n_grp;
                         // streaming loads: the payload is read exactly once and should not displace the few hot lines

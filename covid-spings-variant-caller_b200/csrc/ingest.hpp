@@ -24,6 +24,8 @@ struct lvc_reads {
     int32_t* pos = nullptr; uint16_t* flag = nullptr; uint8_t* mapq = nullptr; uint8_t* keep = nullptr;
     uint32_t* cigar_off = nullptr; uint32_t* cigar = nullptr; uint64_t* seq_off = nullptr;
     uint8_t* seq4 = nullptr; uint8_t* qual = nullptr;
+    uint8_t* qcode = nullptr;                        // 2-bit quality codes (lvc_batch::qual_bits == 2) when the file qualifies
+    uint8_t qdict[4] = {0, 0, 0, 0};
     bool pinned = false;
     uint64_t overlap_pairs = 0, overlap_bases = 0;   // mate pairs / quality bytes rewritten by the overlap model
     std::vector<std::pair<void*, size_t>> allocs;    // (pointer, capacity)
@@ -298,6 +300,18 @@ static std::string pack(lvc_reads* r, const std::vector<Rec>& recs, int min_mapq
     if (rc) return fail("admission failed (%d)", rc);
     for (size_t i = 0; i < n; ++i) r->keep[i] |= adm[i];
     timer.mark("keep bits");
+    // instrument-binned qualities (at most four distinct values among the admitted reads, after the mate-overlap
+    // rewrite): the batch also gets the 2-bit code form, which is what lvc_reads_batch hands out (half the payload
+    // bytes over PCIe).  LVC_QUALITY_CODES=0 keeps the byte form only.
+    const char* qc_env = getenv("LVC_QUALITY_CODES");
+    if (n && r->n_qual && !(qc_env && atoi(qc_env) == 0)) {
+        uint8_t* codes = (uint8_t*)host_alloc(r, (size_t)(r->n_qual / 4) + 64);
+        if (codes) {
+            const int nd = lvc::pack_quality_codes(r->qual, r->n_qual, r->n, r->keep, r->seq_off, r->cigar_off, r->cigar, n_threads, r->qdict, codes);
+            if (nd > 0) { memset(codes + (r->n_qual + 3) / 4, 0, 64 - 4); r->qcode = codes; }
+        }
+        timer.mark("quality codes");
+    }
     return "";
 }
 
@@ -636,12 +650,19 @@ int lvc_reads_overlap_stats(const lvc_reads* r, uint64_t* n_pairs, uint64_t* n_b
     return LVC_OK;
 }
 
-int lvc_reads_batch(const lvc_reads* r, lvc_batch* b) {
+int lvc_reads_batch_bytes(const lvc_reads* r, lvc_batch* b) {
     if (!r || !b) return LVC_EINVAL;
-    b->n_reads = r->n; b->reserved = 0; b->n_cigar_ops = r->n_cigar; b->n_qual_bytes = r->n_qual;
+    b->n_reads = r->n; b->qual_bits = 8; b->reserved = 0; b->n_cigar_ops = r->n_cigar; b->n_qual_bytes = r->n_qual;
     b->pos = r->pos; b->flag = r->flag; b->mapq = r->mapq; b->keep = r->keep; b->cigar_off = r->cigar_off;
     b->cigar = r->cigar; b->seq_off = r->seq_off; b->seq4 = r->seq4; b->qual = r->qual;
+    memset(b->qual_dict, 0, 4);
     return LVC_OK;
+}
+
+int lvc_reads_batch(const lvc_reads* r, lvc_batch* b) {
+    const int rc = lvc_reads_batch_bytes(r, b);
+    if (rc == LVC_OK && r->qcode) { b->qual_bits = 2; b->qual = r->qcode; memcpy(b->qual_dict, r->qdict, 4); }
+    return rc;
 }
 
 int lvc_reads_info(const lvc_reads* r, char* contig_name, int name_cap, int64_t* contig_len, int* n_contigs, int* pinned) {

@@ -20,6 +20,7 @@
 #include "deposit_ont.cuh"
 #include "genotype.cuh"
 #include "overlap.hpp"
+#include "qcode.hpp"
 
 // NVTX range around the host side of an entry point (ingest / push / genotype / exchange show up
 // as named ranges in Nsight Systems).
@@ -56,6 +57,7 @@ struct lvc_handle {
     int sm_count = 148;
     uint64_t launches = 0;
     bool zero_copy_ok = true;                // read page-locked caller payload in place (LVC_ZERO_COPY=0 disables)
+    bool zc_headers = false;                 // also read the per-read arrays (all but `keep`) in place (LVC_ZC_HEADERS=1)
     uint64_t h2d_payload_bytes = 0;          // payload bytes actually copied by lvc_push_batch (cumulative)
     uint64_t ordinal = 0;
     int qprim = 255;                         // primary quality of the current batch (tiled kernel)
@@ -217,6 +219,7 @@ int lvc_create(lvc_handle** out, int device, int64_t ref_len, const uint8_t* ref
     h->min_mq = min_mapping_quality;
     for (int k = 0; k < kMaxKeys; ++k) h->lut[k] = kNoPlane;
     if (const char* zc = getenv("LVC_ZERO_COPY")) h->zero_copy_ok = atoi(zc) != 0;
+    if (const char* zh = getenv("LVC_ZC_HEADERS")) h->zc_headers = atoi(zh) != 0;
     if (const char* gl = getenv("LVC_GENO_LPP")) { const int v = atoi(gl); if (v == 1 || v == 2 || v == 4 || v == 8) h->geno_lpp_wide = v; }
     if (const char* li = getenv("LVC_LONG_IMPL")) { const int v = atoi(li); if (v == 3 || v == 6) h->long_impl = v; }
     if (const char* ti = getenv("LVC_TILE_IMPL")) { const int v = atoi(ti); if (v == 2 || v == 4 || v == 5) h->tile_impl = v; }
@@ -268,6 +271,10 @@ int lvc_create(lvc_handle** out, int device, int64_t ref_len, const uint8_t* ref
         CU(cudaFuncSetAttribute(k_deposit_tile5<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTile5SmemBytes));
         CU(cudaFuncSetAttribute(k_deposit_tile5<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTile5SmemBytes));
         CU(cudaFuncSetAttribute(k_deposit_tile5<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTile5SmemBytes));
+        CU(cudaFuncSetAttribute(k_deposit_tile5<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTile5SmemBytes));
+        CU(cudaFuncSetAttribute(k_deposit_tile5<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTile5SmemBytes));
+        CU(cudaFuncSetAttribute(k_deposit_tile5<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTile5SmemBytes));
+        CU(cudaFuncSetAttribute(k_deposit_tile5<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTile5SmemBytes));
         CU(cudaStreamSynchronize(h->stream));
         return LVC_OK;
     };
@@ -376,6 +383,14 @@ int lvc_admit_overlaps(uint32_t n, const int32_t* pos, const uint16_t* flag, con
                                    min_mq, max_depth, overlap_model, keep, n_pairs, n_bases);
 }
 
+int lvc_pack_quality_codes(const uint8_t* qual, uint64_t n_qual_bytes, uint32_t n_reads, const uint8_t* keep,
+                           const uint64_t* seq_off, const uint32_t* cigar_off, const uint32_t* cigar, int n_threads,
+                           uint8_t dict_out[4], uint8_t* codes_out) {
+    if ((n_qual_bytes && !qual) || !dict_out || !codes_out) return LVC_EINVAL;
+    if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    return lvc::pack_quality_codes(qual, n_qual_bytes, n_reads, keep, seq_off, cigar_off, cigar, n_threads, dict_out, codes_out);
+}
+
 // ------------------------------------------------------------------------------------------------
 // deposit
 // ------------------------------------------------------------------------------------------------
@@ -403,8 +418,28 @@ static int launch_deposit(lvc_handle* h, const BatchView& bv, int replay, uint64
         impl = (impl == 5 || (h->impl == 0 && !long_reads)) ? 5 : (long_reads ? 3 : 1);
     }
     // the tiled kernels' byte arithmetic assumes a primary quality and a threshold below 128
-    const bool tile_ok = h->qprim < 128 && h->min_bq <= 128 && h->lut[h->qprim] != kNoPlane;
-    if (impl == 6 && !replay && h->G < (1ll << 30)) {
+    bool tile_ok = h->qprim < 128 && h->min_bq <= 128 && h->lut[h->qprim] != kNoPlane;
+    // quality-code batches (lvc_batch::qual_bits == 2): the generation-5 tiled kernel, or the any-record kernel
+    const bool qc = bv.qbits == 2u;
+    uint32_t qc_pcode = 4, qc_cold = 0;
+    if (qc) {
+        if (h->impl != 0 && h->impl != 1 && h->impl != 5)
+            return fail(h, LVC_EINVAL, "quality-code batches run on impl 0, 1 or 5 (selected: %d)", h->impl);
+        for (uint32_t c = 0; c < 4; ++c) {
+            const int v = (int)((bv.qdict >> (8 * c)) & 255u);
+            if (v == h->qprim && qc_pcode == 4) qc_pcode = c;
+        }
+        for (uint32_t c = 0; c < 4; ++c)
+            if (c != qc_pcode && (int)((bv.qdict >> (8 * c)) & 255u) >= h->min_bq) qc_cold |= 1u << c;
+        tile_ok = tile_ok && qc_pcode < 4;
+        impl = (impl == 1 || replay || !tile_ok) ? 1 : 5;
+    }
+    if (qc && impl == 1) {
+        { KernelTimer t(h, 1);
+          if (h->peer_ranks > 1) k_deposit_general<true><<<(n + 127) / 128, 128, 0, h->stream>>>(bv, tv, dp, n);
+          else k_deposit_general<false><<<(n + 127) / 128, 128, 0, h->stream>>>(bv, tv, dp, n); }
+        h->launches++;
+    } else if (impl == 6 && !replay && h->G < (1ll << 30)) {
         // reads per CTA: as many as keep the CTA's unit list (16 query bases per unit) about three quarters full
         const uint64_t avg_q = std::max<uint64_t>(n_qual / n, 1);
         const uint32_t rpc = (uint32_t)std::min<uint64_t>(kOntMaxReads, std::max<uint64_t>(1, (uint64_t)kOntMaxUnits * 12 / avg_q));
@@ -438,6 +473,8 @@ static int launch_deposit(lvc_handle* h, const BatchView& bv, int replay, uint64
         TileParams tp = make_tile_params(n, h->sm_count);
         tp.qprim = (uint32_t)h->qprim;
         tp.prim_plane = h->lut[h->qprim];
+        tp.qc_pcode = qc_pcode & 3u;
+        tp.qc_cold = qc_cold;
         { KernelTimer t(h, 0);
           if (impl == 4 || impl == 5) {
               // programmatic stream serialization: the chunk headers are read (and dead chunks retire) while the
@@ -453,9 +490,11 @@ static int launch_deposit(lvc_handle* h, const BatchView& bv, int replay, uint64
               cfg.attrs = at; cfg.numAttrs = 1;
               if (impl == 5) {
                   using T5 = decltype(&k_deposit_tile5<false, false>);
-                  static const T5 t5[2][2] = {{k_deposit_tile5<false, false>, k_deposit_tile5<false, true>},
-                                              {k_deposit_tile5<true, false>, k_deposit_tile5<true, true>}};
-                  CU(cudaLaunchKernelEx(&cfg, t5[h->min_bq <= 0 ? 1 : 0][h->peer_ranks > 1 ? 1 : 0], bv, tv, dp, tp));
+                  static const T5 t5[2][2][2] = {{{k_deposit_tile5<false, false>, k_deposit_tile5<false, false, true>},
+                                                  {k_deposit_tile5<false, true>, k_deposit_tile5<false, true, true>}},
+                                                 {{k_deposit_tile5<true, false>, k_deposit_tile5<true, false, true>},
+                                                  {k_deposit_tile5<true, true>, k_deposit_tile5<true, true, true>}}};
+                  CU(cudaLaunchKernelEx(&cfg, t5[h->min_bq <= 0 ? 1 : 0][h->peer_ranks > 1 ? 1 : 0][qc ? 1 : 0], bv, tv, dp, tp));
               } else if (h->min_bq <= 0) CU(cudaLaunchKernelEx(&cfg, k_deposit_tile4<true>, bv, tv, dp, tp));
               else CU(cudaLaunchKernelEx(&cfg, k_deposit_tile4<false>, bv, tv, dp, tp));
           } else if (h->min_bq <= 0)
@@ -493,7 +532,7 @@ static int deposit_with_replay(lvc_handle* h, const BatchView& bv, uint64_t n_ci
                                   !((f & 1u) && !(f & 2u));
                 if (live) { lo = std::min<uint64_t>(lo, account->seq_off[i]); hi = std::max<uint64_t>(hi, account->seq_off[i + 1]); }
             }
-            if (hi > lo) { const uint64_t q = ((hi + 15) & ~15ull) - (lo & ~15ull); moved += q + q / 2; }
+            if (hi > lo) { const uint64_t q = ((hi + 15) & ~15ull) - (lo & ~15ull); moved += (account->qual_bits == 2u ? q / 4 : q) + q / 2; }
         }
         h->h2d_payload_bytes += moved;
     }
@@ -523,8 +562,14 @@ static int deposit_with_replay(lvc_handle* h, const BatchView& bv, uint64_t n_ci
 
 // Sample qualities: pre-allocate planes for the passing values seen (so the first pass rarely needs a
 // replay) and pick the most frequent passing value as the tiled kernel's register-path quality.
-static int premap_from_sample(lvc_handle* h, const uint8_t* q, uint64_t n, uint64_t stride) {
+// `dict` != nullptr: the sample holds 2-bit quality codes (four per byte) of a quality-code batch
+static int premap_from_sample(lvc_handle* h, const uint8_t* q, uint64_t n, uint64_t stride, const uint8_t* dict = nullptr) {
     uint32_t hist[256] = {0};
+    if (dict) {
+        uint32_t ch[4] = {0, 0, 0, 0};
+        for (uint64_t i = 0; i < n; i += stride) { const uint32_t v = q[i]; ch[v & 3]++; ch[(v >> 2) & 3]++; ch[(v >> 4) & 3]++; ch[v >> 6]++; }
+        for (int c = 0; c < 4; ++c) hist[dict[c]] += ch[c];
+    } else
     for (uint64_t i = 0; i < n; i += stride) hist[q[i]]++;
     int best = 255;
     uint32_t best_n = 0;
@@ -546,12 +591,14 @@ static int premap_host(lvc_handle* h, const lvc_batch* b) {
     // The first batch of a handle pays that (it creates the planes); later batches only re-elect the primary
     // quality from 2048 probes, and a quality never seen before still gets its plane through the replay path.
     const uint64_t probes = h->planes.empty() ? 32768 : 2048;
+    if (b->qual_bits == 2u) return premap_from_sample(h, b->qual, nq / 4, std::max<uint64_t>(1, nq / 4 / probes), b->qual_dict);
     return premap_from_sample(h, b->qual, nq, std::max<uint64_t>(1, nq / probes));
 }
 
 // device-resident batch: gather a strided sample (kSampleRows rows of 64 bytes) with one 2-D copy
 static int premap_device(lvc_handle* h, const lvc_batch* b) {
-    const uint64_t nq = b->n_qual_bytes;
+    const bool qc = b->qual_bits == 2u;
+    const uint64_t nq = qc ? b->n_qual_bytes / 4 : b->n_qual_bytes;       // bytes of the quality array
     if (nq == 0) { h->qprim = 255; return LVC_OK; }
     if (!h->h_sample) CU(cudaHostAlloc(&h->h_sample, kSampleRows * kSampleRowBytes, cudaHostAllocDefault));
     uint64_t rows = kSampleRows, width = kSampleRowBytes;
@@ -559,7 +606,7 @@ static int premap_device(lvc_handle* h, const lvc_batch* b) {
     const uint64_t pitch = rows > 1 ? nq / rows : width;
     CU(cudaMemcpy2DAsync(h->h_sample, width, b->qual, pitch, width, rows, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    return premap_from_sample(h, h->h_sample, rows * width, 1);
+    return premap_from_sample(h, h->h_sample, rows * width, 1, qc ? b->qual_dict : nullptr);
 }
 
 static int validate_batch(lvc_handle* h, const lvc_batch* b) {
@@ -567,7 +614,16 @@ static int validate_batch(lvc_handle* h, const lvc_batch* b) {
     if (b->n_reads == 0) return LVC_OK;
     if (!b->pos || !b->flag || !b->mapq || !b->keep || !b->cigar_off || !b->cigar || !b->seq_off || !b->seq4 || !b->qual)
         return fail(h, LVC_EINVAL, "lvc_batch has a null array");
+    if (b->qual_bits != 0 && b->qual_bits != 8 && b->qual_bits != 2)
+        return fail(h, LVC_EINVAL, "lvc_batch.qual_bits must be 0 / 8 (phred bytes) or 2 (codes into qual_dict), not %u", b->qual_bits);
     return LVC_OK;
+}
+
+// the batch's quality form as the kernels see it
+static void set_quality_form(BatchView& bv, const lvc_batch* b) {
+    bv.qbits = b->qual_bits == 2u ? 2u : 0u;
+    bv.qdict = (uint32_t)b->qual_dict[0] | ((uint32_t)b->qual_dict[1] << 8) | ((uint32_t)b->qual_dict[2] << 16) |
+               ((uint32_t)b->qual_dict[3] << 24);
 }
 
 int lvc_push_batch(lvc_handle* h, const lvc_batch* b) {
@@ -584,9 +640,26 @@ int lvc_push_batch(lvc_handle* h, const lvc_batch* b) {
         {&h->b_mapq, b->mapq, n, true},             {&h->b_keep, b->keep, n, true},
         {&h->b_coff, b->cigar_off, (n + 1) * 4, true}, {&h->b_cig, b->cigar, (size_t)b->n_cigar_ops * 4, true},
         {&h->b_soff, b->seq_off, (n + 1) * 8, true},   {&h->b_seq, b->seq4, (size_t)(b->n_qual_bytes + 1) / 2, false},
-        {&h->b_qual, b->qual, (size_t)b->n_qual_bytes, false},
+        {&h->b_qual, b->qual, (size_t)(b->qual_bits == 2u ? (b->n_qual_bytes + 3) / 4 : b->n_qual_bytes), false},
     };
-    for (auto& c : cp) {
+    const bool qc = b->qual_bits == 2u;
+    // LVC_ZC_HEADERS=1: the per-read arrays other than `keep` are read in place too when they are page-locked -- a chunk
+    // whose reads were all dropped leaves after its `keep` bytes (copied in bulk) and never asks for the rest
+    const void* hdr_alias[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool hdr_in_place = false;
+    if (h->zero_copy_ok && h->zc_headers) {
+        hdr_in_place = true;
+        for (int k = 0; k < 7 && hdr_in_place; ++k) {
+            if (k == 3) continue;                                       // keep: always copied
+            cudaPointerAttributes a;
+            if (cudaPointerGetAttributes(&a, cp[k].s) == cudaSuccess && a.type == cudaMemoryTypeHost && a.devicePointer)
+                hdr_alias[k] = a.devicePointer;
+            else { cudaGetLastError(); hdr_in_place = false; }
+        }
+    }
+    for (int k = 0; k < 9; ++k) {
+        auto& c = cp[k];
+        if (hdr_in_place && k < 7 && k != 3) continue;
         rc = ensure(h, *c.d, c.bytes + 64);     // +64: the tiled kernel reads whole 16-byte groups
         if (rc) return rc;
         if (c.bytes && c.copy) CU(cudaMemcpyAsync(c.d->p, c.s, c.bytes, cudaMemcpyHostToDevice, h->stream));
@@ -621,10 +694,12 @@ int lvc_push_batch(lvc_handle* h, const lvc_batch* b) {
             const size_t end = last_live + 1;
             const uint64_t q0 = b->seq_off[i] & ~15ull, q1 = std::min<uint64_t>((b->seq_off[end] + 15) & ~15ull, b->n_qual_bytes);
             if (q1 > q0) {
+                if (qc) CU(cudaMemcpyAsync((uint8_t*)h->b_qual.p + q0 / 4, b->qual + q0 / 4, (q1 - q0 + 3) / 4, cudaMemcpyHostToDevice, h->stream));
+                else
                 CU(cudaMemcpyAsync((uint8_t*)h->b_qual.p + q0, b->qual + q0, q1 - q0, cudaMemcpyHostToDevice, h->stream));
                 const uint64_t s0 = q0 >> 1, s1 = std::min<uint64_t>((q1 + 1) >> 1, (b->n_qual_bytes + 1) >> 1);
                 CU(cudaMemcpyAsync((uint8_t*)h->b_seq.p + s0, b->seq4 + s0, s1 - s0, cudaMemcpyHostToDevice, h->stream));
-                h->h2d_payload_bytes += (q1 - q0) + (s1 - s0);
+                h->h2d_payload_bytes += (qc ? (q1 - q0 + 3) / 4 : (q1 - q0)) + (s1 - s0);
             }
             i = end;
         }
@@ -637,7 +712,14 @@ int lvc_push_batch(lvc_handle* h, const lvc_batch* b) {
     bv.mapq = (const uint8_t*)h->b_mapq.p;     bv.keep = (const uint8_t*)h->b_keep.p;
     bv.cigar_off = (const uint32_t*)h->b_coff.p; bv.cigar = (const uint32_t*)h->b_cig.p;
     bv.seq_off = (const uint64_t*)h->b_soff.p; bv.seq4 = dev_seq;
+    if (hdr_in_place) {
+        bv.pos = (const int32_t*)hdr_alias[0]; bv.flag = (const uint16_t*)hdr_alias[1]; bv.mapq = (const uint8_t*)hdr_alias[2];
+        bv.cigar_off = (const uint32_t*)hdr_alias[4]; bv.cigar = (const uint32_t*)hdr_alias[5];
+        bv.seq_off = (const uint64_t*)hdr_alias[6];
+        bv.hdr_lazy = 1;
+    }
     bv.qual = dev_qual;
+    set_quality_form(bv, b);
     return deposit_with_replay(h, bv, b->n_cigar_ops, b->n_qual_bytes, zero_copy ? b : nullptr);
 }
 
@@ -651,6 +733,7 @@ int lvc_push_batch_device(lvc_handle* h, const lvc_batch* b) {
     bv.n_reads = b->n_reads;
     bv.pos = b->pos; bv.flag = b->flag; bv.mapq = b->mapq; bv.keep = b->keep;
     bv.cigar_off = b->cigar_off; bv.cigar = b->cigar; bv.seq_off = b->seq_off; bv.seq4 = b->seq4; bv.qual = b->qual;
+    set_quality_form(bv, b);
     rc = premap_device(h, b);
     if (rc) return rc;
     return deposit_with_replay(h, bv, b->n_cigar_ops, b->n_qual_bytes);
@@ -668,6 +751,7 @@ int lvc_push_batch_device_async(lvc_handle* h, const lvc_batch* b) {
     bv.n_reads = b->n_reads;
     bv.pos = b->pos; bv.flag = b->flag; bv.mapq = b->mapq; bv.keep = b->keep;
     bv.cigar_off = b->cigar_off; bv.cigar = b->cigar; bv.seq_off = b->seq_off; bv.seq4 = b->seq4; bv.qual = b->qual;
+    set_quality_form(bv, b);
     if (h->qprim == 255) {
         // the first push of this handle is an asynchronous one (peer tables: nothing may be deposited before the tables
         // are mapped): elect the tiled kernel's primary quality now (one small copy + stream synchronisation)

@@ -68,7 +68,20 @@ struct BatchView {
     const uint64_t* seq_off;
     const uint8_t* seq4;
     const uint8_t* qual;
+    uint32_t qbits = 0;           // 2: `qual` holds 2-bit codes (four bases per byte, low bits first), phred = byte `code` of qdict
+    uint32_t qdict = 0;           // lvc_batch::qual_dict, code 0 in the low byte
+    uint32_t hdr_lazy = 0;        // the per-read arrays other than `keep` sit in host memory (read in place over PCIe): a
+                                  // chunk asks for them only after its `keep` bytes say that some read is admitted
 };
+
+// quality of the base with quality index x (= seq_off[read] + query index), either batch form
+__device__ __forceinline__ uint32_t batch_qual(const BatchView& b, uint64_t x) {
+    if (b.qbits == 2u) {
+        const uint32_t c = ((uint32_t)b.qual[x >> 2] >> (2u * ((uint32_t)x & 3u))) & 3u;
+        return (b.qdict >> (8u * c)) & 255u;
+    }
+    return b.qual[x];
+}
 
 struct DepositParams {
     int min_bq;

@@ -33,10 +33,10 @@ class LvcError(RuntimeError):
 
 
 class Batch(C.Structure):
-    _fields_ = [("n_reads", C.c_uint32), ("reserved", C.c_uint32), ("n_cigar_ops", C.c_uint64),
+    _fields_ = [("n_reads", C.c_uint32), ("qual_bits", C.c_uint32), ("n_cigar_ops", C.c_uint64),
                 ("n_qual_bytes", C.c_uint64), ("pos", C.c_void_p), ("flag", C.c_void_p), ("mapq", C.c_void_p),
                 ("keep", C.c_void_p), ("cigar_off", C.c_void_p), ("cigar", C.c_void_p), ("seq_off", C.c_void_p),
-                ("seq4", C.c_void_p), ("qual", C.c_void_p)]
+                ("seq4", C.c_void_p), ("qual", C.c_void_p), ("qual_dict", C.c_uint8 * 4), ("reserved", C.c_uint32)]
 
 
 class Candidate(C.Structure):
@@ -72,6 +72,9 @@ SIGNATURES = [
                                          C.c_char_p, C.c_int]),
     ("lvc_reads_overlap_stats", C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     ("lvc_reads_batch", C.c_int, [C.c_void_p, C.POINTER(Batch)]),
+    ("lvc_reads_batch_bytes", C.c_int, [C.c_void_p, C.POINTER(Batch)]),
+    ("lvc_pack_quality_codes", C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_int, C.c_void_p, C.c_void_p]),
     ("lvc_reads_info", C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int),
                                  C.POINTER(C.c_int)]),
     ("lvc_reads_free", None, [C.c_void_p]),
@@ -203,6 +206,33 @@ def admit_overlaps(pos, flag, mapq, cigar_off, cigar, seq_off, seq4, qual, names
     return keep, int(pairs.value), int(bases.value)
 
 
+def pack_quality_codes(qual: np.ndarray, n_qual: int, keep: Optional[np.ndarray] = None,
+                       seq_off: Optional[np.ndarray] = None, cigar_off: Optional[np.ndarray] = None,
+                       cigar: Optional[np.ndarray] = None, n_threads: int = 0):
+    """lvc_pack_quality_codes: (codes uint8 [(n_qual+3)//4 + 64 slack], dict bytes[4]) or None if the qualities (of the
+    l_qseq bases of the reads with keep bit0 set, when the per-read arrays are given) take more than four distinct
+    values."""
+    lib = load_library()
+    qual = np.ascontiguousarray(qual, dtype=np.uint8)
+    codes = np.zeros((n_qual + 3) // 4 + 64, dtype=np.uint8)
+    d = np.zeros(4, dtype=np.uint8)
+    n_reads = 0
+    if keep is not None and seq_off is not None and cigar_off is not None and cigar is not None:
+        keep = np.ascontiguousarray(keep, dtype=np.uint8)
+        seq_off = np.ascontiguousarray(seq_off, dtype=np.uint64)
+        cigar_off = np.ascontiguousarray(cigar_off, dtype=np.uint32)
+        cigar = np.ascontiguousarray(cigar, dtype=np.uint32)
+        n_reads = len(keep)
+    rc = lib.lvc_pack_quality_codes(_ptr(qual), int(n_qual), int(n_reads), _ptr(keep) if n_reads else None,
+                                    _ptr(seq_off) if n_reads else None, _ptr(cigar_off) if n_reads else None,
+                                    _ptr(cigar) if n_reads else None, int(n_threads), _ptr(d), _ptr(codes))
+    if rc < 0:
+        raise LvcError(rc, "lvc_pack_quality_codes failed")
+    if rc == 0:
+        return None
+    return codes, bytes(d)
+
+
 class NativeReads:
     """Alignments of one contig read and packed by the native ingest (lvc_read_alignments)."""
 
@@ -224,9 +254,12 @@ class NativeReads:
                 raise UnsupportedInput(msg)
             raise LvcError(rc, msg)
         self.r = r
-        self.batch = Batch()
+        self.batch = Batch()                                   # what process_bam pushes: 2-bit quality codes if the file qualifies
         self.lib.lvc_reads_batch(self.r, C.byref(self.batch))
         self.batch._keepalive = self
+        self.batch_bytes = Batch()                             # always one phred byte per base
+        self.lib.lvc_reads_batch_bytes(self.r, C.byref(self.batch_bytes))
+        self.batch_bytes._keepalive = self
         name = C.create_string_buffer(256)
         ln, nc, pinned = C.c_int64(0), C.c_int(0), C.c_int(0)
         self.lib.lvc_reads_info(self.r, name, 256, C.byref(ln), C.byref(nc), C.byref(pinned))
@@ -242,7 +275,7 @@ class NativeReads:
     def as_readbatch(self):
         """numpy views (no copy) in the layout of packing.ReadBatch; valid while this object lives"""
         from .packing import ReadBatch
-        b = self.batch
+        b = self.batch_bytes
         n = b.n_reads
 
         def view(ptr, dtype, count):
@@ -254,6 +287,9 @@ class NativeReads:
                        view(b.keep, np.uint8, n), view(b.cigar_off, np.uint32, n + 1),
                        view(b.cigar, np.uint32, max(int(b.n_cigar_ops), 1)), view(b.seq_off, np.uint64, n + 1),
                        view(b.seq4, np.uint8, int(b.n_qual_bytes) // 2 + 64), view(b.qual, np.uint8, int(b.n_qual_bytes) + 64))
+        if self.batch.qual_bits == 2:
+            rb.qcode = view(self.batch.qual, np.uint8, int(b.n_qual_bytes) // 4 + 16)
+            rb.qdict = bytes(self.batch.qual_dict)
         rb._keepalive = self
         return rb
 
@@ -353,9 +389,15 @@ class Handle:
 
     # ---- deposit
     @staticmethod
-    def make_batch(n_reads, n_cigar, n_qual, pos, flag, mapq, keep, cigar_off, cigar, seq_off, seq4, qual) -> Batch:
-        return Batch(int(n_reads), 0, int(n_cigar), int(n_qual), _ptr(pos), _ptr(flag), _ptr(mapq), _ptr(keep),
-                     _ptr(cigar_off), _ptr(cigar), _ptr(seq_off), _ptr(seq4), _ptr(qual))
+    def make_batch(n_reads, n_cigar, n_qual, pos, flag, mapq, keep, cigar_off, cigar, seq_off, seq4, qual,
+                   qual_dict=None) -> Batch:
+        """`qual_dict` (4 phred values): `qual` holds 2-bit quality codes (lvc_batch::qual_bits == 2), else phred bytes"""
+        b = Batch(int(n_reads), 2 if qual_dict is not None else 0, int(n_cigar), int(n_qual), _ptr(pos), _ptr(flag),
+                  _ptr(mapq), _ptr(keep), _ptr(cigar_off), _ptr(cigar), _ptr(seq_off), _ptr(seq4), _ptr(qual))
+        if qual_dict is not None:
+            for k in range(4):
+                b.qual_dict[k] = int(qual_dict[k])
+        return b
 
     def push_batch(self, batch: Batch):
         self._check(self.lib.lvc_push_batch(self.h, C.byref(batch)))

@@ -42,6 +42,10 @@ class ReadBatch:
     seq_off: np.ndarray    # uint64 [n+1]  even byte offsets into qual; seq4 offset = seq_off/2
     seq4: np.ndarray       # uint8  [seq_off[n]/2 (+pad)]
     qual: np.ndarray       # uint8  [seq_off[n] (+pad)]
+    # optional 2-bit quality-code form (include/lvc.h, qual_bits == 2): when set, as_capi() ships the codes instead of
+    # the phred bytes; `qual` stays for the host side (oracle, BAM writer, tests)
+    qcode: Optional[np.ndarray] = None   # uint8 [seq_off[n]/4 (+pad)]
+    qdict: Optional[bytes] = None        # 4 phred values
 
     @property
     def n_reads(self) -> int:
@@ -68,10 +72,40 @@ class ReadBatch:
         return int(20 * self.n_reads + 4 * self.n_cigar + ((lq + 1) // 2).sum() + lq.sum() + 52 * ref_len)
 
     def as_capi(self) -> capi.Batch:
-        b = capi.Handle.make_batch(self.n_reads, self.n_cigar, self.n_qual, self.pos, self.flag, self.mapq,
-                                   self.keep, self.cigar_off, self.cigar, self.seq_off, self.seq4, self.qual)
+        if self.qcode is not None:
+            b = capi.Handle.make_batch(self.n_reads, self.n_cigar, self.n_qual, self.pos, self.flag, self.mapq,
+                                       self.keep, self.cigar_off, self.cigar, self.seq_off, self.seq4, self.qcode,
+                                       qual_dict=self.qdict)
+        else:
+            b = capi.Handle.make_batch(self.n_reads, self.n_cigar, self.n_qual, self.pos, self.flag, self.mapq,
+                                       self.keep, self.cigar_off, self.cigar, self.seq_off, self.seq4, self.qual)
         b._keepalive = self         # the struct only carries raw pointers: keep the arrays alive with it
         return b
+
+    def with_quality_codes(self, n_threads: int = 0) -> "ReadBatch":
+        """the same batch carrying 2-bit quality codes (lvc_pack_quality_codes) if the qualities of its admitted reads
+        take at most four distinct values; otherwise the batch itself.  Arrays are shared, nothing is copied."""
+        if self.qcode is not None or self.n_reads == 0 or self.n_qual == 0:
+            return self
+        got = capi.pack_quality_codes(self.qual, self.n_qual, self.keep, self.seq_off, self.cigar_off, self.cigar, n_threads)
+        if got is None:
+            return self
+        out = ReadBatch(self.pos, self.flag, self.mapq, self.keep, self.cigar_off, self.cigar, self.seq_off, self.seq4,
+                        self.qual, got[0], got[1])
+        for extra in ("overlap_pairs", "overlap_bases", "_keepalive", "_pins"):
+            if hasattr(self, extra):
+                setattr(out, extra, getattr(self, extra))
+        return out
+
+    def without_quality_codes(self) -> "ReadBatch":
+        if self.qcode is None:
+            return self
+        out = ReadBatch(self.pos, self.flag, self.mapq, self.keep, self.cigar_off, self.cigar, self.seq_off, self.seq4,
+                        self.qual)
+        for extra in ("overlap_pairs", "overlap_bases", "_keepalive", "_pins"):
+            if hasattr(self, extra):
+                setattr(out, extra, getattr(self, extra))
+        return out
 
     def slice(self, a: int, b: int) -> "ReadBatch":
         """reads [a, b) as a new batch sharing the payload arrays (offsets rebased)."""
@@ -224,9 +258,15 @@ class _Pinned:
 
 
 def pin_batch(b: ReadBatch) -> ReadBatch:
-    """Copy a batch into page-locked host memory so lvc_push_batch's H2D copies run at full PCIe speed."""
-    pins = [_Pinned(getattr(b, f)) for f in ("pos", "flag", "mapq", "keep", "cigar_off", "cigar", "seq_off", "seq4",
-                                              "qual")]
-    out = ReadBatch(*[p.array for p in pins])
+    """Copy a batch into page-locked host memory so lvc_push_batch's H2D copies run at full PCIe speed.  A batch that
+    carries quality codes gets those pinned (they are what is shipped); its phred bytes stay where they are."""
+    fields = ["pos", "flag", "mapq", "keep", "cigar_off", "cigar", "seq_off", "seq4"]
+    pins = [_Pinned(getattr(b, f)) for f in fields]
+    if b.qcode is not None:
+        pins.append(_Pinned(b.qcode))
+        out = ReadBatch(*[p.array for p in pins[:8]], b.qual, pins[8].array, b.qdict)
+    else:
+        pins.append(_Pinned(b.qual))
+        out = ReadBatch(*[p.array for p in pins])
     out._pins = pins            # keep the allocations alive as long as the batch
     return out

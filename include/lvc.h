@@ -51,10 +51,20 @@ typedef struct lvc_handle lvc_handle;
  *                 is A, C, G or T (set ONLY if true; reads without it take the general kernel).
  *   The payload arrays seq4 / qual must be readable for 16 bytes past their end (TMA stages whole
  *   16-byte groups) and 16-byte aligned at their start.
+ *
+ *   Quality codes (qual_bits = 2) [EXT]: instrument-binned base qualities (NovaSeq RTA3: 2, 12, 23, 37) take four
+ *   values, so a batch whose qualities take at most four distinct values may carry them as 2-bit CODES, four bases
+ *   per byte: the base with quality index x (x = seq_off[i] + k, the index it would have in the byte array) has its
+ *   code in bits 2*(x & 3) of qual[x >> 2], and its phred value is qual_dict[code].  Offsets, seq4 and n_qual_bytes
+ *   keep their meaning (`qual` then holds n_qual_bytes / 4 bytes); the tables, records and checkpoints that result
+ *   are identical to those of the byte form.  The payload that crosses PCIe drops from 1.5 to 0.75 bytes per base.
+ *   lvc_read_alignments produces this form by itself when a file qualifies (lvc_reads_batch; lvc_reads_batch_bytes
+ *   always gives the byte form); lvc_pack_quality_codes converts a byte array.  Code batches run on the generation-5
+ *   tiled kernel and the any-record kernel (impl 0, 1 or 5; other selections are refused with LVC_EINVAL).
  */
 typedef struct lvc_batch {
     uint32_t n_reads;
-    uint32_t reserved;
+    uint32_t qual_bits;    /* 0 or 8: one phred byte per base; 2: 2-bit codes into qual_dict */
     uint64_t n_cigar_ops;  /* == cigar_off[n_reads] */
     uint64_t n_qual_bytes; /* == seq_off[n_reads]   */
     const int32_t* pos;    /* [n_reads] 0-based leftmost reference position */
@@ -65,8 +75,20 @@ typedef struct lvc_batch {
     const uint32_t* cigar;     /* [n_cigar_ops] */
     const uint64_t* seq_off;   /* [n_reads+1] */
     const uint8_t* seq4;       /* [n_qual_bytes/2] */
-    const uint8_t* qual;       /* [n_qual_bytes]   */
+    const uint8_t* qual;       /* [n_qual_bytes], or [n_qual_bytes/4] codes when qual_bits == 2 */
+    uint8_t qual_dict[4];      /* qual_bits == 2: phred value of code 0..3 (unused entries 0) */
+    uint32_t reserved;
 } lvc_batch;
+
+/* Byte qualities -> 2-bit codes (no GPU needed).  Returns the number of distinct values found (1..4) after writing
+ * dict_out[4] (ascending, unused entries 0) and codes_out[(n_qual_bytes + 3) / 4]; returns 0 and writes nothing useful
+ * if the array holds more than four distinct values (the batch stays in the byte form); LVC_EINVAL on null arguments.
+ * n_reads / keep / seq_off / cigar_off / cigar (optional, all or none): only the l_qseq qualities of the reads with keep
+ * bit0 set decide -- the payload of reads the admission dropped is never read by any kernel, and the pad byte of an
+ * odd-length read is not a quality.  Bytes that do not decide get code 0. */
+int lvc_pack_quality_codes(const uint8_t* qual, uint64_t n_qual_bytes, uint32_t n_reads, const uint8_t* keep,
+                           const uint64_t* seq_off, const uint32_t* cigar_off, const uint32_t* cigar, int n_threads,
+                           uint8_t dict_out[4], uint8_t* codes_out);
 
 /* One (position, allele) that passed the genotype-stage filters; the host finalises log10/round/
  * formatting with the host libm so the text matches the reference. */
@@ -145,7 +167,9 @@ int lvc_read_alignments(const char* path, const char* contig, int min_mapping_qu
 int lvc_read_alignments_ex(const char* path, const char* contig, int min_mapping_quality, int max_depth, int n_threads,
                            int overlap_model, lvc_reads** out, char* errbuf, int errlen);
 int lvc_reads_overlap_stats(const lvc_reads* r, uint64_t* n_pairs, uint64_t* n_bases);
-int lvc_reads_batch(const lvc_reads* r, lvc_batch* batch_out);   /* pointers stay valid until lvc_reads_free */
+int lvc_reads_batch(const lvc_reads* r, lvc_batch* batch_out);   /* pointers stay valid until lvc_reads_free; the
+                                                                    quality-code form when the file qualifies */
+int lvc_reads_batch_bytes(const lvc_reads* r, lvc_batch* batch_out); /* always one phred byte per base */
 int lvc_reads_info(const lvc_reads* r, char* contig_name, int name_cap, int64_t* contig_len, int* n_contigs, int* pinned);
 void lvc_reads_free(lvc_reads* r);
 

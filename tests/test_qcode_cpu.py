@@ -1,0 +1,104 @@
+"""2-bit quality codes (lvc_batch::qual_bits == 2, include/lvc.h) on the CPU: the integer transforms the generation-5
+tiled kernel applies while it stages a quality-code batch (csrc/qcode.hpp, host + device functions, compiled here with
+g++) against a base-by-base restatement, and the host packer lvc_pack_quality_codes through the product library."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import ROOT
+from lvc_b200 import capi, packing
+
+CSRC = os.path.join(ROOT, "covid-spings-variant-caller_b200", "csrc")
+
+HARNESS = r"""
+#include "qcode.hpp"
+extern "C" {
+void keys16(uint32_t s0, uint32_t s1, uint32_t w, uint32_t pcode, uint32_t* out) { lvc::qc_keys16(s0, s1, w, pcode, out[0], out[1]); }
+uint32_t cold_flags(uint32_t w, uint32_t cold) { return lvc::qc_cold_flags(w, cold); }
+uint32_t eq_flags(uint32_t w, uint32_t c) { return lvc::qc_eq_flags(w, c); }
+uint32_t spread8(uint32_t v) { return lvc::qc_spread8(v); }
+}
+"""
+
+
+@pytest.fixture(scope="module")
+def qc(tmp_path_factory):
+    d = tmp_path_factory.mktemp("qcode")
+    src, so = os.path.join(d, "h.cpp"), os.path.join(d, "h.so")
+    with open(src, "w") as fh:
+        fh.write(HARNESS)
+    subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-pthread", "-I", CSRC, "-o", so, src], check=True)
+    lib = C.CDLL(so)
+    for f in ("cold_flags", "eq_flags", "spread8"):
+        getattr(lib, f).restype = C.c_uint32
+        getattr(lib, f).argtypes = [C.c_uint32, C.c_uint32] if f != "spread8" else [C.c_uint32]
+    lib.keys16.argtypes = [C.c_uint32] * 4 + [C.POINTER(C.c_uint32)]
+    return lib
+
+
+def test_key_transform_matches_base_by_base(qc):
+    rng = np.random.default_rng(7)
+    for it in range(3000):
+        nib = rng.integers(0, 16, 16)
+        code = rng.integers(0, 4, 16) if it % 5 else np.full(16, it % 4)
+        pcode = int(rng.integers(0, 4))
+        s0 = sum(int(nib[k]) << (4 * k) for k in range(8))
+        s1 = sum(int(nib[8 + k]) << (4 * k) for k in range(8))
+        w = sum(int(code[k]) << (2 * k) for k in range(16))
+        out = (C.c_uint32 * 2)()
+        qc.keys16(s0, s1, w, pcode, out)
+        want = [int(nib[k]) if code[k] == pcode else 0 for k in range(16)]
+        got = [(out[k // 8] >> (4 * (k % 8))) & 15 for k in range(16)]
+        assert got == want
+        for c in range(4):
+            assert qc.eq_flags(w, c) == sum(1 << (2 * k) for k in range(16) if code[k] == c)
+        cold = int(rng.integers(0, 16))
+        assert qc.cold_flags(w, cold) == sum(1 << (2 * k) for k in range(16) if (cold >> int(code[k])) & 1)
+    for v in range(0, 1 << 16, 37):
+        flags = v & 0x5555
+        assert qc.spread8(v & 0x5555 | (v << 16)) == sum(15 << (4 * k) for k in range(8) if (flags >> (2 * k)) & 1)
+
+
+def _decode(codes, d, n):
+    c = np.asarray(codes[: (n + 3) // 4])
+    four = np.stack([(c >> s) & 3 for s in (0, 2, 4, 6)], axis=1).ravel()[:n]
+    return np.frombuffer(d, dtype=np.uint8)[four]
+
+
+def test_pack_quality_codes_roundtrip_and_refusal():
+    rng = np.random.default_rng(11)
+    for n in (0, 2, 6, 150, 4098, (1 << 21) + 2):          # the last one runs the threaded path
+        q = np.array([2, 12, 23, 37], dtype=np.uint8)[rng.integers(0, 4, n)]
+        got = capi.pack_quality_codes(q, n)
+        assert got is not None
+        codes, d = got
+        assert list(d) == sorted(set(q.tolist())) + [0] * (4 - len(set(q.tolist()))) or n == 0
+        assert np.array_equal(_decode(codes, d, n), q)
+    q = rng.integers(0, 5, 1000).astype(np.uint8)                          # five distinct values: byte form stays
+    assert capi.pack_quality_codes(q, 1000) is None
+    # only the qualities of ADMITTED reads decide: a dropped read may carry anything
+    # ... and so does the pad byte of an odd-length read (here 99 after the 9 bases of the third read)
+    so = np.array([0, 10, 20, 30], dtype=np.uint64)
+    q = np.concatenate([np.full(10, 37), np.arange(10) + 50, np.full(9, 12), [99]]).astype(np.uint8)
+    assert capi.pack_quality_codes(q, 30) is None
+    coff, cig = np.array([0, 1, 2, 4], dtype=np.uint32), np.array([10 << 4, 10 << 4, (4 << 4) | 4, 5 << 4], dtype=np.uint32)
+    codes, d = capi.pack_quality_codes(q, 30, np.array([1, 0, 3], dtype=np.uint8), so, coff, cig)
+    assert list(d) == [12, 37, 0, 0]
+    dec = _decode(codes, d, 30)
+    assert np.array_equal(dec[:10], q[:10]) and np.array_equal(dec[20:29], q[20:29])
+
+
+def test_readbatch_code_form_is_optional_and_lossless():
+    rows = [(99, 5, 60, [(0, 20)], "ACGTN" * 4, [37] * 10 + [12] * 10), (147, 9, 60, [(0, 7), (2, 2), (0, 8)], "ACGTACGTACGTACG", [23] * 15)]
+    b = packing.pack_reads(rows, 20)
+    c = b.with_quality_codes()
+    assert c is not b and c.qcode is not None and list(c.qdict) == [12, 23, 37, 0]
+    assert np.array_equal(_decode(c.qcode, c.qdict, b.n_qual)[:20], b.qual[:20])
+    cb = c.as_capi()
+    assert cb.qual_bits == 2 and list(cb.qual_dict) == [12, 23, 37, 0] and b.as_capi().qual_bits == 0
+    assert c.without_quality_codes().qcode is None
+    wide = packing.pack_reads([(0, 1, 60, [(0, 8)], "ACGTACGT", list(range(8)))], 20)
+    assert wide.with_quality_codes() is wide
