@@ -737,32 +737,47 @@ def main():
                             device=local)
     lvc._handle.set_stream(stream.cuda_stream)
     lvc._handle.set_impl(args.kernel_impl)
-    pinned = packing.pin_batch(batch)
-    small_h2d = sum(getattr(batch, k).nbytes for k in ("pos", "flag", "mapq", "keep", "cigar_off", "cigar", "seq_off"))
-    for _ in range(2):
-        lvc.process_batch(pinned)
-        variants = lvc.prepare_variants()
-    payload0 = lvc._handle.h2d_payload_bytes
-    barrier()
-    torch.cuda.synchronize()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record(stream)
-    for _ in range(args.e2e_steps):
-        lvc.process_batch(pinned)
-        variants = lvc.prepare_variants()
-    f1.record(stream)
-    torch.cuda.synchronize()
-    barrier()
-    e2e_ms = f0.elapsed_time(f1)
-    if world > 1:
-        t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
+
+    def run_e2e(b):
+        """process_batch(page-locked SoA) + prepare_variants, e2e_steps times between two events; (ms, h2d bytes per
+        step, records)"""
+        pinned = packing.pin_batch(b)
+        small = sum(getattr(b, k).nbytes for k in ("pos", "flag", "mapq", "keep", "cigar_off", "cigar", "seq_off"))
+        lvc.reset_memory()
+        for _ in range(2):
+            lvc.process_batch(pinned)
+            recs = lvc.prepare_variants()
+        payload0 = lvc._handle.h2d_payload_bytes
+        barrier()
+        torch.cuda.synchronize()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(stream)
+        for _ in range(args.e2e_steps):
+            lvc.process_batch(pinned)
+            recs = lvc.prepare_variants()
+        f1.record(stream)
+        torch.cuda.synchronize()
+        barrier()
+        t_ms = f0.elapsed_time(f1)
+        if world > 1:
+            t = torch.tensor([t_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_ms = float(t.item())
+        # bytes that cross PCIe per step: the small per-read arrays in full (copied) + the payload the kernel pulls in
+        # place (library count: the 16-byte groups of every chunk's staged extent, i.e. what the kernel requests)
+        moved = small + (lvc._handle.h2d_payload_bytes - payload0) // args.e2e_steps
+        del pinned
+        return t_ms, moved, recs
+
+    # the batch as the packer hands it over: reads the admission dropped are left out (ReadBatch.admitted_only); the
+    # keep-masked batch of the device-resident legs is timed beside it
+    e2e_ms, h2d, variants = run_e2e(batch.admitted_only())
+    e2e_masked_ms, h2d_masked, variants_masked = run_e2e(batch)
+    assert [(v["start"], v["alleles"], v["info"]["DP"], v["info"]["AD"]) for v in variants] == \
+           [(v["start"], v["alleles"], v["info"]["DP"], v["info"]["AD"]) for v in variants_masked], \
+        "e2e: the admitted-only batch and the keep-masked batch must give the same records"
     e2e_value = world * bases * args.e2e_steps / (e2e_ms * 1e-3)
     d2h = len(variants) * 48 + 4 + 32 * 4 + 8 * 4
-    # bytes that cross PCIe per step: the small per-read arrays in full (copied) + the payload the kernel pulls in place
-    # (library count: the 16-byte groups of every chunk's staged extent, i.e. what the kernel requests)
-    h2d = small_h2d + (lvc._handle.h2d_payload_bytes - payload0) // args.e2e_steps
     # admission is part of the reference's process_bam; here it runs once at pack time: its cost for this batch
     t_adm = time.perf_counter()
     capi.admit(batch.pos, batch.flag, batch.mapq, batch.cigar_off, batch.cigar, THRESH["minMQ"])
@@ -789,7 +804,7 @@ def main():
         return out
 
     h.close()
-    del t_arr, pinned
+    del t_arr
     if "config5" in legs:
         if world == 1:
             configs["config5"] = guarded("config5", lambda: leg_config5_single(torch, capi, records, stream, dev))
@@ -843,7 +858,10 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms / args.e2e_steps, "steps": args.e2e_steps,
                     "api": "LiveVariantCaller.process_batch(pinned SoA, admitted at pack time) + prepare_variants()",
-                    "batch_form": form_of(batch),
+                    "batch_form": form_of(batch) + "; reads the admission dropped are left out of the batch at pack time",
+                    "keep_masked_batch": {"ms_per_step": e2e_masked_ms / args.e2e_steps, "h2d_bytes_per_step": int(h2d_masked),
+                                          "value": world * bases * args.e2e_steps / (e2e_masked_ms * 1e-3),
+                                          "note": "the same step with the dropped reads still in the batch (keep bit clear)"},
                     "admit_ms": admit_ms,
                     "h2d_note": "small per-read arrays copied in full + payload read in place over PCIe: the 16-byte "
                                 "groups of each chunk's staged extent, counted by the library"},

@@ -97,6 +97,43 @@ class ReadBatch:
                 setattr(out, extra, getattr(self, extra))
         return out
 
+    def admitted_only(self) -> "ReadBatch":
+        """the same batch without the reads the host admission dropped (keep bit0 clear: htslib's max_depth rule and
+        the read-level filter): no kernel ever reads them, so a batch that leaves them out deposits the same counts,
+        and first-seen ordinals number the admitted reads in the same order (record order is unchanged).  What crosses
+        PCIe shrinks by their per-read arrays (config 2: 60 % of the reads).  Returns self if nothing is dropped."""
+        n = self.n_reads
+        live = (self.keep[:n] & 1) != 0
+        if n == 0 or bool(live.all()):
+            return self
+        idx = np.nonzero(live)[0]
+        co = self.cigar_off.astype(np.int64)
+        so = self.seq_off.astype(np.int64)
+        nc = (co[1:] - co[:-1])[idx]
+        nq = (so[1:] - so[:-1])[idx]                       # even (pad included)
+        new_co = np.concatenate([[0], np.cumsum(nc)])
+        new_so = np.concatenate([[0], np.cumsum(nq)])
+
+        def gather(starts, lens, new_off, src, scale=1):
+            # concatenation of src[starts[i] : starts[i] + lens[i]] (in units of `scale` source items)
+            total = int(new_off[-1]) // scale
+            if total == 0:
+                return np.zeros(0, dtype=src.dtype)
+            rep = np.repeat(np.arange(len(lens)), lens // scale)
+            within = np.arange(total) - np.repeat(new_off[:-1] // scale, lens // scale)
+            return src[(starts // scale)[rep] + within]
+        cigar = gather(co[:-1][idx], nc, new_co, self.cigar)
+        qual = gather(so[:-1][idx], nq, new_so, self.qual)
+        seq4 = gather(so[:-1][idx], nq, new_so, self.seq4, 2)
+        out = ReadBatch(self.pos[:n][idx].copy(), self.flag[:n][idx].copy(), self.mapq[:n][idx].copy(),
+                        self.keep[:n][idx].copy(), new_co.astype(np.uint32),
+                        cigar if len(cigar) else np.zeros(1, np.uint32), new_so.astype(np.uint64),
+                        _with_slack(seq4, int(new_so[-1]) // 2), _with_slack(qual, int(new_so[-1])))
+        for extra in ("overlap_pairs", "overlap_bases"):
+            if hasattr(self, extra):
+                setattr(out, extra, getattr(self, extra))
+        return out.with_quality_codes() if self.qcode is not None else out
+
     def without_quality_codes(self) -> "ReadBatch":
         if self.qcode is None:
             return self

@@ -102,3 +102,21 @@ def test_readbatch_code_form_is_optional_and_lossless():
     assert c.without_quality_codes().qcode is None
     wide = packing.pack_reads([(0, 1, 60, [(0, 8)], "ACGTACGT", list(range(8)))], 20)
     assert wide.with_quality_codes() is wide
+
+
+def test_admitted_only_keeps_exactly_the_admitted_reads():
+    from helpers import synth_small
+    ref, reads = synth_small.make_scenario(seed=301, ref_len=120, n_reads=700, len_lo=90, len_hi=101, q_lo=0, q_hi=0,
+                                           indel_rate=0.05, weird=True, fixed_pos=3, qbins=(2, 12, 23, 37))
+    b = packing.pack_reads([(r.flag, r.pos, r.mapq, r.cigar, r.seq, r.qual) for r in reads], 20, 300)
+    c = b.admitted_only()
+    idx = np.nonzero(b.keep & 1)[0]
+    assert 0 < c.n_reads == len(idx) < b.n_reads and c.admitted_only() is c
+    for j, i in enumerate(idx):
+        assert (c.pos[j], c.flag[j], c.mapq[j], c.keep[j]) == (b.pos[i], b.flag[i], b.mapq[i], b.keep[i])
+        assert np.array_equal(c.cigar[c.cigar_off[j]:c.cigar_off[j + 1]], b.cigar[b.cigar_off[i]:b.cigar_off[i + 1]])
+        s0, s1, t0, t1 = int(c.seq_off[j]), int(c.seq_off[j + 1]), int(b.seq_off[i]), int(b.seq_off[i + 1])
+        assert np.array_equal(c.qual[s0:s1], b.qual[t0:t1]) and np.array_equal(c.seq4[s0 // 2:s1 // 2], b.seq4[t0 // 2:t1 // 2])
+    assert c.n_cigar == int(c.cigar_off[-1]) and c.n_qual == int(c.seq_off[-1]) and len(c.qual) >= c.n_qual + 64
+    coded = b.with_quality_codes().admitted_only()
+    assert coded.qcode is not None and coded.n_reads == c.n_reads
