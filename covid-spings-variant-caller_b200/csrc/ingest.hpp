@@ -6,8 +6,10 @@
 // input order).  Mate overlaps (pysam's ignore_overlaps=True default) are handled at pack time by the admission pass
 // of overlap.hpp.  Included by lvc_api.cu (host code only).
 #include <zlib.h>
+#include <sys/mman.h>
 
 #include <atomic>
+#include <memory>
 #include <mutex>
 #include <chrono>
 #include <fstream>
@@ -26,6 +28,8 @@ struct lvc_reads {
     uint8_t* seq4 = nullptr; uint8_t* qual = nullptr;
     uint8_t* qcode = nullptr;                        // 2-bit quality codes (lvc_batch::qual_bits == 2) when the file qualifies
     uint8_t qdict[4] = {0, 0, 0, 0};
+    bool codes_tried = false;                        // the code form is made on the first lvc_reads_batch
+    int n_threads = 1;
     bool pinned = false;
     uint64_t overlap_pairs = 0, overlap_bases = 0;   // mate pairs / quality bytes rewritten by the overlap model
     std::vector<std::pair<void*, size_t>> allocs;    // (pointer, capacity)
@@ -135,7 +139,15 @@ struct RawBuf {
     const uint8_t& operator[](size_t i) const { return p[i]; }
 };
 
-static std::string bgzf_inflate(const std::vector<uint8_t>& file, RawBuf& out, int n_threads) {
+// the input file: a read-only mapping (no copy: the inflate threads fault the pages in), or a buffer for a pipe
+struct Bytes {
+    const uint8_t* p = nullptr; size_t n = 0;
+    size_t size() const { return n; }
+    const uint8_t* data() const { return p; }
+    const uint8_t& operator[](size_t i) const { return p[i]; }
+};
+
+static std::string bgzf_inflate(const Bytes& file, RawBuf& out, int n_threads) {
     struct Blk { size_t coff, clen, uoff; uint32_t ulen, crc; };
     std::vector<Blk> blks;
     size_t i = 0, n = file.size(), total = 0;
@@ -215,6 +227,94 @@ struct NotAcgtPair {
 static const NotAcgtPair kNotAcgtPair;
 #define kAsciiToNib kNib.t
 
+static void release_alloc(lvc_reads* r, void* p) {
+    for (size_t k = 0; k < r->allocs.size(); ++k)
+        if (r->allocs[k].first == p) {
+            if (r->pinned) g_pinned_pool.give(p, r->allocs[k].second); else free(p);
+            r->allocs.erase(r->allocs.begin() + (long)k);
+            return;
+        }
+}
+
+// Instrument-binned qualities (at most four distinct values among the admitted reads, after the mate-overlap rewrite):
+// the batch also gets the 2-bit code form, which is what lvc_reads_batch hands out (half the payload bytes over PCIe).
+// LVC_QUALITY_CODES=0 keeps the byte form only.
+static void make_quality_codes(lvc_reads* r, int n_threads) {
+    if (r->qcode) { release_alloc(r, r->qcode); r->qcode = nullptr; }
+    const char* qc_env = getenv("LVC_QUALITY_CODES");
+    if (!r->n || !r->n_qual || (qc_env && atoi(qc_env) == 0)) return;
+    uint8_t* codes = (uint8_t*)host_alloc(r, (size_t)(r->n_qual / 4) + 64);
+    if (!codes) return;
+    const int nd = lvc::pack_quality_codes(r->qual, r->n_qual, r->n, r->keep, r->seq_off, r->cigar_off, r->cigar, n_threads,
+                                           r->qdict, codes);
+    if (nd > 0) { memset(codes + (r->n_qual + 3) / 4, 0, 64 - 4); r->qcode = codes; }
+    else release_alloc(r, codes);
+}
+
+// lvc_reads_compact: leave out the reads the admission dropped (keep bit0 clear).  No kernel reads them, so the tables
+// that result are the same; first-seen ordinals then number the admitted reads (same order).  The arrays are re-packed
+// into fresh buffers (page-locked like the old ones), the old ones go back to the pool.
+static int compact(lvc_reads* r, int n_threads) {
+    const size_t n = r->n;
+    size_t m = 0;
+    for (size_t i = 0; i < n; ++i) m += r->keep[i] & 1u;
+    if (m == n) return 0;
+    std::vector<uint32_t> src(m);
+    std::vector<uint64_t> coff(m + 1, 0), soff(m + 1, 0);
+    for (size_t i = 0, j = 0; i < n; ++i)
+        if (r->keep[i] & 1u) {
+            src[j] = (uint32_t)i;
+            coff[j + 1] = coff[j] + (r->cigar_off[i + 1] - r->cigar_off[i]);
+            soff[j + 1] = soff[j] + (r->seq_off[i + 1] - r->seq_off[i]);
+            ++j;
+        }
+    int32_t* pos = (int32_t*)host_alloc(r, m * 4); uint16_t* flag = (uint16_t*)host_alloc(r, m * 2);
+    uint8_t* mapq = (uint8_t*)host_alloc(r, m); uint8_t* keep = (uint8_t*)host_alloc(r, m);
+    uint32_t* cigar_off = (uint32_t*)host_alloc(r, (m + 1) * 4); uint32_t* cigar = (uint32_t*)host_alloc(r, coff[m] * 4 + 4);
+    uint64_t* seq_off = (uint64_t*)host_alloc(r, (m + 1) * 8);
+    uint8_t* seq4 = (uint8_t*)host_alloc(r, soff[m] / 2 + 64); uint8_t* qual = (uint8_t*)host_alloc(r, soff[m] + 64);
+    void* fresh[9] = {pos, flag, mapq, keep, cigar_off, cigar, seq_off, seq4, qual};
+    for (void* p : fresh)
+        if (!p) {                                            // out of (page-locked) memory: the batch stays as it is
+            for (void* q : fresh) if (q) release_alloc(r, q);
+            return 0;
+        }
+    std::atomic<size_t> next{0};
+    auto work = [&]() {
+        for (;;) {
+            const size_t b0 = next.fetch_add(4096);
+            if (b0 >= m) return;
+            const size_t b1 = std::min(m, b0 + 4096);
+            for (size_t j = b0; j < b1; ++j) {
+                const size_t i = src[j];
+                pos[j] = r->pos[i]; flag[j] = r->flag[i]; mapq[j] = r->mapq[i]; keep[j] = r->keep[i];
+                cigar_off[j] = (uint32_t)coff[j]; seq_off[j] = soff[j];
+                memcpy(cigar + coff[j], r->cigar + r->cigar_off[i], (size_t)(coff[j + 1] - coff[j]) * 4);
+                const size_t nq = (size_t)(soff[j + 1] - soff[j]);
+                memcpy(qual + soff[j], r->qual + r->seq_off[i], nq);
+                memcpy(seq4 + soff[j] / 2, r->seq4 + r->seq_off[i] / 2, nq / 2);
+            }
+        }
+    };
+    n_threads = std::max(1, std::min(n_threads, 64));
+    std::vector<std::thread> th;
+    for (int t = 1; t < n_threads; ++t) th.emplace_back(work);
+    work();
+    for (auto& t : th) t.join();
+    cigar_off[m] = (uint32_t)coff[m];
+    seq_off[m] = soff[m];
+    memset(seq4 + soff[m] / 2, 0, 64);
+    memset(qual + soff[m], 0, 64);
+    void* old[9] = {r->pos, r->flag, r->mapq, r->keep, r->cigar_off, r->cigar, r->seq_off, r->seq4, r->qual};
+    for (void* p : old) release_alloc(r, p);
+    r->pos = pos; r->flag = flag; r->mapq = mapq; r->keep = keep; r->cigar_off = cigar_off; r->cigar = cigar;
+    r->seq_off = seq_off; r->seq4 = seq4; r->qual = qual;
+    r->n = (uint32_t)m; r->n_cigar = coff[m]; r->n_qual = soff[m];
+    if (r->qcode) { release_alloc(r, r->qcode); r->qcode = nullptr; }
+    r->codes_tried = false;                                  // made again, for the new layout, when a batch is asked for
+    return 1;
+}
+
 // pack `recs` (already in coordinate order) into the SoA arrays of `r`
 static std::string pack(lvc_reads* r, const std::vector<Rec>& recs, int min_mapq, int max_depth, int n_threads,
                         int overlap_model, PhaseTimer& timer) {
@@ -243,12 +343,25 @@ static std::string pack(lvc_reads* r, const std::vector<Rec>& recs, int min_mapq
     timer.mark("offsets + alloc");
     memset(r->seq4 + soff[n] / 2, 0, 64);
     memset(r->qual + soff[n], 0, 64);
+    // mate fields for the overlap pass, filled by the same threads (unpaired data -- ONT, single-end -- has nothing to
+    // pair up and skips the overlap bookkeeping altogether)
+    std::unique_ptr<int32_t[]> mpos, tlen;
+    std::unique_ptr<int8_t[]> mref;
+    if (overlap_model != LVC_OVERLAP_OFF && n) { mpos.reset(new int32_t[n]); tlen.reset(new int32_t[n]); mref.reset(new int8_t[n]); }
+    std::atomic<bool> any_pair_seen{false};
     std::atomic<size_t> next{0};
     auto work = [&]() {
         for (;;) {
             const size_t b0 = next.fetch_add(4096);
             if (b0 >= n) return;
             const size_t b1 = std::min(n, b0 + 4096);
+            bool pair_here = false;
+            if (mpos)
+                for (size_t i = b0; i < b1; ++i) {
+                    mpos[i] = recs[i].next_pos; tlen[i] = recs[i].tlen; mref[i] = recs[i].next_ref;
+                    pair_here |= (recs[i].flag & 0x3u) == 0x3u && !(recs[i].flag & 0x8u);
+                }
+            if (pair_here) any_pair_seen.store(true, std::memory_order_relaxed);
             for (size_t i = b0; i < b1; ++i) {
                 const Rec& x = recs[i];
                 r->pos[i] = x.pos; r->flag[i] = x.flag; r->mapq[i] = x.mapq;
@@ -278,21 +391,11 @@ static std::string pack(lvc_reads* r, const std::vector<Rec>& recs, int min_mapq
     r->seq_off[n] = soff[n];
     timer.mark("pack");
     std::vector<uint8_t> adm(n ? n : 1);
-    // unpaired data (ONT, single-end) has nothing to pair up: skip the overlap bookkeeping altogether
-    bool any_pair = false;
-    if (overlap_model != LVC_OVERLAP_OFF)
-        for (size_t i = 0; i < n && !any_pair; ++i) any_pair = (recs[i].flag & 0x3u) == 0x3u && !(recs[i].flag & 0x8u);
-    std::vector<int32_t> mpos, tlen;
-    std::vector<int8_t> mref;
-    if (any_pair) {
-        mpos.resize(n); tlen.resize(n); mref.resize(n);
-        for (size_t i = 0; i < n; ++i) { mpos[i] = recs[i].next_pos; tlen[i] = recs[i].tlen; mref[i] = recs[i].next_ref; }
-    }
-    timer.mark("mate arrays");
+    const bool any_pair = any_pair_seen.load();
     auto name = [&](uint32_t i) { return lvc_overlap::NameKey{recs[i].name, recs[i].l_name}; };
     const int rc = lvc_overlap::admit_core((uint32_t)n, r->pos, r->flag, r->mapq, r->cigar_off, r->cigar, r->seq_off, r->seq4,
-                                           r->qual, name, any_pair ? mpos.data() : nullptr, any_pair ? mref.data() : nullptr,
-                                           any_pair ? tlen.data() : nullptr, min_mapq, max_depth,
+                                           r->qual, name, any_pair ? mpos.get() : nullptr, any_pair ? mref.get() : nullptr,
+                                           any_pair ? tlen.get() : nullptr, min_mapq, max_depth,
                                            any_pair ? overlap_model : LVC_OVERLAP_OFF, adm.data(), &r->overlap_pairs,
                                            &r->overlap_bases);
     timer.mark("admit + overlaps");
@@ -300,18 +403,7 @@ static std::string pack(lvc_reads* r, const std::vector<Rec>& recs, int min_mapq
     if (rc) return fail("admission failed (%d)", rc);
     for (size_t i = 0; i < n; ++i) r->keep[i] |= adm[i];
     timer.mark("keep bits");
-    // instrument-binned qualities (at most four distinct values among the admitted reads, after the mate-overlap
-    // rewrite): the batch also gets the 2-bit code form, which is what lvc_reads_batch hands out (half the payload
-    // bytes over PCIe).  LVC_QUALITY_CODES=0 keeps the byte form only.
-    const char* qc_env = getenv("LVC_QUALITY_CODES");
-    if (n && r->n_qual && !(qc_env && atoi(qc_env) == 0)) {
-        uint8_t* codes = (uint8_t*)host_alloc(r, (size_t)(r->n_qual / 4) + 64);
-        if (codes) {
-            const int nd = lvc::pack_quality_codes(r->qual, r->n_qual, r->n, r->keep, r->seq_off, r->cigar_off, r->cigar, n_threads, r->qdict, codes);
-            if (nd > 0) { memset(codes + (r->n_qual + 3) / 4, 0, 64 - 4); r->qcode = codes; }
-        }
-        timer.mark("quality codes");
-    }
+    r->n_threads = n_threads;
     return "";
 }
 
@@ -328,7 +420,7 @@ static std::string validate(const Rec& x, const char* what) {
     return "";
 }
 
-static std::string read_bam(lvc_reads* r, const std::vector<uint8_t>& file, const char* contig, int min_mapq, int max_depth,
+static std::string read_bam(lvc_reads* r, const Bytes& file, const char* contig, int min_mapq, int max_depth,
                             int n_threads, RawBuf& raw, int overlap_model, PhaseTimer& timer) {
     std::string e = bgzf_inflate(file, raw, n_threads);
     if (!e.empty()) return e;
@@ -357,12 +449,20 @@ static std::string read_bam(lvc_reads* r, const std::vector<uint8_t>& file, cons
     // pass 1 (serial, a hop per record): where the records of this contig start
     std::vector<size_t> offs;
     offs.reserve(raw.size() / 256);
+    // (every hop is a dependent cache miss; records of one run have similar sizes, so the line a few records ahead is
+    // requested by extrapolation: right most of the time, harmless when not)
     while (off + 4 <= raw.size()) {
         const int32_t bs = rdi32(&raw[off]);
         if (bs < 32 || off + 4 + (size_t)bs > raw.size()) return fail("truncated BAM record");
+        const size_t step = 4 + (size_t)bs;
+        if (off + 12 * step + 64 < raw.size()) {
+            __builtin_prefetch(&raw[off + 6 * step]); __builtin_prefetch(&raw[off + 6 * step + 64]);
+            __builtin_prefetch(&raw[off + 12 * step]); __builtin_prefetch(&raw[off + 12 * step + 64]);
+        }
         if (rdi32(&raw[off + 4]) == tid) offs.push_back(off);
-        off += 4 + (size_t)bs;
+        off += step;
     }
+    timer.mark("record offsets");
     // pass 2 (threads): decode and validate; the error of the first bad record wins
     std::vector<Rec> recs(offs.size());
     std::atomic<size_t> next{0};
@@ -428,7 +528,7 @@ static inline int64_t parse_int(const char* p, size_t n) {
     return neg ? -v : v;
 }
 
-static std::string read_sam(lvc_reads* r, const std::vector<uint8_t>& file, const char* contig, int min_mapq, int max_depth,
+static std::string read_sam(lvc_reads* r, const Bytes& file, const char* contig, int min_mapq, int max_depth,
                             int n_threads, int overlap_model, PhaseTimer& timer) {
     // text -> per-record binary blobs (cigar u32s, packed seq, qual), parsed by all threads on line-aligned pieces
     // of the file, then the samtools-order sort and the common packer
@@ -601,22 +701,34 @@ int lvc_read_alignments_ex(const char* path, const char* contig, int min_mapq, i
     ingest::PhaseTimer timer;                                    // per call: the entry point is re-entrant
     auto seterr = [&](const std::string& s) { if (errbuf && errlen > 0) snprintf(errbuf, (size_t)errlen, "%s", s.c_str()); };
     if (!path || !out || overlap_model < LVC_OVERLAP_OFF || overlap_model > LVC_OVERLAP_HTSLIB_1_13) { seterr("bad arguments"); return LVC_EINVAL; }
-    // whole file in one read (a stream iterator would copy it byte by byte)
+    // a regular file is mapped read-only (no copy; the worker threads fault its pages in); anything else (a pipe) is
+    // read in blocks
     FILE* fh = fopen(path, "rb");
     if (!fh) { seterr(std::string("cannot open ") + path); return LVC_EIO; }
-    std::vector<uint8_t> file;
+    std::vector<uint8_t> filebuf;
+    ingest::Bytes file;
+    void* mapped = nullptr; size_t mapped_len = 0;
+    struct Unmap { void*& p; size_t& n; ~Unmap() { if (p) munmap(p, n); } } unmap_guard{mapped, mapped_len};
     if (fseek(fh, 0, SEEK_END) == 0) {
         const long sz = ftell(fh);
         rewind(fh);
         if (sz > 0) {
-            file.resize((size_t)sz);
-            const size_t got = fread(file.data(), 1, (size_t)sz, fh);
-            file.resize(got);
+            void* m = mmap(nullptr, (size_t)sz, PROT_READ, MAP_PRIVATE, fileno(fh), 0);
+            if (m != MAP_FAILED) {
+                mapped = m; mapped_len = (size_t)sz;
+                madvise(m, (size_t)sz, MADV_WILLNEED);
+                file.p = (const uint8_t*)m; file.n = (size_t)sz;
+            } else {
+                filebuf.resize((size_t)sz);
+                filebuf.resize(fread(filebuf.data(), 1, (size_t)sz, fh));
+                file.p = filebuf.data(); file.n = filebuf.size();
+            }
         }
     } else {                                                     // not seekable (a pipe): read in blocks
         uint8_t buf[1 << 16];
         size_t got;
-        while ((got = fread(buf, 1, sizeof buf, fh)) > 0) file.insert(file.end(), buf, buf + got);
+        while ((got = fread(buf, 1, sizeof buf, fh)) > 0) filebuf.insert(filebuf.end(), buf, buf + got);
+        file.p = filebuf.data(); file.n = filebuf.size();
     }
     fclose(fh);
     timer.mark("file read");
@@ -661,7 +773,23 @@ int lvc_reads_batch_bytes(const lvc_reads* r, lvc_batch* b) {
 
 int lvc_reads_batch(const lvc_reads* r, lvc_batch* b) {
     const int rc = lvc_reads_batch_bytes(r, b);
+    if (rc == LVC_OK && !r->codes_tried) {
+        lvc_reads* w = const_cast<lvc_reads*>(r);            // a cache inside the object: the batch itself is unchanged
+        ingest::PhaseTimer timer;
+        ingest::make_quality_codes(w, w->n_threads);
+        w->codes_tried = true;
+        timer.mark("quality codes");
+    }
     if (rc == LVC_OK && r->qcode) { b->qual_bits = 2; b->qual = r->qcode; memcpy(b->qual_dict, r->qdict, 4); }
+    return rc;
+}
+
+int lvc_reads_compact(lvc_reads* r, int n_threads) {
+    if (!r) return LVC_EINVAL;
+    if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    ingest::PhaseTimer timer;
+    const int rc = ingest::compact(r, n_threads);
+    timer.mark("compact");
     return rc;
 }
 

@@ -261,10 +261,16 @@ static int admit_core(uint32_t n, const int32_t* pos, const uint16_t* flag, cons
             if (overlap_model == LVC_OVERLAP_HTSLIB_1_10) possible = !(aisz >= 2 * l_qseq);
             else possible = !((mref == 0) || (aisz >= 2 * l_qseq && mp >= e));
             if (possible) {
+                // (nothing is buffered: the lookup cannot hit, and a read that is not added either never has its name
+                // touched -- the name bytes live in the inflated file, one cache miss per read)
+                const bool add = overlap_model == LVC_OVERLAP_HTSLIB_1_10 ? true : (mp >= p || ((f & 0x1u) && mp == -1));
+                if (olap.empty()) {
+                    if (add) olap.emplace(name(i), i);
+                    goto pushed;
+                }
                 const NameKey key = name(i);
                 auto it = olap.find(key);
                 if (it == olap.end()) {
-                    const bool add = overlap_model == LVC_OVERLAP_HTSLIB_1_10 ? true : (mp >= p || ((f & 0x1u) && mp == -1));
                     if (add) olap.emplace(key, i);
                 } else {
                     const uint32_t a = it->second;
@@ -275,6 +281,7 @@ static int admit_core(uint32_t n, const int32_t* pos, const uint16_t* flag, cons
                 }
             }
         }
+    pushed:
         // bam_plp_next: emit columns while max_pos > iter_pos; each built column frees ended reads
         while (max_pos > iter_pos) {
             const int64_t c = iter_pos;

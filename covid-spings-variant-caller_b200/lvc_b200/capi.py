@@ -73,6 +73,7 @@ SIGNATURES = [
     ("lvc_reads_overlap_stats", C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     ("lvc_reads_batch", C.c_int, [C.c_void_p, C.POINTER(Batch)]),
     ("lvc_reads_batch_bytes", C.c_int, [C.c_void_p, C.POINTER(Batch)]),
+    ("lvc_reads_compact", C.c_int, [C.c_void_p, C.c_int]),
     ("lvc_pack_quality_codes", C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_int, C.c_void_p, C.c_void_p]),
     ("lvc_reads_info", C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int),
@@ -254,12 +255,9 @@ class NativeReads:
                 raise UnsupportedInput(msg)
             raise LvcError(rc, msg)
         self.r = r
-        self.batch = Batch()                                   # what process_bam pushes: 2-bit quality codes if the file qualifies
-        self.lib.lvc_reads_batch(self.r, C.byref(self.batch))
-        self.batch._keepalive = self
-        self.batch_bytes = Batch()                             # always one phred byte per base
-        self.lib.lvc_reads_batch_bytes(self.r, C.byref(self.batch_bytes))
-        self.batch_bytes._keepalive = self
+        self.n_threads = int(n_threads)
+        self._take_batches()
+        self.n_presented = int(self.batch_bytes.n_reads)       # reads of the contig in the file
         name = C.create_string_buffer(256)
         ln, nc, pinned = C.c_int64(0), C.c_int(0), C.c_int(0)
         self.lib.lvc_reads_info(self.r, name, 256, C.byref(ln), C.byref(nc), C.byref(pinned))
@@ -268,9 +266,32 @@ class NativeReads:
         self.lib.lvc_reads_overlap_stats(self.r, C.byref(op), C.byref(ob))
         self.overlap_pairs, self.overlap_bases = int(op.value), int(ob.value)
 
+    def _take_batches(self):
+        self._batch = None
+        self.batch_bytes = Batch()                             # always one phred byte per base
+        self.lib.lvc_reads_batch_bytes(self.r, C.byref(self.batch_bytes))
+        self.batch_bytes._keepalive = self
+
+    @property
+    def batch(self) -> Batch:
+        """what process_bam pushes: 2-bit quality codes if the file qualifies (made on first use), else phred bytes"""
+        if self._batch is None:
+            self._batch = Batch()
+            self.lib.lvc_reads_batch(self.r, C.byref(self._batch))
+            self._batch._keepalive = self
+        return self._batch
+
+    def compact(self) -> bool:
+        """lvc_reads_compact: leave out the reads the admission dropped (views taken before are invalid)"""
+        rc = self.lib.lvc_reads_compact(self.r, self.n_threads)
+        if rc < 0:
+            raise LvcError(rc, "lvc_reads_compact failed")
+        self._take_batches()
+        return rc == 1
+
     @property
     def n_reads(self) -> int:
-        return int(self.batch.n_reads)
+        return int(self.batch_bytes.n_reads)
 
     def as_readbatch(self):
         """numpy views (no copy) in the layout of packing.ReadBatch; valid while this object lives"""

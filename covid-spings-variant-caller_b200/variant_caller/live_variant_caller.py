@@ -117,6 +117,7 @@ class LiveVariantCaller:
             reads = samio.read_alignments_native(inputBam, self._contig, int(self.minMappingQuality), self.maxDepth,
                                                  overlap_model=self.overlapModel)
             try:
+                reads.compact()                 # reads the admission dropped never reach the device
                 if reads.n_reads:
                     self._handle.push_batch(reads.batch)
             finally:

@@ -170,6 +170,12 @@ int lvc_reads_overlap_stats(const lvc_reads* r, uint64_t* n_pairs, uint64_t* n_b
 int lvc_reads_batch(const lvc_reads* r, lvc_batch* batch_out);   /* pointers stay valid until lvc_reads_free; the
                                                                     quality-code form when the file qualifies */
 int lvc_reads_batch_bytes(const lvc_reads* r, lvc_batch* batch_out); /* always one phred byte per base */
+/* Leaves out the reads the admission dropped (keep bit0 clear: read-level filter, max_depth rule): no kernel reads them,
+ * the tables that result are the same, and first-seen ordinals number the admitted reads in the same order.  The arrays
+ * are re-packed (batches obtained before the call are invalid).  Returns 1 if reads were removed, 0 if the batch stays
+ * as it was (nothing dropped, or no memory for the copy).  What lvc_push_batch moves over PCIe shrinks by the dropped
+ * reads' per-read arrays: 60 % of the reads of an amplicon sample at 10,000x. */
+int lvc_reads_compact(lvc_reads* r, int n_threads);
 int lvc_reads_info(const lvc_reads* r, char* contig_name, int name_cap, int64_t* contig_len, int* n_contigs, int* pinned);
 void lvc_reads_free(lvc_reads* r);
 

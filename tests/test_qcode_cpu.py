@@ -120,3 +120,31 @@ def test_admitted_only_keeps_exactly_the_admitted_reads():
     assert c.n_cigar == int(c.cigar_off[-1]) and c.n_qual == int(c.seq_off[-1]) and len(c.qual) >= c.n_qual + 64
     coded = b.with_quality_codes().admitted_only()
     assert coded.qcode is not None and coded.n_reads == c.n_reads
+
+
+def test_native_ingest_compact_and_codes(tmp_path):
+    """lvc_reads_compact == ReadBatch.admitted_only() of the same file; the code form follows the re-packed layout"""
+    from helpers import synth_small
+    from lvc_b200 import samio
+    ref, reads = synth_small.make_scenario(seed=302, ref_len=300, n_reads=1500, len_lo=60, len_hi=151, q_lo=0, q_hi=0,
+                                           indel_rate=0.05, weird=True, amplicon=(0, 0, 40, 120), qbins=(2, 12, 23, 37))
+    bam = str(tmp_path / "c.bam")
+    samio.write_bam(bam, [("chrS", len(ref))], [(r.flag, r.pos, r.mapq, r.cigar, r.seq, r.qual, r.name) for r in reads])
+    nat = samio.read_alignments_native(bam, None, 20, max_depth=200)
+    full = nat.as_readbatch()
+    want = packing.ReadBatch(*[np.array(getattr(full, k)) for k in ("pos", "flag", "mapq", "keep", "cigar_off", "cigar",
+                                                                   "seq_off", "seq4", "qual")]).admitted_only()
+    assert nat.batch.qual_bits == 2 and nat.n_presented == len(reads)
+    assert nat.compact() and not nat.compact()
+    got = nat.as_readbatch()
+    assert got.n_reads == want.n_reads < len(reads) and nat.batch.n_reads == want.n_reads
+    for k in ("pos", "flag", "mapq", "keep"):
+        assert np.array_equal(getattr(got, k)[:got.n_reads], getattr(want, k)[:want.n_reads]), k
+    assert np.array_equal(got.cigar_off, want.cigar_off) and np.array_equal(got.seq_off, want.seq_off)
+    assert np.array_equal(got.cigar[:got.n_cigar], want.cigar[:want.n_cigar])
+    assert np.array_equal(got.qual[:got.n_qual], want.qual[:want.n_qual])
+    assert np.array_equal(got.seq4[:got.n_qual // 2], want.seq4[:want.n_qual // 2])
+    assert nat.batch.qual_bits == 2 and got.qcode is not None
+    wc = want.with_quality_codes()
+    assert bytes(got.qdict) == wc.qdict and np.array_equal(got.qcode[:(got.n_qual + 3) // 4], wc.qcode[:(got.n_qual + 3) // 4])
+    nat.close()
