@@ -38,6 +38,14 @@ static_assert(kT5Threads % 32 == 0 && kT5Threads <= 256, "read index in a chunk 
 constexpr uint32_t kT5WinStride = kT5Reads * 160u;                   // payload bytes per staged window
 constexpr uint32_t kT5KeyCapBases = kT5WinStride + kMaxReadBytes;    // + one longest tileable read
 constexpr int kTile5CtasPerSM = LVC5_CTAS_PER_SM;
+// Where the kernel waits for the previous kernel of the stream (programmatic dependent launch):
+//   0  before the byte extents (everything after the read-level filter follows the wait)
+//   1  before the coverage atomics (extents, payload prefetch and classification precede it)
+//   2  after the first window is staged: the coverage / deletion updates are parked in shared memory, so that headers,
+//      classification AND the payload loads of a chunk overlap the tail of the previous kernel
+#ifndef LVC5_WAIT
+#define LVC5_WAIT 2
+#endif
 constexpr int kTask5Runs = 224;                  // runs per task: 7 units per lane, three bit planes hold <= 7
 
 struct Tile5Smem {
@@ -56,7 +64,9 @@ struct Tile5Smem {
     static constexpr uint32_t misc_off = (slab_per_off + kMaxSlabs * 4 + 15) & ~15u;
     static constexpr uint32_t lut_off = misc_off + 256;                        // uint4 [2][33] edge masks
     static constexpr uint32_t pk_off = lut_off + 2 * 33 * 16;                  // uint2 [kMaxRuns]: what the pass loop reads
-    static constexpr uint32_t total = pk_off + kMaxRuns * 8;
+    static constexpr uint32_t cov_off = pk_off + kMaxRuns * 8;                 // uint2 [kT5Reads]: parked coverage update
+    static constexpr uint32_t del_off = cov_off + (LVC5_WAIT == 2 ? kT5Reads * 8 : 0);   // uint4 [kT5Reads]: parked deletions
+    static constexpr uint32_t total = del_off + (LVC5_WAIT == 2 ? kT5Reads * 16 : 0);
 };
 constexpr size_t kTile5SmemBytes = Tile5Smem::total;
 static_assert((kTile5SmemBytes + 1024) * kTile5CtasPerSM <= 227 * 1024, "the intended CTAs per SM must fit");
@@ -162,7 +172,9 @@ k_deposit_tile5(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
     if (!__syncthreads_or(read_passes_filter(hd.flag, hd.mapq, hd.keep, dp.min_mq))) return;
     // Up to here only the batch was read.  The tables may still be in use by the previous kernel of the stream (this
     // kernel is launched with programmatic stream serialization): wait for it before the first table access.
+#if LVC5_WAIT == 0
     asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
     // byte extent of the reads that pass the read-level filter (a superset of what will be deposited):
     // known before the CIGARs arrive, so the bulk copy overlaps classification
     const uint32_t so_rel = hd.so - (uint32_t)so0, so1_rel = hd.so1 - (uint32_t)so0;
@@ -185,6 +197,7 @@ k_deposit_tile5(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
         }
         __syncthreads();
         const uint32_t n_def = s_misc[6];
+        asm volatile("griddepcontrol.wait;" ::: "memory");
         for (uint32_t d = warp; d < n_def; d += kT5Warps) (PEER ? deposit_read_warp_peer : deposit_read_warp)(b, tv, dp, cur * kT5Reads + s_dlist[d], lane);
         return;
     }
@@ -382,19 +395,45 @@ k_deposit_tile5(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
         }
         const bool active = rspan != 0;                                   // deposited by this kernel
         if (defer) s_dlist[atomicAdd(&s_misc[6], 1u)] = (uint16_t)tid;
-        {
-            // coverage difference array: one atomic per distinct start / end among the warp's reads
-            const int32_t ks = active ? hd.pos : (int32_t)(0x80000000u + lane);
+        // coverage difference array (one atomic per distinct start / end among the warp's reads) and deletion entries:
+        // the first table accesses of the chunk.  All 32 lanes of every warp call this together.
+        auto deposit_cov = [&](bool act, int32_t rpos, uint32_t span, uint32_t n_del, int32_t dpos0, uint32_t dlen0, int32_t dpos1,
+                               uint32_t dlen1) {
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            const int32_t ks = act ? rpos : (int32_t)(0x80000000u + lane);
             const uint32_t ms = __match_any_sync(0xFFFFFFFFu, ks);
-            if (active && lane == __ffs(ms) - 1) atomicAdd(PEER ? covdiff_cell(tv, hd.pos) : tv.covdiff + hd.pos, (int32_t)__popc(ms));
-            const int32_t ke = active ? (int32_t)(hd.pos + rspan) : (int32_t)(0x80000000u + lane);
+            if (act && lane == __ffs(ms) - 1) atomicAdd(PEER ? covdiff_cell(tv, rpos) : tv.covdiff + rpos, (int32_t)__popc(ms));
+            const int32_t ke = act ? (int32_t)(rpos + span) : (int32_t)(0x80000000u + lane);
             const uint32_t me = __match_any_sync(0xFFFFFFFFu, ke);
-            if (active && lane == __ffs(me) - 1) atomicAdd(PEER ? covdiff_cell(tv, (int64_t)hd.pos + rspan) : tv.covdiff + hd.pos + rspan, -(int32_t)__popc(me));
-#pragma unroll
-            for (int k = 0; k < kMaxDelsPerRead; ++k)
-                if ((uint32_t)k < nd && (int)del_q[k] >= dp.min_bq)
-                    for (uint32_t j = 0; j < del_len[k]; ++j) atomicAdd(PEER ? dels_cell(tv, (int64_t)del_pos[k] + j) : tv.dels + del_pos[k] + j, 1u);
-        }
+            if (act && lane == __ffs(me) - 1) atomicAdd(PEER ? covdiff_cell(tv, (int64_t)rpos + span) : tv.covdiff + rpos + span, -(int32_t)__popc(me));
+            if (n_del) {
+                for (uint32_t j = 0; j < dlen0; ++j) atomicAdd(PEER ? dels_cell(tv, (int64_t)dpos0 + j) : tv.dels + dpos0 + j, 1u);
+                for (uint32_t j = 0; j < dlen1; ++j) atomicAdd(PEER ? dels_cell(tv, (int64_t)dpos1 + j) : tv.dels + dpos1 + j, 1u);
+            }
+        };
+        // deletion entries that passed the quality rule (a failed one keeps length 0)
+        const uint32_t dl0 = (nd >= 1 && (int)del_q[0] >= dp.min_bq) ? del_len[0] : 0u;
+        const uint32_t dl1 = (nd >= 2 && (int)del_q[1] >= dp.min_bq) ? del_len[1] : 0u;
+#if LVC5_WAIT == 2
+        // parked: the update is issued once the first window is staged (or right away if nothing is staged)
+        uint2* s_cov = reinterpret_cast<uint2*>(smem + Tile5Smem::cov_off);
+        uint4* s_del = reinterpret_cast<uint4*>(smem + Tile5Smem::del_off);
+        s_cov[tid] = make_uint2((uint32_t)hd.pos, (active ? rspan : 0u) | ((dl0 | dl1) ? 0x80000000u : 0u));
+        if (dl0 | dl1) s_del[tid] = make_uint4((uint32_t)del_pos[0], dl0, (uint32_t)del_pos[1], dl1);
+        bool cov_parked = true;
+        auto deposit_parked = [&]() {
+            if (!cov_parked) return;                          // (uniform over the CTA)
+            cov_parked = false;
+            const uint2 cv = s_cov[tid];
+            uint4 dv = make_uint4(0, 0, 0, 0);
+            if (cv.y & 0x80000000u) dv = s_del[tid];
+            const uint32_t span = cv.y & 0x7FFFFFFFu;
+            deposit_cov(span != 0, (int32_t)cv.x, span, cv.y >> 31, (int32_t)dv.x, dv.y, (int32_t)dv.z, dv.w);
+        };
+        if (!n_runs) deposit_parked();
+#else
+        deposit_cov(active, hd.pos, rspan, (dl0 | dl1) ? 1u : 0u, del_pos[0], dl0, del_pos[1], dl1);
+#endif
         if (n_runs) {
             if (nr) {
                 const uint32_t off = so_rel - base_rel;                   // read's first byte relative to the base
@@ -527,6 +566,9 @@ k_deposit_tile5(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
                                     while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if (s_qo[m] <= x_rel) lo = m + 1; else hi = m; }
                                     if (lo > a0) {
                                         const uint32_t r = lo - 1, d = x_rel - s_qo[r];
+#if LVC5_WAIT == 2
+                                        asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
                                         if (d < (uint32_t)s_len[r])
                                             deposit_base<PEER>(tv, dp, (int64_t)s_pos[r] + d, (sx >> (4 * bb)) & 15u,
                                                          (qv >> (8 * bb)) & 255u, chunk_ord + (s_rix[r] & 255u));
@@ -557,6 +599,9 @@ k_deposit_tile5(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
                                 while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if (s_qo[m] <= x_rel) lo = m + 1; else hi = m; }
                                 if (lo > a0) {
                                     const uint32_t r = lo - 1, d = x_rel - s_qo[r];
+#if LVC5_WAIT == 2
+                                    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
                                     if (d < (uint32_t)s_len[r])
                                         deposit_base<PEER>(tv, dp, (int64_t)s_pos[r] + d, ((bb < 8u ? s0 : s1) >> (4u * (bb & 7u))) & 15u,
                                                            (b.qdict >> (8u * ((w >> (2u * bb)) & 3u))) & 255u, chunk_ord + (s_rix[r] & 255u));
@@ -593,6 +638,9 @@ k_deposit_tile5(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
                     }
                 }
 
+#if LVC5_WAIT == 2
+                deposit_parked();                                          // first window staged: the tables are needed from here on
+#endif
                 // ---- column windows of kTabCols (one for amplicon / deep shotgun chunks)
                 const uint32_t chunk_ord0 = dp.ord_base + chunk0;
                 uint32_t* plane = tv.planes[tp.prim_plane];
@@ -779,6 +827,9 @@ k_deposit_tile5(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
                 a0 = a1;
             }
         }
+#if LVC5_WAIT == 2
+        deposit_parked();                                                  // (no-op unless no window was staged)
+#endif
         // ---- reads the tiled path could not take (many runs, long, exotic base codes): general path, one warp each
         __syncthreads();
         const uint32_t n_def = s_misc[6];
