@@ -628,6 +628,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--legs", default="all", help="all | main | comma list of: config3,config4,config5,e2e_api")
     ap.add_argument("--no-numa", action="store_true")
+    ap.add_argument("--device-batch", default="admitted", choices=["admitted", "masked"],
+                    help="admitted: the device-resident batch holds the admitted reads only, as the packer hands it over "
+                         "(ReadBatch.admitted_only / lvc_reads_compact); masked: dropped reads stay in the batch with keep bit0 clear")
     ap.add_argument("--quality-form", default="codes", choices=["codes", "bytes"],
                     help="codes: batches whose qualities take <= 4 values ship 2-bit codes (what process_bam does); bytes: one phred byte per base")
     args = ap.parse_args()
@@ -668,7 +671,8 @@ def main():
 
     # ---- device-resident inputs
     dev = torch.device("cuda", local)
-    dbatch, t_arr = to_device(torch, capi, batch, dev)
+    dev_batch = in_form(batch.admitted_only()) if args.device_batch == "admitted" else batch
+    dbatch, t_arr = to_device(torch, capi, dev_batch, dev)
     stream = torch.cuda.Stream(device=dev)          # a real (non-null) stream: the library launches on it
     torch.cuda.set_stream(stream)
     h = capi.Handle(ref.encode("latin-1"), THRESH["minBQ"], THRESH["minMQ"], device=local, stream=stream.cuda_stream)
@@ -866,6 +870,10 @@ def main():
                     "h2d_note": "small per-read arrays copied in full + payload read in place over PCIe: the 16-byte "
                                 "groups of each chunk's staged extent, counted by the library"},
             "e2e_api": e2e_api,
+            "device_batch": f"{dev_batch.n_reads} reads on the device ({args.device_batch}: " + (
+                "the reads the host admission dropped are left out at pack time, as process_bam does" if args.device_batch == "admitted"
+                else "dropped reads stay in the batch with keep bit0 clear") + f") of {batch.n_reads} presented; value counts "
+                "the aligned bases of every presented read",
             "batch_form": form_of(batch) + "; the algorithmic bytes of the roofline are SURVEY 8d's (1.5 B per base) "
                           "whatever the form; --quality-form bytes ships one phred byte per base",
             "configs": configs,

@@ -43,8 +43,10 @@ constexpr int kTile5CtasPerSM = LVC5_CTAS_PER_SM;
 //   1  before the coverage atomics (extents, payload prefetch and classification precede it)
 //   2  after the first window is staged: the coverage / deletion updates are parked in shared memory, so that headers,
 //      classification AND the payload loads of a chunk overlap the tail of the previous kernel
+// Measured (config 2 / config 5 step): 0: 75.0 / 539 us, 1: 74.1 / 538 us, 2: 77.9 / 582 us -- the parked update costs more
+// than the overlap returns; 1 is the default.
 #ifndef LVC5_WAIT
-#define LVC5_WAIT 2
+#define LVC5_WAIT 1
 #endif
 constexpr int kTask5Runs = 224;                  // runs per task: 7 units per lane, three bit planes hold <= 7
 

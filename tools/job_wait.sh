@@ -1,7 +1,6 @@
-# where the tiled kernel waits for the previous kernel (LVC5_WAIT 0 / 1 / 2): parity of the default build, then config 2 / 5 / 4 per variant
+# the default build (LVC5_WAIT 1): GPU tests, then config 2 with the admitted-only and the keep-masked device batch
 python -m pytest tests -m gpu -x -q > gpurun_out/w_tests.log 2>&1; echo "rc=$?" >> gpurun_out/w_tests.log
 tail -4 gpurun_out/w_tests.log
-B="python bench.py --steps 40 --warmup 3 --no-cpu-baseline --e2e-steps 3 --legs config5,config4"
-$B > gpurun_out/w2.json 2> gpurun_out/w2.err; echo "w2 rc=$?"
-LVC_LIB_PATH=$PWD/exp/lvc_w1.so $B > gpurun_out/w1.json 2> gpurun_out/w1.err; echo "w1 rc=$?"
-LVC_LIB_PATH=$PWD/exp/lvc_w0.so $B > gpurun_out/w0.json 2> gpurun_out/w0.err; echo "w0 rc=$?"
+B="python bench.py --steps 40 --warmup 3 --no-cpu-baseline --e2e-steps 3 --legs main"
+$B --device-batch admitted > gpurun_out/w_adm.json 2> gpurun_out/w_adm.err; echo "adm rc=$?"
+$B --device-batch masked > gpurun_out/w_msk.json 2> gpurun_out/w_msk.err; echo "msk rc=$?"
