@@ -3,9 +3,9 @@
 deposit_tile5.cuh it was attributed to, bucketed by line ranges.  Inlined helpers are attributed to the bucket of the
 nearest preceding tile5 line in address order."""
 import csv, sys
-PH = [(0, 168, "headers+setup"), (169, 209, "extent+prefetch"), (210, 342, "classification"), (343, 417, "run table + cov/dels"),
-      (418, 483, "window/slab setup"), (484, 553, "staging (keys)"), (554, 583, "task fetch"), (584, 619, "pass loop"),
-      (620, 676, "bit-sliced reduce"), (677, 729, "flush + first-seen"), (730, 9999, "deferred/tail")]
+PH = [(0, 179, "headers+setup"), (180, 225, "extent+prefetch"), (226, 359, "classification"), (360, 460, "run table + cov/dels"),
+      (461, 526, "window/slab setup"), (527, 645, "staging (keys)"), (646, 677, "task fetch"), (678, 710, "pass loop"),
+      (711, 767, "bit-sliced reduce"), (768, 834, "flush + first-seen"), (835, 9999, "deferred/tail")]
 def phase(ln):
     for a, b, n in PH:
         if a <= ln <= b: return n
