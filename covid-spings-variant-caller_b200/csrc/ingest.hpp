@@ -10,6 +10,7 @@
 
 #include <atomic>
 #include <memory>
+#include <functional>
 #include <mutex>
 #include <chrono>
 #include <fstream>
@@ -147,7 +148,12 @@ struct Bytes {
     const uint8_t& operator[](size_t i) const { return p[i]; }
 };
 
-static std::string bgzf_inflate(const Bytes& file, RawBuf& out, int n_threads) {
+// `follower(raw, total, need)`, if given, runs on a thread of its own WHILE the blocks are inflated: need(end) blocks until
+// every byte below `end` is in place (false: inflation failed, give up).  The BAM record walk -- a chain of dependent hops
+// that no second thread can help with -- hides behind the inflate that way.
+using NeedFn = std::function<bool(size_t)>;
+using FollowerFn = std::function<void(const uint8_t*, size_t, const NeedFn&)>;
+static std::string bgzf_inflate(const Bytes& file, RawBuf& out, int n_threads, const FollowerFn& follower = nullptr) {
     struct Blk { size_t coff, clen, uoff; uint32_t ulen, crc; };
     std::vector<Blk> blks;
     size_t i = 0, n = file.size(), total = 0;
@@ -171,15 +177,19 @@ static std::string bgzf_inflate(const Bytes& file, RawBuf& out, int n_threads) {
         i += bsize + 1;
     }
     if (!out.resize(total)) return fail("out of host memory");
+    constexpr size_t kGrab = 16;                                 // blocks (~1 MB) per grab
+    const size_t n_grabs = (blks.size() + kGrab - 1) / kGrab;
+    std::unique_ptr<std::atomic<uint8_t>[]> done(new std::atomic<uint8_t>[n_grabs ? n_grabs : 1]);
+    for (size_t g = 0; g < n_grabs; ++g) done[g].store(0, std::memory_order_relaxed);
     std::atomic<size_t> next{0};
     std::atomic<bool> bad{false};
     auto work = [&]() {
         z_stream zs; memset(&zs, 0, sizeof zs);                 // one inflate state per thread, reset per block
         if (inflateInit2(&zs, -15) != Z_OK) { bad = true; return; }
         for (;;) {
-            const size_t k0 = next.fetch_add(16);                // 16 blocks (~1 MB) per grab
+            const size_t k0 = next.fetch_add(kGrab);
             if (k0 >= blks.size() || bad) break;
-            for (size_t k = k0; k < std::min(blks.size(), k0 + 16); ++k) {
+            for (size_t k = k0; k < std::min(blks.size(), k0 + kGrab); ++k) {
                 const Blk& b = blks[k];
                 if (b.ulen == 0) continue;
                 inflateReset(&zs);
@@ -189,15 +199,38 @@ static std::string bgzf_inflate(const Bytes& file, RawBuf& out, int n_threads) {
                 if (rc != Z_STREAM_END || zs.avail_out != 0) { bad = true; break; }
                 if ((uint32_t)crc32(crc32(0L, Z_NULL, 0), &out[b.uoff], b.ulen) != b.crc) { bad = true; break; }   // htslib checks it too
             }
+            if (!bad) done[k0 / kGrab].store(1, std::memory_order_release);
         }
         inflateEnd(&zs);
     };
     n_threads = std::max(1, std::min(n_threads, 64));
     std::vector<std::thread> th;
+    std::thread follow;
+    if (follower && n_threads > 1) {
+        follow = std::thread([&]() {
+            size_t ready = 0, g = 0;                              // bytes below `ready` are in place; g = next grab to wait for
+            const NeedFn need = [&](size_t end) -> bool {
+                end = std::min(end, total);
+                while (ready < end) {
+                    if (g >= n_grabs) { ready = total; break; }
+                    while (!done[g].load(std::memory_order_acquire)) {
+                        if (bad.load()) return false;
+                        std::this_thread::yield();
+                    }
+                    ++g;
+                    ready = g * kGrab < blks.size() ? blks[g * kGrab].uoff : total;
+                }
+                return true;
+            };
+            follower(out.data(), total, need);
+        });
+    }
     for (int t = 1; t < n_threads; ++t) th.emplace_back(work);
     work();
     for (auto& t : th) t.join();
+    if (follow.joinable()) follow.join();
     if (bad) return fail("BGZF inflate failed (corrupt block or CRC mismatch)");
+    if (follower && n_threads <= 1) follower(out.data(), total, [](size_t) { return true; });
     return "";
 }
 
@@ -316,13 +349,34 @@ static int compact(lvc_reads* r, int n_threads) {
 }
 
 // pack `recs` (already in coordinate order) into the SoA arrays of `r`
-static std::string pack(lvc_reads* r, const std::vector<Rec>& recs, int min_mapq, int max_depth, int n_threads,
+static std::string pack(lvc_reads* r, const Rec* recs, const size_t n, int min_mapq, int max_depth, int n_threads,
                         int overlap_model, PhaseTimer& timer) {
-    const size_t n = recs.size();
-    std::vector<uint64_t> coff(n + 1, 0), soff(n + 1, 0);
-    for (size_t i = 0; i < n; ++i) {
-        coff[i + 1] = coff[i] + recs[i].n_cig;
-        soff[i + 1] = soff[i] + recs[i].l_seq + (recs[i].l_seq & 1u);
+    n_threads = std::max(1, std::min(n_threads, 64));
+    // offsets: a two-level scan over the records (sum per slice, exclusive scan of the slices, prefix inside each slice)
+    std::unique_ptr<uint64_t[]> coff(new uint64_t[n + 1]), soff(new uint64_t[n + 1]);
+    {
+        const int nt = n < (1u << 16) ? 1 : n_threads;
+        std::vector<uint64_t> csum((size_t)nt + 1, 0), ssum((size_t)nt + 1, 0);
+        auto slice = [&](int t, size_t& a, size_t& b) { a = n * (size_t)t / (size_t)nt; b = n * ((size_t)t + 1) / (size_t)nt; };
+        auto run = [&](auto&& fn) {
+            std::vector<std::thread> th;
+            for (int t = 1; t < nt; ++t) th.emplace_back(fn, t);
+            fn(0);
+            for (auto& x : th) x.join();
+        };
+        run([&](int t) {
+            size_t a, b; slice(t, a, b);
+            uint64_t c = 0, q = 0;
+            for (size_t i = a; i < b; ++i) { c += recs[i].n_cig; q += recs[i].l_seq + (recs[i].l_seq & 1u); }
+            csum[(size_t)t + 1] = c; ssum[(size_t)t + 1] = q;
+        });
+        for (int t = 0; t < nt; ++t) { csum[(size_t)t + 1] += csum[(size_t)t]; ssum[(size_t)t + 1] += ssum[(size_t)t]; }
+        run([&](int t) {
+            size_t a, b; slice(t, a, b);
+            uint64_t c = csum[(size_t)t], q = ssum[(size_t)t];
+            for (size_t i = a; i < b; ++i) { coff[i] = c; soff[i] = q; c += recs[i].n_cig; q += recs[i].l_seq + (recs[i].l_seq & 1u); }
+        });
+        coff[n] = csum[(size_t)nt]; soff[n] = ssum[(size_t)nt];
     }
     if (coff[n] > 0xFFFFFFFFull) return fail("too many CIGAR operations in one batch");
     r->n = (uint32_t)n; r->n_cigar = coff[n]; r->n_qual = soff[n];
@@ -382,7 +436,6 @@ static std::string pack(lvc_reads* r, const std::vector<Rec>& recs, int min_mapq
             }
         }
     };
-    n_threads = std::max(1, std::min(n_threads, 64));
     std::vector<std::thread> th;
     for (int t = 1; t < n_threads; ++t) th.emplace_back(work);
     work();
@@ -422,49 +475,58 @@ static std::string validate(const Rec& x, const char* what) {
 
 static std::string read_bam(lvc_reads* r, const Bytes& file, const char* contig, int min_mapq, int max_depth,
                             int n_threads, RawBuf& raw, int overlap_model, PhaseTimer& timer) {
-    std::string e = bgzf_inflate(file, raw, n_threads);
-    if (!e.empty()) return e;
-    timer.mark("bgzf inflate");
-    if (raw.size() < 12 || memcmp(raw.data(), "BAM\1", 4) != 0) return fail("bad BAM magic");
-    const int32_t l_text = rdi32(&raw[4]);
-    if (l_text < 0 || (size_t)l_text > raw.size() - 12) return fail("truncated BAM header");
-    size_t off = 8 + (size_t)l_text;
-    if (off + 4 > raw.size()) return fail("truncated BAM header");
-    const int32_t n_ref = rdi32(&raw[off]); off += 4;
-    if (n_ref < 0) return fail("corrupt BAM header");
-    for (int32_t k = 0; k < n_ref; ++k) {
-        if (off + 8 > raw.size()) return fail("truncated BAM header");
-        const int32_t l_name = rdi32(&raw[off]);
-        if (l_name < 1 || (size_t)l_name > raw.size() - off - 8) return fail("corrupt BAM header");
-        std::string name((const char*)&raw[off + 4], (size_t)std::max(0, l_name - 1));
-        const int32_t l_ref = rdi32(&raw[off + 4 + l_name]);
-        r->contigs.push_back({name, l_ref});
-        off += 8 + l_name;
-    }
+    // header + pass 1 (serial, a hop per record: where the records of this contig start) follow the inflate threads
     int tid = -1;
-    for (size_t k = 0; k < r->contigs.size(); ++k)
-        if ((!contig || !*contig) ? k == 0 : r->contigs[k].first == contig) { tid = (int)k; break; }
-    if (tid < 0) return fail("invalid contig `%s`", contig ? contig : "");
-    r->contig = r->contigs[tid].first; r->contig_len = r->contigs[tid].second;
-    // pass 1 (serial, a hop per record): where the records of this contig start
     std::vector<size_t> offs;
-    offs.reserve(raw.size() / 256);
-    // (every hop is a dependent cache miss; records of one run have similar sizes, so the line a few records ahead is
-    // requested by extrapolation: right most of the time, harmless when not)
-    while (off + 4 <= raw.size()) {
-        const int32_t bs = rdi32(&raw[off]);
-        if (bs < 32 || off + 4 + (size_t)bs > raw.size()) return fail("truncated BAM record");
-        const size_t step = 4 + (size_t)bs;
-        if (off + 12 * step + 64 < raw.size()) {
-            __builtin_prefetch(&raw[off + 6 * step]); __builtin_prefetch(&raw[off + 6 * step + 64]);
-            __builtin_prefetch(&raw[off + 12 * step]); __builtin_prefetch(&raw[off + 12 * step + 64]);
+    std::string scan_err;
+    const FollowerFn scan = [&](const uint8_t* raw_p, size_t raw_n, const NeedFn& need) {
+        auto bail = [&](const std::string& m) { scan_err = m; };
+        if (!need(12)) return;
+        if (raw_n < 12 || memcmp(raw_p, "BAM\1", 4) != 0) return bail(fail("bad BAM magic"));
+        const int32_t l_text = rdi32(raw_p + 4);
+        if (l_text < 0 || (size_t)l_text > raw_n - 12) return bail(fail("truncated BAM header"));
+        size_t off = 8 + (size_t)l_text;
+        if (off + 4 > raw_n) return bail(fail("truncated BAM header"));
+        if (!need(off + 4)) return;
+        const int32_t n_ref = rdi32(raw_p + off); off += 4;
+        if (n_ref < 0) return bail(fail("corrupt BAM header"));
+        for (int32_t k = 0; k < n_ref; ++k) {
+            if (off + 8 > raw_n) return bail(fail("truncated BAM header"));
+            if (!need(off + 4)) return;
+            const int32_t l_name = rdi32(raw_p + off);
+            if (l_name < 1 || (size_t)l_name > raw_n - off - 8) return bail(fail("corrupt BAM header"));
+            if (!need(off + 8 + (size_t)l_name)) return;
+            std::string name((const char*)raw_p + off + 4, (size_t)std::max(0, l_name - 1));
+            const int32_t l_ref = rdi32(raw_p + off + 4 + l_name);
+            r->contigs.push_back({name, l_ref});
+            off += 8 + l_name;
         }
-        if (rdi32(&raw[off + 4]) == tid) offs.push_back(off);
-        off += step;
-    }
-    timer.mark("record offsets");
+        for (size_t k = 0; k < r->contigs.size(); ++k)
+            if ((!contig || !*contig) ? k == 0 : r->contigs[k].first == contig) { tid = (int)k; break; }
+        if (tid < 0) return bail(fail("invalid contig `%s`", contig ? contig : ""));
+        r->contig = r->contigs[tid].first; r->contig_len = r->contigs[tid].second;
+        offs.reserve(raw_n / 256);
+        // (every hop is a dependent cache miss; records of one run have similar sizes, so the line a few records ahead
+        // is requested by extrapolation: right most of the time, harmless when not)
+        while (off + 4 <= raw_n) {
+            if (!need(off + 8)) return;
+            const int32_t bs = rdi32(raw_p + off);
+            if (bs < 32 || off + 4 + (size_t)bs > raw_n) return bail(fail("truncated BAM record"));
+            const size_t step = 4 + (size_t)bs;
+            if (off + 12 * step + 64 < raw_n) {
+                __builtin_prefetch(raw_p + off + 6 * step); __builtin_prefetch(raw_p + off + 6 * step + 64);
+                __builtin_prefetch(raw_p + off + 12 * step); __builtin_prefetch(raw_p + off + 12 * step + 64);
+            }
+            if (rdi32(raw_p + off + 4) == tid) offs.push_back(off);
+            off += step;
+        }
+    };
+    std::string e = bgzf_inflate(file, raw, n_threads, scan);
+    if (!e.empty()) return e;
+    if (!scan_err.empty()) return scan_err;
+    timer.mark("bgzf inflate + walk");
     // pass 2 (threads): decode and validate; the error of the first bad record wins
-    std::vector<Rec> recs(offs.size());
+    std::unique_ptr<Rec[]> recs(new Rec[offs.size() ? offs.size() : 1]);     // not zero-filled: every slot is written below
     std::atomic<size_t> next{0};
     std::mutex emu;
     size_t err_at = offs.size();
@@ -518,7 +580,7 @@ static std::string read_bam(lvc_reads* r, const Bytes& file, const char* contig,
     }
     if (err_at < offs.size()) return err_msg;
     timer.mark("record scan");
-    return pack(r, recs, min_mapq, max_depth, n_threads, overlap_model, timer);
+    return pack(r, recs.get(), offs.size(), min_mapq, max_depth, n_threads, overlap_model, timer);
 }
 
 static inline int64_t parse_int(const char* p, size_t n) {
@@ -688,7 +750,7 @@ static std::string read_sam(lvc_reads* r, const Bytes& file, const char* contig,
         recs.push_back(t.rec);
     }
     timer.mark("validate");
-    return pack(r, recs, min_mapq, max_depth, n_threads, overlap_model, timer);
+    return pack(r, recs.data(), recs.size(), min_mapq, max_depth, n_threads, overlap_model, timer);
 }
 
 }  // namespace ingest
