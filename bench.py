@@ -863,7 +863,7 @@ def main():
                          "timing": "per-kernel CUDA events (library, launching stream) over a second pass of the same "
                                    "K steps; the first pass (ms_per_step) has no events between the kernels",
                          "ms_per_step_with_kernel_events": ms_ev / args.steps,
-                         "step_frac": (alg_bytes / (ms / args.steps * 1e-3) / 1e9) / peak,
+                         "step_frac": ((lb + 52 * G if args.device_batch == "admitted" else alg_bytes) / (ms / args.steps * 1e-3) / 1e9) / peak,
                          "other_kernels_ms_per_step": {"general_deposit": gen_ms / args.steps,
                                                        "genotype": geno_ms / args.steps}},
             "long_pass": {"steps": n_long, "ms_per_step": ms_long / n_long, "ms_total": ms_long,
