@@ -192,6 +192,13 @@ void lvc_reads_free(lvc_reads* r);
  * allocation is; a sub-allocation that ends exactly at the end of a mapped range is not).  NVTX ranges named after the
  * entry points (lvc_read_alignments, lvc_push_batch*, lvc_genotype*, lvc_reduce_tables) are emitted when a tool is
  * attached. */
+/* How lvc_push_batch moves a host batch: the per-read arrays are copied; the payload (seq4 + qual) of a batch WITHOUT
+ * dropped reads (lvc_reads_compact / every keep bit0 set) is copied in bulk, one copy per array; the payload of a batch
+ * with dropped reads is read in place over PCIe when the caller's arrays are page-locked (only the chunks with admitted
+ * reads are touched), else the byte ranges of the admitted reads are copied.  Environment switches for experiments:
+ * LVC_ZERO_COPY=0 (never read in place), LVC_DENSE_BULK_COPY=0 (always read page-locked payload in place),
+ * LVC_ZC_HEADERS=1 (per-read arrays other than `keep` read in place too), LVC_QUALITY_CODES=0 (the ingest keeps the byte
+ * form). */
 int lvc_push_batch(lvc_handle* h, const lvc_batch* host_batch);
 int lvc_push_batch_device(lvc_handle* h, const lvc_batch* device_batch);
 int lvc_set_impl(lvc_handle* h, int impl);
