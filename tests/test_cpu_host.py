@@ -289,3 +289,83 @@ def test_native_ingest_random_files_match_python_readers(lib, tmp_path):
             seen_kept += int((nb.keep & 1).sum())
             nat.close()
     assert seen_reads > 500 and 0 < seen_kept < seen_reads          # the comparison saw real, partly filtered data
+
+
+def _rewrite_bgzf(src: str, dst: str, level: int, strategy: int, block_sizes):
+    """the same uncompressed bytes as BGZF blocks of the given sizes (cycled), deflated with (level, strategy)"""
+    import struct, zlib
+    from lvc_b200 import samio
+    body = samio._bgzf_decompress(src)
+    with open(dst, "wb") as fh:
+        i = k = 0
+        while i < len(body):
+            chunk = body[i:i + block_sizes[k % len(block_sizes)]]
+            i += len(chunk); k += 1
+            comp = zlib.compressobj(level, zlib.DEFLATED, -15, 8, strategy)
+            cdata = comp.compress(chunk) + comp.flush()
+            assert len(cdata) + 25 < 65536
+            fh.write(b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", len(cdata) + 25))
+            fh.write(cdata)
+            fh.write(struct.pack("<II", zlib.crc32(chunk) & 0xFFFFFFFF, len(chunk)))
+        fh.write(samio._BGZF_EOF)
+
+
+def test_native_inflate_every_deflate_form(lib, tmp_path, monkeypatch):
+    """the ingest's own DEFLATE decoder (csrc/inflate_fast.hpp) on stored, fixed-code and dynamic-code blocks of every size
+    class (1 byte ... 0xFF00, i.e. blocks that never enter its hot loop and blocks that live in it), against zlib's
+    inflate (LVC_INFLATE=zlib) and the pure-Python reader; corrupted and truncated blocks are rejected, not misread"""
+    import zlib
+    from lvc_b200 import samio, synth, capi, packing
+    rejected = (capi.LvcError, packing.UnsupportedInput)
+    ref, batch = synth.amplicon_sample(seed=5, n_pairs=4000)[:2]
+    src = str(tmp_path / "src.bam")
+    samio.write_bam_batch(src, ("chrS", len(ref)), batch, level=6)
+    _, want = samio.read_alignments(src, None, 20)
+
+    def native(path):
+        nat = samio.read_alignments_native(path, None, 20, n_threads=3)
+        nb = nat.as_readbatch()
+        got = {f: np.array(getattr(nb, f)[:len(getattr(want, f))]) for f in ("pos", "flag", "mapq", "keep", "cigar_off", "seq_off")}
+        got["cigar"] = np.array(nb.cigar[:nb.n_cigar]); got["qual"] = np.array(nb.qual[:nb.n_qual])
+        got["seq4"] = np.array(nb.seq4[:nb.n_qual // 2]); got["n"] = nat.n_reads
+        nat.close()
+        return got
+
+    forms = [(0, zlib.Z_DEFAULT_STRATEGY, [0xFF00]),                      # stored blocks
+             (6, zlib.Z_FIXED, [0xFF00, 300, 1]),                         # fixed Huffman code, tiny blocks too
+             (1, zlib.Z_DEFAULT_STRATEGY, [0xFF00, 17, 4096]),
+             (9, zlib.Z_DEFAULT_STRATEGY, [0xFF00]),
+             (6, zlib.Z_HUFFMAN_ONLY, [0x8000, 281, 282, 283]),           # literals only; sizes around the hot loop's margin
+             (6, zlib.Z_RLE, [0xFF00, 5000])]                             # distance-1 matches
+    for level, strategy, sizes in forms:
+        path = str(tmp_path / f"f{level}_{strategy}.bam")
+        _rewrite_bgzf(src, path, level, strategy, sizes)
+        monkeypatch.delenv("LVC_INFLATE", raising=False)
+        fast = native(path)
+        monkeypatch.setenv("LVC_INFLATE", "zlib")
+        slow = native(path)
+        assert fast["n"] == slow["n"] == want.n_reads, (level, strategy)
+        for f in fast:
+            assert np.array_equal(fast[f], slow[f]), (level, strategy, f)
+        for f in ("pos", "flag", "mapq", "keep", "cigar_off", "seq_off"):
+            assert fast[f].tolist() == getattr(want, f).tolist(), (level, strategy, f)
+        assert fast["qual"].tolist() == want.qual[:want.n_qual].tolist()
+    monkeypatch.delenv("LVC_INFLATE", raising=False)
+    # a flipped bit anywhere in a deflate stream, or a block cut short, is an error (the decoder's own checks or the CRC)
+    good = open(src, "rb").read()
+    rng = np.random.default_rng(3)
+    for trial in range(12):
+        bad = bytearray(good)
+        at = int(rng.integers(18, len(good) - 60))
+        bad[at] ^= 1 << int(rng.integers(0, 8))
+        p = str(tmp_path / "bad.bam")
+        open(p, "wb").write(bytes(bad))
+        try:
+            got = native(p)
+        except rejected:
+            continue
+        # the flip hit a header byte the reader does not interpret (gzip MTIME / XFL / OS): the data must be intact
+        assert got["qual"].tolist() == want.qual[:want.n_qual].tolist(), at
+    with pytest.raises(rejected):
+        open(str(tmp_path / "cut.bam"), "wb").write(good[:len(good) // 2])
+        native(str(tmp_path / "cut.bam"))
