@@ -440,58 +440,94 @@ static std::string pack(lvc_reads* r, const Rec* recs, const size_t n, int min_m
     std::unique_ptr<int32_t[]> mpos, tlen;
     std::unique_ptr<int8_t[]> mref;
     if (overlap_model != LVC_OVERLAP_OFF && n) { mpos.reset(new int32_t[n]); tlen.reset(new int32_t[n]); mref.reset(new int8_t[n]); }
+    // Two passes over the records, each on all threads.  Pass A fills what the admission reads (position, flag, mapping
+    // quality, CIGAR, offsets, mate fields); pass B copies the payload (1.5 bytes per base) and makes the A/C/G/T hint.
+    // The admission (htslib's bam_plp_push rule and the mate-overlap hash: sequential by definition) runs on a thread of
+    // its own beside pass B -- it never looks at a base or a quality; the quality rewrites of the overlapping pairs it
+    // finds are listed and applied, on all threads, once the payload is in place.
     std::atomic<bool> any_pair_seen{false};
-    std::atomic<size_t> next{0};
-    auto work = [&]() {
-        for (;;) {
-            const size_t b0 = next.fetch_add(4096);
-            if (b0 >= n) return;
-            const size_t b1 = std::min(n, b0 + 4096);
-            bool pair_here = false;
-            if (mpos)
-                for (size_t i = b0; i < b1; ++i) {
-                    mpos[i] = recs[i].next_pos; tlen[i] = recs[i].tlen; mref[i] = recs[i].next_ref;
-                    pair_here |= (recs[i].flag & 0x3u) == 0x3u && !(recs[i].flag & 0x8u);
-                }
-            if (pair_here) any_pair_seen.store(true, std::memory_order_relaxed);
-            for (size_t i = b0; i < b1; ++i) {
-                const Rec& x = recs[i];
-                r->pos[i] = x.pos; r->flag[i] = x.flag; r->mapq[i] = x.mapq;
-                r->cigar_off[i] = (uint32_t)coff[i]; r->seq_off[i] = soff[i];
-                memcpy(r->cigar + coff[i], x.cig, (size_t)x.n_cig * 4);
-                const size_t nb = (x.l_seq + 1) / 2;
-                uint8_t* sq = r->seq4 + soff[i] / 2;
-                memcpy(sq, x.seq, nb);
-                uint8_t* q = r->qual + soff[i];
-                memcpy(q, x.qual, x.l_seq);
-                // A/C/G/T-only hint: two bases per table lookup (the pad nibble of an odd-length read is not a base)
-                uint32_t bad_b = 0;
-                const size_t full = x.l_seq / 2;
-                for (size_t k = 0; k < full; ++k) bad_b |= kNotAcgtPair.t[sq[k]];
-                if (x.l_seq & 1) { bad_b |= kNotAcgtPair.t[(sq[nb - 1] & 0xF0u) | 1u]; q[x.l_seq] = 0; sq[nb - 1] &= 0xF0; }
-                const bool acgt = bad_b == 0;
-                r->keep[i] = acgt ? 2 : 0;          // bit1: ACGT-only hint; bit0 is OR-ed in after admission
+    auto run_all = [&](auto&& fn, int reserve) {
+        std::atomic<size_t> next{0};
+        auto work = [&]() {
+            for (;;) {
+                const size_t b0 = next.fetch_add(4096);
+                if (b0 >= n) return;
+                fn(b0, std::min(n, b0 + 4096));
             }
-        }
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < std::max(1, n_threads - reserve); ++t) th.emplace_back(work);
+        work();
+        for (auto& t : th) t.join();
     };
-    std::vector<std::thread> th;
-    for (int t = 1; t < n_threads; ++t) th.emplace_back(work);
-    work();
-    for (auto& t : th) t.join();
+    run_all([&](size_t b0, size_t b1) {
+        bool pair_here = false;
+        if (mpos)
+            for (size_t i = b0; i < b1; ++i) {
+                mpos[i] = recs[i].next_pos; tlen[i] = recs[i].tlen; mref[i] = recs[i].next_ref;
+                pair_here |= (recs[i].flag & 0x3u) == 0x3u && !(recs[i].flag & 0x8u);
+            }
+        if (pair_here) any_pair_seen.store(true, std::memory_order_relaxed);
+        for (size_t i = b0; i < b1; ++i) {
+            const Rec& x = recs[i];
+            r->pos[i] = x.pos; r->flag[i] = x.flag; r->mapq[i] = x.mapq;
+            r->cigar_off[i] = (uint32_t)coff[i]; r->seq_off[i] = soff[i];
+            memcpy(r->cigar + coff[i], x.cig, (size_t)x.n_cig * 4);
+        }
+    }, 0);
     r->cigar_off[n] = (uint32_t)coff[n];
     r->seq_off[n] = soff[n];
-    timer.mark("pack");
+    timer.mark("pack: per-read arrays");
     std::vector<uint8_t> adm(n ? n : 1);
     const bool any_pair = any_pair_seen.load();
-    auto name = [&](uint32_t i) { return lvc_overlap::NameKey{recs[i].name, recs[i].l_name}; };
-    const int rc = lvc_overlap::admit_core((uint32_t)n, r->pos, r->flag, r->mapq, r->cigar_off, r->cigar, r->seq_off, r->seq4,
-                                           r->qual, name, any_pair ? mpos.get() : nullptr, any_pair ? mref.get() : nullptr,
-                                           any_pair ? tlen.get() : nullptr, min_mapq, max_depth,
-                                           any_pair ? overlap_model : LVC_OVERLAP_OFF, adm.data(), &r->overlap_pairs,
-                                           &r->overlap_bases);
-    timer.mark("admit + overlaps");
+    std::vector<lvc_overlap::PendingTweak> pend;
+    int rc = 0;
+    auto admit = [&]() {
+        auto name = [&](uint32_t i) { return lvc_overlap::NameKey{recs[i].name, recs[i].l_name}; };
+        rc = lvc_overlap::admit_core((uint32_t)n, r->pos, r->flag, r->mapq, r->cigar_off, r->cigar, r->seq_off, r->seq4,
+                                     r->qual, name, any_pair ? mpos.get() : nullptr, any_pair ? mref.get() : nullptr,
+                                     any_pair ? tlen.get() : nullptr, min_mapq, max_depth,
+                                     any_pair ? overlap_model : LVC_OVERLAP_OFF, adm.data(), nullptr, nullptr, &pend);
+    };
+    std::thread admit_thread;
+    if (n_threads > 1) admit_thread = std::thread(admit);
+    run_all([&](size_t b0, size_t b1) {
+        for (size_t i = b0; i < b1; ++i) {
+            const Rec& x = recs[i];
+            const size_t nb = (x.l_seq + 1) / 2;
+            uint8_t* sq = r->seq4 + soff[i] / 2;
+            memcpy(sq, x.seq, nb);
+            uint8_t* q = r->qual + soff[i];
+            memcpy(q, x.qual, x.l_seq);
+            // A/C/G/T-only hint: two bases per table lookup (the pad nibble of an odd-length read is not a base)
+            uint32_t bad_b = 0;
+            const size_t full = x.l_seq / 2;
+            for (size_t k = 0; k < full; ++k) bad_b |= kNotAcgtPair.t[sq[k]];
+            if (x.l_seq & 1) { bad_b |= kNotAcgtPair.t[(sq[nb - 1] & 0xF0u) | 1u]; q[x.l_seq] = 0; sq[nb - 1] &= 0xF0; }
+            const bool acgt = bad_b == 0;
+            r->keep[i] = acgt ? 2 : 0;          // bit1: ACGT-only hint; bit0 is OR-ed in after admission
+        }
+    }, n_threads > 2 ? 1 : 0);
+    if (admit_thread.joinable()) admit_thread.join(); else admit();
+    timer.mark("pack: payload | admission");
     if (rc == LVC_EUNSORTED) return fail("reads are not coordinate sorted");
     if (rc) return fail("admission failed (%d)", rc);
+    r->overlap_pairs = 0; r->overlap_bases = 0;
+    if (!pend.empty()) {
+        const size_t np = pend.size();
+        const int nt = (int)std::min<size_t>((size_t)n_threads, (np + 1023) / 1024);
+        std::vector<uint64_t> pr((size_t)nt, 0), bs((size_t)nt, 0);
+        std::vector<std::thread> th;
+        auto part = [&](int t) {
+            lvc_overlap::apply_pending(pend.data(), np * (size_t)t / (size_t)nt, np * ((size_t)t + 1) / (size_t)nt, r->pos, r->cigar_off,
+                                       r->cigar, r->seq_off, r->seq4, r->qual, overlap_model, &pr[(size_t)t], &bs[(size_t)t]);
+        };
+        for (int t = 1; t < nt; ++t) th.emplace_back(part, t);
+        part(0);
+        for (auto& t : th) t.join();
+        for (int t = 0; t < nt; ++t) { r->overlap_pairs += pr[(size_t)t]; r->overlap_bases += bs[(size_t)t]; }
+    }
+    timer.mark("mate-overlap rewrites");
     for (size_t i = 0; i < n; ++i) r->keep[i] |= adm[i];
     timer.mark("keep bits");
     r->n_threads = n_threads;

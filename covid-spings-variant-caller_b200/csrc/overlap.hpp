@@ -187,13 +187,22 @@ struct NameHash {
     }
 };
 
+// a pair of overlapping mates found by the admission pass whose quality rewrite is still to be done (apply_pending)
+struct PendingTweak {
+    uint32_t a, b;       // read indices: `a` was buffered first
+    bool a_keeps;
+};
+
 // Admission (SURVEY B2 + B4, htslib bam_plp_push / bam_plp_next) with the overlap hash (B5).
 // name(i) -> NameKey of read i; mate_* may be null when overlap_model == LVC_OVERLAP_OFF.
+// `pending` != nullptr: the quality rewrites are not done here but listed (the admission itself never looks at a base or
+// a quality, so it can run while the payload is still being packed); seq4 / qual are not touched then.
 template <class NameFn>
 static int admit_core(uint32_t n, const int32_t* pos, const uint16_t* flag, const uint8_t* mapq, const uint32_t* cigar_off,
                       const uint32_t* cigar, const uint64_t* seq_off, const uint8_t* seq4, uint8_t* qual, NameFn name,
                       const int32_t* mate_pos, const int8_t* mate_ref, const int32_t* tlen, int min_mq, int max_depth,
-                      int overlap_model, uint8_t* keep, uint64_t* n_pairs, uint64_t* n_bases) {
+                      int overlap_model, uint8_t* keep, uint64_t* n_pairs, uint64_t* n_bases,
+                      std::vector<PendingTweak>* pending = nullptr) {
     constexpr uint32_t kFilter = 0x4u | 0x100u | 0x200u | 0x400u;
     const bool ov = overlap_model != LVC_OVERLAP_OFF;
     std::vector<uint32_t> ring;            // buffered reads per end position
@@ -276,8 +285,11 @@ static int admit_core(uint32_t n, const int32_t* pos, const uint16_t* flag, cons
                     const uint32_t a = it->second;
                     olap.erase(it);
                     const bool a_keeps = (wang_hash(x31_hash(name(a).p, name(a).n)) & 1u) != 0;
-                    const uint64_t t = tweak(read_ref(a), read_ref(i), overlap_model, a_keeps);
-                    if (t) { ++pairs; bases += t; }
+                    if (pending) pending->push_back(PendingTweak{a, i, a_keeps});
+                    else {
+                        const uint64_t t = tweak(read_ref(a), read_ref(i), overlap_model, a_keeps);
+                        if (t) { ++pairs; bases += t; }
+                    }
                 }
             }
         }
@@ -318,6 +330,28 @@ static int admit_core(uint32_t n, const int32_t* pos, const uint16_t* flag, cons
     if (n_pairs) *n_pairs = pairs;
     if (n_bases) *n_bases = bases;
     return LVC_OK;
+}
+
+// The rewrites admit_core listed.  A read takes part in at most one of them (the buffered mate leaves the hash when its
+// partner arrives, and the partner never enters it), so they are independent: entries [k0, k1) can be applied by any thread.
+static void apply_pending(const PendingTweak* list, size_t k0, size_t k1, const int32_t* pos, const uint32_t* cigar_off,
+                          const uint32_t* cigar, const uint64_t* seq_off, const uint8_t* seq4, uint8_t* qual, int overlap_model,
+                          uint64_t* n_pairs, uint64_t* n_bases) {
+    auto read_ref = [&](uint32_t i) {
+        ReadRef r;
+        r.pos = pos[i]; r.cig = cigar + cigar_off[i]; r.n_cig = cigar_off[i + 1] - cigar_off[i];
+        r.seq4 = seq4 + (seq_off[i] >> 1); r.qual = qual + seq_off[i];
+        int64_t lq = 0;
+        for (uint32_t k = 0; k < r.n_cig; ++k) { const uint32_t op = r.cig[k] & 15u; if (op == 0 || op == 1 || op == 4 || op == 7 || op == 8) lq += r.cig[k] >> 4; }
+        r.l_qseq = lq;
+        return r;
+    };
+    uint64_t pairs = 0, bases = 0;
+    for (size_t k = k0; k < k1; ++k) {
+        const uint64_t t = tweak(read_ref(list[k].a), read_ref(list[k].b), overlap_model, list[k].a_keeps);
+        if (t) { ++pairs; bases += t; }
+    }
+    *n_pairs = pairs; *n_bases = bases;
 }
 
 }  // namespace lvc_overlap
