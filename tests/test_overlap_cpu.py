@@ -193,3 +193,23 @@ def test_native_ingest_and_python_reader_agree_on_overlaps(lib, tmp_path, model)
     _, py2 = samio.read_sam(sam, None, 0, overlap_model=model)
     assert np.array_equal(nb2.qual[:py2.n_qual], py2.qual[:py2.n_qual]) and np.array_equal(nb2.pos, py2.pos)
     nat2.close()
+
+
+def test_native_ingest_many_overlapping_pairs(lib, tmp_path):
+    """thousands of overlapping pairs: the native ingest lists the rewrites while the admission pass runs beside the payload
+    copy and applies them on several threads afterwards; the result is the pure-Python reader's, byte for byte"""
+    from lvc_b200 import samio, capi
+    reads = make_pairs(11, n_pairs=4200, with_extras=True)
+    for r in reads:
+        r.qual = [min(q, 93) for q in r.qual]
+    recs = [(r.flag, r.pos, r.mapq, r.cigar, r.seq, r.qual, r.name, r.mpos, r.mref, r.tlen) for r in reads]
+    bam = str(tmp_path / "many.bam")
+    samio.write_bam(bam, [("chrT", 1000), ("chrU", 500)], recs)
+    _, py = samio.read_bam(bam, None, 0)
+    for nt in (1, 2, 7):
+        nat = capi.NativeReads(bam, None, 0, n_threads=nt)
+        nb = nat.as_readbatch()
+        assert nat.overlap_pairs == py.overlap_pairs > 2048 and nat.overlap_bases == py.overlap_bases, nt
+        assert np.array_equal(nb.qual[:py.n_qual], py.qual[:py.n_qual]), nt
+        assert np.array_equal(nb.keep, py.keep), nt
+        nat.close()
