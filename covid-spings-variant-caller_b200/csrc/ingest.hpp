@@ -439,7 +439,8 @@ static std::string pack(lvc_reads* r, const Rec* recs, const size_t n, int min_m
     // pair up and skips the overlap bookkeeping altogether)
     std::unique_ptr<int32_t[]> mpos, tlen;
     std::unique_ptr<int8_t[]> mref;
-    if (overlap_model != LVC_OVERLAP_OFF && n) { mpos.reset(new int32_t[n]); tlen.reset(new int32_t[n]); mref.reset(new int8_t[n]); }
+    std::unique_ptr<uint64_t[]> nhash;         // hash of every read name, for the admission pass's name table
+    if (overlap_model != LVC_OVERLAP_OFF && n) { mpos.reset(new int32_t[n]); tlen.reset(new int32_t[n]); mref.reset(new int8_t[n]); nhash.reset(new uint64_t[n]); }
     // Two passes over the records, each on all threads.  Pass A fills what the admission reads (position, flag, mapping
     // quality, CIGAR, offsets, mate fields); pass B copies the payload (1.5 bytes per base) and makes the A/C/G/T hint.
     // The admission (htslib's bam_plp_push rule and the mate-overlap hash: sequential by definition) runs on a thread of
@@ -465,6 +466,9 @@ static std::string pack(lvc_reads* r, const Rec* recs, const size_t n, int min_m
         if (mpos)
             for (size_t i = b0; i < b1; ++i) {
                 mpos[i] = recs[i].next_pos; tlen[i] = recs[i].tlen; mref[i] = recs[i].next_ref;
+                // (every read's name may be looked up: a read that leaves the pileup, or is dropped at the depth cap,
+                // removes the entry of its NAME, as htslib's overlap_remove does)
+                nhash[i] = lvc_overlap::name_hash64(recs[i].name, recs[i].l_name);
                 pair_here |= (recs[i].flag & 0x3u) == 0x3u && !(recs[i].flag & 0x8u);
             }
         if (pair_here) any_pair_seen.store(true, std::memory_order_relaxed);
@@ -487,7 +491,8 @@ static std::string pack(lvc_reads* r, const Rec* recs, const size_t n, int min_m
         rc = lvc_overlap::admit_core((uint32_t)n, r->pos, r->flag, r->mapq, r->cigar_off, r->cigar, r->seq_off, r->seq4,
                                      r->qual, name, any_pair ? mpos.get() : nullptr, any_pair ? mref.get() : nullptr,
                                      any_pair ? tlen.get() : nullptr, min_mapq, max_depth,
-                                     any_pair ? overlap_model : LVC_OVERLAP_OFF, adm.data(), nullptr, nullptr, &pend);
+                                     any_pair ? overlap_model : LVC_OVERLAP_OFF, adm.data(), nullptr, nullptr, &pend,
+                                     any_pair ? nhash.get() : nullptr);
     };
     std::thread admit_thread;
     if (n_threads > 1) admit_thread = std::thread(admit);

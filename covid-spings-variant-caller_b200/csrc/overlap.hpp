@@ -110,10 +110,59 @@ struct ReadRef {
 static inline uint32_t seqi(const uint8_t* s, int64_t i) { return (s[i >> 1] >> ((~i & 1) << 2)) & 15u; }
 static inline uint8_t scale08(uint8_t q) { return (uint8_t)(0.8 * q); }
 
+// the rule for one reference position both mates cover with a base (htslib tweak_overlap_quality)
+static inline void rewrite_base(uint8_t& qa, uint8_t& qb, bool same_base, bool legacy, uint8_t amul, uint8_t bmul) {
+    if (same_base) {
+        const int q = (int)qa + (int)qb;
+        const uint8_t qq = (uint8_t)(q > 200 ? 200 : q);
+        if (legacy) { qa = qq; qb = 0; }
+        else { qa = (uint8_t)(amul * qq); qb = (uint8_t)(bmul * qq); }
+    } else if (legacy) {
+        if (qa >= qb) { qa = scale08(qa); qb = 0; }
+        else { qb = scale08(qb); qa = 0; }
+    } else {
+        if (qa > qb) { qa = scale08(qa); qb = 0; }
+        else if (qa < qb) { qb = scale08(qb); qa = 0; }
+        else { qa = (uint8_t)((amul * 0.8) * qa); qb = (uint8_t)((bmul * 0.8) * qb); }
+    }
+}
+
+// a read whose CIGAR is [clips] ONE match op [clips] (the usual short read): first query index and length of the match
+struct SimpleMatch { bool ok; int64_t q0, len; };
+static inline SimpleMatch simple_match(const ReadRef& r) {
+    SimpleMatch m{false, 0, 0};
+    uint32_t k = 0;
+    while (k < r.n_cig && ((r.cig[k] & 15u) == 4 || (r.cig[k] & 15u) == 5)) { if ((r.cig[k] & 15u) == 4) m.q0 += r.cig[k] >> 4; ++k; }
+    if (k >= r.n_cig) return m;
+    const uint32_t op = r.cig[k] & 15u;
+    if (!(op == 0 || op == 7 || op == 8)) return m;
+    m.len = r.cig[k] >> 4;
+    ++k;
+    while (k < r.n_cig && ((r.cig[k] & 15u) == 4 || (r.cig[k] & 15u) == 5)) ++k;
+    m.ok = k == r.n_cig && m.len > 0 && m.q0 + m.len <= r.l_qseq;
+    return m;
+}
+
 // htslib tweak_overlap_quality(a = the buffered first read, b = the read being pushed).  `a_keeps`: model 1.13 picks the
 // mate that keeps the combined quality by the name hash; model 1.10 always keeps a.  Returns the number of rewritten
 // positions.
 static inline uint64_t tweak(const ReadRef& a, const ReadRef& b, int model, bool a_keeps) {
+    {
+        // Two reads of one match op each (clips aside): the walk below visits exactly the reference positions
+        // [b.pos, min(end of a, end of b)) with both cursors on a base, so the rule can be applied in a plain loop.
+        const SimpleMatch ma = simple_match(a), mb = simple_match(b);
+        if (ma.ok && mb.ok && b.pos >= a.pos) {
+            const bool legacy = model == LVC_OVERLAP_HTSLIB_1_10;
+            const uint8_t amul = legacy ? 1 : (a_keeps ? 1 : 0), bmul = legacy ? 0 : (a_keeps ? 0 : 1);
+            const int64_t hi = a.pos + ma.len < b.pos + mb.len ? a.pos + ma.len : b.pos + mb.len;
+            uint64_t touched = 0;
+            for (int64_t r = b.pos; r < hi; ++r, ++touched) {
+                const int64_t ia = ma.q0 + (r - a.pos), ib = mb.q0 + (r - b.pos);
+                rewrite_base(a.qual[ia], b.qual[ib], seqi(a.seq4, ia) == seqi(b.seq4, ib), legacy, amul, bmul);
+            }
+            return touched;
+        }
+    }
     Cursor ca{a.cig, a.cig + a.n_cig, a.cig}, cb{b.cig, b.cig + b.n_cig, b.cig};
     int64_t iref = b.pos;
     int a_ret = cursor_set(ca, iref - a.pos);
@@ -155,22 +204,8 @@ static inline uint64_t tweak(const ReadRef& a, const ReadRef& b, int model, bool
             }
         }
         if (ca.iseq < 0 || cb.iseq < 0 || ca.iseq >= a.l_qseq || cb.iseq >= b.l_qseq) return touched;   // bad CIGAR
-        uint8_t& qa = a.qual[ca.iseq];
-        uint8_t& qb = b.qual[cb.iseq];
         ++touched;
-        if (seqi(a.seq4, ca.iseq) == seqi(b.seq4, cb.iseq)) {
-            const int q = (int)qa + (int)qb;
-            const uint8_t qq = (uint8_t)(q > 200 ? 200 : q);
-            if (legacy) { qa = qq; qb = 0; }
-            else { qa = (uint8_t)(amul * qq); qb = (uint8_t)(bmul * qq); }
-        } else if (legacy) {
-            if (qa >= qb) { qa = scale08(qa); qb = 0; }
-            else { qb = scale08(qb); qa = 0; }
-        } else {
-            if (qa > qb) { qa = scale08(qa); qb = 0; }
-            else if (qa < qb) { qb = scale08(qb); qa = 0; }
-            else { qa = (uint8_t)((amul * 0.8) * qa); qb = (uint8_t)((bmul * 0.8) * qb); }
-        }
+        rewrite_base(a.qual[ca.iseq], b.qual[cb.iseq], seqi(a.seq4, ca.iseq) == seqi(b.seq4, cb.iseq), legacy, amul, bmul);
     }
     return touched;
 }
@@ -184,6 +219,68 @@ struct NameHash {
         uint64_t h = 1469598103934665603ull;
         for (uint32_t i = 0; i < k.n; ++i) { h ^= (uint8_t)k.p[i]; h *= 1099511628211ull; }
         return (size_t)h;
+    }
+};
+
+// 64-bit hash of a read name (what the name table below is keyed by; the ingest computes it for every read on all threads
+// before the sequential admission pass)
+static inline uint64_t name_hash64(const char* p, uint32_t n) {
+    uint64_t h = 1469598103934665603ull;
+    for (uint32_t i = 0; i < n; ++i) { h ^= (uint8_t)p[i]; h *= 1099511628211ull; }
+    h ^= h >> 32; h *= 0x9E3779B97F4A7C15ull; h ^= h >> 29;
+    return h;
+}
+
+// The overlap hash of htslib's pileup iterator (name -> buffered read), as an open-addressing table of (hash, read):
+// linear probing, deletion by backward shift, names compared only where the 64-bit hashes agree.  Real paired data
+// sends every read through it up to three times (lookup / insert, removal when the mate arrives, removal when the read
+// leaves the pileup); a node-based map spends ~200 ns per read there, which made the admission pass the longest phase
+// of the ingest on files whose mates overlap.
+struct NameTable {
+    struct Slot { uint64_t h; uint32_t idx1; };          // idx1 = read index + 1, 0 = free
+    std::vector<Slot> t;
+    size_t mask = 0, count = 0;
+    bool empty() const { return count == 0; }
+    void grow() {
+        std::vector<Slot> old;
+        old.swap(t);
+        const size_t cap = old.empty() ? 1024 : old.size() * 2;
+        t.assign(cap, Slot{0, 0});
+        mask = cap - 1;
+        for (const Slot& s : old)
+            if (s.idx1) { size_t k = (size_t)s.h & mask; while (t[k].idx1) k = (k + 1) & mask; t[k] = s; }
+    }
+    // slot of the entry whose name equals that of the probe (same(read) compares the names), or -1
+    template <class SameFn>
+    long find(uint64_t h, SameFn same) const {
+        if (!count) return -1;
+        for (size_t k = (size_t)h & mask;; k = (k + 1) & mask) {
+            if (!t[k].idx1) return -1;
+            if (t[k].h == h && same(t[k].idx1 - 1)) return (long)k;
+        }
+    }
+    void insert(uint64_t h, uint32_t idx) {               // the name is known to be absent
+        if ((count + 1) * 2 > t.size()) grow();
+        size_t k = (size_t)h & mask;
+        while (t[k].idx1) k = (k + 1) & mask;
+        t[k] = Slot{h, idx + 1};
+        ++count;
+    }
+    void erase(long at) {
+        size_t k = (size_t)at;
+        for (;;) {                                        // close the gap: move back every entry the gap separates from its home
+            size_t j = k;
+            for (;;) {
+                j = (j + 1) & mask;
+                if (!t[j].idx1) { t[k].idx1 = 0; --count; return; }
+                const size_t home = (size_t)t[j].h & mask;
+                // the entry at j may move to k iff its home is NOT cyclically in (k, j]
+                const bool stays = k <= j ? (home > k && home <= j) : (home > k || home <= j);
+                if (!stays) break;
+            }
+            t[k] = t[j];
+            k = j;
+        }
     }
 };
 
@@ -202,14 +299,21 @@ static int admit_core(uint32_t n, const int32_t* pos, const uint16_t* flag, cons
                       const uint32_t* cigar, const uint64_t* seq_off, const uint8_t* seq4, uint8_t* qual, NameFn name,
                       const int32_t* mate_pos, const int8_t* mate_ref, const int32_t* tlen, int min_mq, int max_depth,
                       int overlap_model, uint8_t* keep, uint64_t* n_pairs, uint64_t* n_bases,
-                      std::vector<PendingTweak>* pending = nullptr) {
+                      std::vector<PendingTweak>* pending = nullptr, const uint64_t* name_hash = nullptr) {
     constexpr uint32_t kFilter = 0x4u | 0x100u | 0x200u | 0x400u;
     const bool ov = overlap_model != LVC_OVERLAP_OFF;
     std::vector<uint32_t> ring;            // buffered reads per end position
     std::vector<uint32_t> ring_head;       // overlap handling: list of the reads that end there (index + 1)
     std::vector<uint32_t> next_in_slot;    // linked through this
     if (ov) next_in_slot.assign(n, 0);
-    std::unordered_map<NameKey, uint32_t, NameHash> olap;
+    NameTable olap;
+    // name_hash (optional): name_hash64 of every read's name, made beforehand; else hashed here
+    auto hash_of = [&](uint32_t i) { if (name_hash) return name_hash[i]; const NameKey k = name(i); return name_hash64(k.p, k.n); };
+    auto find_name = [&](uint32_t i, uint64_t h) {
+        const NameKey key = name(i);
+        return olap.find(h, [&](uint32_t j) { return j == i || name(j) == key; });
+    };
+    auto erase_name = [&](uint32_t i) { const long at = find_name(i, hash_of(i)); if (at >= 0) olap.erase(at); };
     int64_t ring_base = 0;
     auto ring_add = [&](int64_t e, int64_t p, uint32_t i) {
         if (ring.empty()) { ring.assign(4096, 0); if (ov) ring_head.assign(4096, 0); ring_base = p; }
@@ -249,7 +353,7 @@ static int admit_core(uint32_t n, const int32_t* pos, const uint16_t* flag, cons
         const int64_t p = pos[i], e = p + rlen;
         if (p < max_pos) return LVC_EUNSORTED;
         if (p == iter_pos && nbuf + 1 > (int64_t)max_depth) {       // bam_plp_push: cnt > maxcnt -> overlap_remove, drop
-            if (ov && !olap.empty()) olap.erase(name(i));
+            if (ov && !olap.empty()) erase_name(i);
             continue;
         }
         max_pos = p;
@@ -273,17 +377,17 @@ static int admit_core(uint32_t n, const int32_t* pos, const uint16_t* flag, cons
                 // (nothing is buffered: the lookup cannot hit, and a read that is not added either never has its name
                 // touched -- the name bytes live in the inflated file, one cache miss per read)
                 const bool add = overlap_model == LVC_OVERLAP_HTSLIB_1_10 ? true : (mp >= p || ((f & 0x1u) && mp == -1));
+                const uint64_t hi = hash_of(i);
                 if (olap.empty()) {
-                    if (add) olap.emplace(name(i), i);
+                    if (add) olap.insert(hi, i);
                     goto pushed;
                 }
-                const NameKey key = name(i);
-                auto it = olap.find(key);
-                if (it == olap.end()) {
-                    if (add) olap.emplace(key, i);
+                const long at = find_name(i, hi);
+                if (at < 0) {
+                    if (add) olap.insert(hi, i);
                 } else {
-                    const uint32_t a = it->second;
-                    olap.erase(it);
+                    const uint32_t a = olap.t[(size_t)at].idx1 - 1;
+                    olap.erase(at);
                     const bool a_keeps = (wang_hash(x31_hash(name(a).p, name(a).n)) & 1u) != 0;
                     if (pending) pending->push_back(PendingTweak{a, i, a_keeps});
                     else {
@@ -303,7 +407,7 @@ static int admit_core(uint32_t n, const int32_t* pos, const uint16_t* flag, cons
                 ring[off] = 0;
                 if (ov) {
                     if (!olap.empty())
-                        for (uint32_t r = ring_head[off]; r; r = next_in_slot[r - 1]) { olap.erase(name(r - 1)); if (olap.empty()) break; }
+                        for (uint32_t r = ring_head[off]; r; r = next_in_slot[r - 1]) { erase_name(r - 1); if (olap.empty()) break; }
                     ring_head[off] = 0;
                 }
             }

@@ -213,3 +213,42 @@ def test_native_ingest_many_overlapping_pairs(lib, tmp_path):
         assert np.array_equal(nb.qual[:py.n_qual], py.qual[:py.n_qual]), nt
         assert np.array_equal(nb.keep, py.keep), nt
         nat.close()
+
+
+@pytest.mark.parametrize("model", MODELS)
+def test_rewrite_single_match_reads(lib, model):
+    """mates whose CIGAR is [clips] one match op [clips] take a plain loop over the shared positions instead of the cursor
+    walk: same result as the literal htslib emulation, for every geometry (mate inside the first read, starting at its
+    last base, just past its end, equal starts) and both release models"""
+    rng = random.Random(2026)
+    reads = []
+    for k in range(400):
+        p1 = rng.randint(0, 300)
+        l1, l2 = rng.randint(1, 80), rng.randint(1, 80)
+        p2 = p1 + rng.choice([0, 0, l1 - 1, l1, l1 + 3, rng.randint(0, l1)])
+
+        def cig(l):
+            ops = []
+            if rng.random() < 0.2: ops.append((5, rng.randint(1, 5)))
+            if rng.random() < 0.4: ops.append((4, rng.randint(1, 9)))
+            ops.append((rng.choice([0, 0, 7, 8]), l))
+            if rng.random() < 0.4: ops.append((4, rng.randint(1, 9)))
+            if rng.random() < 0.2: ops.append((5, rng.randint(1, 5)))
+            return ops, sum(n for o, n in ops if o in (0, 4, 7, 8))
+        c1, lq1 = cig(l1)
+        c2, lq2 = cig(l2)
+        s1 = "".join(rng.choice("ACGT") for _ in range(lq1))
+        s2 = "".join(rng.choice("AACGT") for _ in range(lq2))
+        q1 = [rng.choice([2, 12, 23, 37, 37, 40, 100, 120]) for _ in range(lq1)]
+        q2 = [rng.choice([2, 12, 23, 37, 37, 40, 100, 120]) for _ in range(lq2)]
+        tl = p2 + l2 - p1
+        reads.append(po.Read(99, p1, 60, c1, s1, q1, f"s{k}", p2, 1, tl))
+        reads.append(po.Read(147, p2, 60, c2, s2, q2, f"s{k}", p1, 1, -tl))
+    reads = po.samtools_sort(reads)
+    b, got = product_rewrite(reads, model)
+    want, admitted = oracle_rewrite(reads, model)
+    changed = 0
+    for i, r in enumerate(reads):
+        assert got[i] == want[i], (i, r.name, r.cigar)
+        changed += got[i] != list(r.qual)
+    assert changed > 300
