@@ -99,6 +99,8 @@ def in_form(batch):
 
 
 def form_of(batch) -> str:
+    if batch.qcode is not None and getattr(batch, "scode", None) is not None:
+        return "2-bit quality codes + 2-bit base codes (lvc_batch.qual_bits = 2, seq_form = 2), 0.5 B per base"
     return "2-bit quality codes (lvc_batch.qual_bits = 2), 0.75 B per base" if batch.qcode is not None else \
         "phred bytes, 1.5 B per base"
 
@@ -631,6 +633,9 @@ def main():
     ap.add_argument("--device-batch", default="admitted", choices=["admitted", "masked"],
                     help="admitted: the device-resident batch holds the admitted reads only, as the packer hands it over "
                          "(ReadBatch.admitted_only / lvc_reads_compact); masked: dropped reads stay in the batch with keep bit0 clear")
+    ap.add_argument("--base-form", default="codes", choices=["codes", "nibbles"],
+                    help="end-to-end legs: codes = a quality-code batch also ships 2-bit base codes where its bases allow it "
+                         "(what process_bam does; 0.5 payload bytes per base over PCIe); nibbles: 4-bit BAM codes (0.75)")
     ap.add_argument("--quality-form", default="codes", choices=["codes", "bytes"],
                     help="codes: batches whose qualities take <= 4 values ship 2-bit codes (what process_bam does); bytes: one phred byte per base")
     args = ap.parse_args()
@@ -742,9 +747,14 @@ def main():
     lvc._handle.set_stream(stream.cuda_stream)
     lvc._handle.set_impl(args.kernel_impl)
 
+    e2e_forms = []
+
     def run_e2e(b):
         """process_batch(page-locked SoA) + prepare_variants, e2e_steps times between two events; (ms, h2d bytes per
         step, records)"""
+        if args.base_form == "codes":
+            b = b.with_base_codes(THRESH["minBQ"])
+        e2e_forms.append(form_of(b))
         pinned = packing.pin_batch(b)
         small = sum(getattr(b, k).nbytes for k in ("pos", "flag", "mapq", "keep", "cigar_off", "cigar", "seq_off"))
         lvc.reset_memory()
@@ -871,7 +881,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms / args.e2e_steps, "steps": args.e2e_steps,
                     "api": "LiveVariantCaller.process_batch(pinned SoA, admitted at pack time) + prepare_variants()",
-                    "batch_form": form_of(batch) + "; reads the admission dropped are left out of the batch at pack time",
+                    "batch_form": e2e_forms[0] + "; reads the admission dropped are left out of the batch at pack time",
                     "keep_masked_batch": {"ms_per_step": e2e_masked_ms / args.e2e_steps, "h2d_bytes_per_step": int(h2d_masked),
                                           "value": world * bases * args.e2e_steps / (e2e_masked_ms * 1e-3),
                                           "note": "the same step with the dropped reads still in the batch (keep bit clear)"},

@@ -64,7 +64,6 @@ __device__ __forceinline__ void deposit_read_general(const BatchView& b, const T
         atomicAdd(PEER ? covdiff_cell(tv, pos + rlen) : tv.covdiff + pos + rlen, -1);
     }
     const uint64_t qb = b.seq_off[i];
-    const uint8_t* seq = b.seq4 + (qb >> 1);
     const uint32_t ord = dp.ord_base + i;
     int64_t r = pos;
     uint32_t qi = 0;
@@ -74,9 +73,7 @@ __device__ __forceinline__ void deposit_read_general(const BatchView& b, const T
             for (uint32_t j = 0; j < len; ++j, ++qi, ++r) {
                 const uint32_t q = batch_qual(b, qb + qi);
                 if ((int)q < dp.min_bq) continue;
-                const uint32_t byte = seq[qi >> 1];
-                const uint32_t nib = (qi & 1u) ? (byte & 15u) : (byte >> 4);
-                deposit_base<PEER>(tv, dp, r, nib, q, ord);
+                deposit_base<PEER>(tv, dp, r, batch_nibble(b, qb + qi), q, ord);
             }
         } else if (op == 2 || op == 3) {
             // deletion / ref-skip entries are kept iff the NEXT query base passes the quality rule
@@ -168,12 +165,13 @@ __device__ __forceinline__ void deposit_read_warp_impl(const BatchView& b, const
     }
     // (byte form; a quality-code batch keeps its codes at a quarter of the offset and is read through batch_qual)
     const uint8_t* qual = b.qual + (b.qbits == 2u ? (qb >> 2) : qb);
-    const uint8_t* seq = b.seq4 + (qb >> 1);
+    // (bases: 4-bit codes at half the offset, or 2-bit codes at a quarter of it: read through batch_nibble)
+    const uint8_t* seq = b.seq4 + (b.sbits == 2u ? (qb >> 2) : (qb >> 1));
     // request the read's whole payload now (one line per lane): the per-run loads below then hit L1 instead of
     // paying a DRAM latency per run
     for (uint32_t off = lane * 128u; off < lq; off += 32u * 128u) {
         if (b.qbits != 2u || off < (lq + 3) / 4) asm volatile("prefetch.global.L1 [%0];" ::"l"(qual + off));
-        if (off < (lq + 1) / 2) asm volatile("prefetch.global.L1 [%0];" ::"l"(seq + off));
+        if (off < (b.sbits == 2u ? (lq + 3) / 4 : (lq + 1) / 2)) asm volatile("prefetch.global.L1 [%0];" ::"l"(seq + off));
     }
     const uint32_t ord = dp.ord_base + i;
     uint32_t ring_head = 0, ring_n = 0;
@@ -215,9 +213,7 @@ __device__ __forceinline__ void deposit_read_warp_impl(const BatchView& b, const
                 for (uint32_t j = lane; j < lenk; j += 32) {
                     const uint32_t q = batch_qual(b, qb + qi + j);
                     if ((int)q < dp.min_bq) continue;
-                    const uint32_t byte = seq[(qi + j) >> 1];
-                    const uint32_t nib = ((qi + j) & 1u) ? (byte & 15u) : (byte >> 4);
-                    deposit_base<PEER>(tv, dp, r + j, nib, q, ord);
+                    deposit_base<PEER>(tv, dp, r + j, batch_nibble(b, qb + qi + j), q, ord);
                 }
             } else if (!dp.replay) {
                 // deletion / ref-skip entries are kept iff the NEXT query base passes the quality rule
@@ -250,8 +246,7 @@ __device__ __forceinline__ void deposit_read_warp_impl(const BatchView& b, const
                 const uint32_t co = __shfl_sync(0xFFFFFFFFu, c, ko);
                 const uint32_t qo = __shfl_sync(0xFFFFFFFFu, q_off, ko), ro = __shfl_sync(0xFFFFFFFFu, r_off, ko);
                 if (lane < cnt && op_is_match(co & 15u)) {
-                    const uint32_t byte = seq[x >> 1];
-                    deposit_base<PEER>(tv, dp, pos + (int64_t)ro + (x - qo), (x & 1u) ? (byte & 15u) : (byte >> 4), q, ord);
+                    deposit_base<PEER>(tv, dp, pos + (int64_t)ro + (x - qo), batch_nibble(b, qb + x), q, ord);
                 }
                 ring_head = (ring_head + cnt) & (kRingEntries - 1);
                 ring_n -= cnt;

@@ -108,7 +108,10 @@ __device__ __forceinline__ void bs_add(const uint32_t (&a)[N], const uint32_t (&
 // QC: quality-code batch (lvc_batch::qual_bits == 2): `b.qual` holds 2-bit codes, 16 bases per 32-bit word; a group of
 //     16 bases is staged from ONE code word + 8 sequence bytes (0.75 bytes per base instead of 1.5); the key transform is
 //     qc_keys16 (qcode.hpp).  Everything after the keys are staged is the same code.
-template <bool GE_ALL, bool PEER, bool QC = false>
+// B2 (with QC): the batch carries 2-bit BASE codes as well (BatchView::sbits == 2): a group of 16 bases is staged from one
+//     word of quality codes + one word of base codes (0.5 bytes per base); b2_onehot16 (qcode.hpp) turns the base codes
+//     into the one-hot nibbles the 4-bit form holds.  Everything after the keys are staged is the same code.
+template <bool GE_ALL, bool PEER, bool QC = false, bool B2 = false>
 __global__ void __launch_bounds__(kT5Threads, kTile5CtasPerSM)
 k_deposit_tile5(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp, LVC_GC TileParams tp) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -216,6 +219,10 @@ k_deposit_tile5(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
         } else
         for (uint64_t a = q0 + (uint64_t)tid * 128u; a < q1; a += (uint64_t)kT5Threads * 128u)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(b.qual + a));
+        if (B2) {
+            for (uint64_t a = (q0 >> 2) + (uint64_t)tid * 128u; a < ((q1 + 3) >> 2); a += (uint64_t)kT5Threads * 128u)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(b.seq4 + a));
+        } else
         for (uint64_t a = (q0 >> 1) + (uint64_t)tid * 128u; a < ((q1 + 1) >> 1); a += (uint64_t)kT5Threads * 128u)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(b.seq4 + a));
     }
@@ -585,8 +592,11 @@ k_deposit_tile5(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
                     // with 5 CTAs per SM the load latency is covered by the other CTAs.  One group per iteration is 8 % slower.)
                     // the same for a quality-code batch: one word of 16 codes + 8 sequence bytes -> 16 keys
                     auto stage_group_qc = [&](uint32_t gg, uint32_t w, const uint2& sraw) {
-                        const uint32_t s0 = bitsel(sraw.x >> 4, sraw.x << 4, 0x0F0F0F0Fu);
-                        const uint32_t s1 = bitsel(sraw.y >> 4, sraw.y << 4, 0x0F0F0F0Fu);
+                        // base nibbles in little-endian nibble order: from the 4-bit form by swapping the nibbles of every
+                        // byte, from the 2-bit form (sraw.x = 16 codes) by b2_onehot16
+                        uint32_t s0, s1;
+                        if (B2) b2_onehot16(sraw.x, s0, s1);
+                        else { s0 = bitsel(sraw.x >> 4, sraw.x << 4, 0x0F0F0F0Fu); s1 = bitsel(sraw.y >> 4, sraw.y << 4, 0x0F0F0F0Fu); }
                         uint32_t k0, k1;
                         qc_keys16(s0, s1, w, tp.qc_pcode, k0, k1);
                         if (tp.qc_cold) {
@@ -613,7 +623,19 @@ k_deposit_tile5(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
                         asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(k_smem + 8u * gg), "r"(k0), "r"(k1) : "memory");
                     };
                     if (warp == 0 && cmin < cmax) slab_setup(cmin);
-                    if (QC) {
+                    if (QC && B2) {
+                        const uint32_t* gc = reinterpret_cast<const uint32_t*>(b.qual + (qbeg >> 2));
+                        const uint32_t* gb = reinterpret_cast<const uint32_t*>(b.seq4 + (qbeg >> 2));
+                        for (uint32_t g = tid; g < n_grp; g += 2 * kT5Threads) {
+                            const bool hasB = g + kT5Threads < n_grp;
+                            const uint32_t wA = __ldcs(gc + g);
+                            const uint32_t bA = __ldcs(gb + g);
+                            uint32_t wB = 0, bB = 0;
+                            if (hasB) { wB = __ldcs(gc + g + kT5Threads); bB = __ldcs(gb + g + kT5Threads); }
+                            stage_group_qc(g, wA, make_uint2(bA, 0));
+                            if (hasB) stage_group_qc(g + kT5Threads, wB, make_uint2(bB, 0));
+                        }
+                    } else if (QC) {
                         const uint32_t* gc = reinterpret_cast<const uint32_t*>(b.qual + (qbeg >> 2));
                         for (uint32_t g = tid; g < n_grp; g += 2 * kT5Threads) {
                             const bool hasB = g + kT5Threads < n_grp;

@@ -32,6 +32,8 @@ struct lvc_reads {
     uint8_t* qcode = nullptr;                        // 2-bit quality codes (lvc_batch::qual_bits == 2) when the file qualifies
     uint8_t qdict[4] = {0, 0, 0, 0};
     bool codes_tried = false;                        // the code form is made on the first lvc_reads_batch
+    uint8_t* scode = nullptr;                        // 2-bit base codes (lvc_batch::seq_form) made by lvc_reads_batch_for
+    int scode_min_bq = -1;                           // the base-quality threshold they were made for (-1: not tried)
     int n_threads = 1;
     bool pinned = false;
     uint64_t overlap_pairs = 0, overlap_bases = 0;   // mate pairs / quality bytes rewritten by the overlap model
@@ -382,6 +384,8 @@ static int compact(lvc_reads* r, int n_threads) {
     r->seq_off = seq_off; r->seq4 = seq4; r->qual = qual;
     r->n = (uint32_t)m; r->n_cigar = coff[m]; r->n_qual = soff[m];
     if (r->qcode) { release_alloc(r, r->qcode); r->qcode = nullptr; }
+    if (r->scode) { release_alloc(r, r->scode); r->scode = nullptr; }
+    r->scode_min_bq = -1;
     r->codes_tried = false;                                  // made again, for the new layout, when a batch is asked for
     return 1;
 }
@@ -905,7 +909,7 @@ int lvc_reads_overlap_stats(const lvc_reads* r, uint64_t* n_pairs, uint64_t* n_b
 
 int lvc_reads_batch_bytes(const lvc_reads* r, lvc_batch* b) {
     if (!r || !b) return LVC_EINVAL;
-    b->n_reads = r->n; b->qual_bits = 8; b->reserved = 0; b->n_cigar_ops = r->n_cigar; b->n_qual_bytes = r->n_qual;
+    b->n_reads = r->n; b->qual_bits = 8; b->seq_form = 0; b->n_cigar_ops = r->n_cigar; b->n_qual_bytes = r->n_qual;
     b->pos = r->pos; b->flag = r->flag; b->mapq = r->mapq; b->keep = r->keep; b->cigar_off = r->cigar_off;
     b->cigar = r->cigar; b->seq_off = r->seq_off; b->seq4 = r->seq4; b->qual = r->qual;
     memset(b->qual_dict, 0, 4);
@@ -922,6 +926,34 @@ int lvc_reads_batch(const lvc_reads* r, lvc_batch* b) {
         timer.mark("quality codes");
     }
     if (rc == LVC_OK && r->qcode) { b->qual_bits = 2; b->qual = r->qcode; memcpy(b->qual_dict, r->qdict, 4); }
+    return rc;
+}
+
+int lvc_reads_batch_for(const lvc_reads* r, int min_base_quality, lvc_batch* b) {
+    const int rc = lvc_reads_batch(r, b);
+    if (rc != LVC_OK || b->qual_bits != 2 || !r->n || !r->n_qual) return rc;
+    const char* env = getenv("LVC_BASE_CODES");
+    if (env && atoi(env) == 0) return rc;
+    lvc_reads* w = const_cast<lvc_reads*>(r);                // a cache inside the object, as for the quality codes
+    const int mbq = std::max(0, std::min(min_base_quality, 255));
+    // codes made for a threshold stay valid for every higher one; a failed attempt is only repeated for a higher threshold,
+    // under which more non-A/C/G/T bases drop out
+    const bool make = w->scode_min_bq < 0 || (w->scode ? w->scode_min_bq > mbq : w->scode_min_bq < mbq);
+    if (make) {
+        ingest::PhaseTimer timer;
+        if (w->scode) { ingest::release_alloc(w, w->scode); w->scode = nullptr; }
+        uint8_t* codes = (uint8_t*)ingest::host_alloc(w, (size_t)(w->n_qual / 4) + 64);
+        if (codes) {
+            if (lvc::pack_base_codes(w->seq4, w->qual, w->n_qual, w->n, w->keep, w->seq_off, w->cigar_off, w->cigar, mbq,
+                                     w->n_threads, codes)) {
+                memset(codes + (w->n_qual + 3) / 4, 0, 64 - 4);
+                w->scode = codes;
+            } else ingest::release_alloc(w, codes);
+        }
+        w->scode_min_bq = mbq;
+        timer.mark("base codes");
+    }
+    if (r->scode && r->scode_min_bq <= mbq) { b->seq4 = r->scode; b->seq_form = 2u | ((uint32_t)r->scode_min_bq << 8); }
     return rc;
 }
 

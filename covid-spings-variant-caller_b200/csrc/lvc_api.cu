@@ -275,6 +275,10 @@ int lvc_create(lvc_handle** out, int device, int64_t ref_len, const uint8_t* ref
         CU(cudaFuncSetAttribute(k_deposit_tile5<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTile5SmemBytes));
         CU(cudaFuncSetAttribute(k_deposit_tile5<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTile5SmemBytes));
         CU(cudaFuncSetAttribute(k_deposit_tile5<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTile5SmemBytes));
+        CU(cudaFuncSetAttribute(k_deposit_tile5<true, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTile5SmemBytes));
+        CU(cudaFuncSetAttribute(k_deposit_tile5<false, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTile5SmemBytes));
+        CU(cudaFuncSetAttribute(k_deposit_tile5<true, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTile5SmemBytes));
+        CU(cudaFuncSetAttribute(k_deposit_tile5<false, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTile5SmemBytes));
         CU(cudaStreamSynchronize(h->stream));
         return LVC_OK;
     };
@@ -391,6 +395,15 @@ int lvc_pack_quality_codes(const uint8_t* qual, uint64_t n_qual_bytes, uint32_t 
     return lvc::pack_quality_codes(qual, n_qual_bytes, n_reads, keep, seq_off, cigar_off, cigar, n_threads, dict_out, codes_out);
 }
 
+int lvc_pack_base_codes(const uint8_t* seq4, const uint8_t* qual, uint64_t n_qual_bytes, uint32_t n_reads, const uint8_t* keep,
+                        const uint64_t* seq_off, const uint32_t* cigar_off, const uint32_t* cigar, int min_base_quality,
+                        int n_threads, uint8_t* codes_out) {
+    if (!seq4 || !qual || !keep || !seq_off || !cigar_off || !cigar || !codes_out) return LVC_EINVAL;
+    if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    return lvc::pack_base_codes(seq4, qual, n_qual_bytes, n_reads, keep, seq_off, cigar_off, cigar, min_base_quality, n_threads,
+                                codes_out);
+}
+
 // ------------------------------------------------------------------------------------------------
 // deposit
 // ------------------------------------------------------------------------------------------------
@@ -494,6 +507,10 @@ static int launch_deposit(lvc_handle* h, const BatchView& bv, int replay, uint64
                                                   {k_deposit_tile5<false, true>, k_deposit_tile5<false, true, true>}},
                                                  {{k_deposit_tile5<true, false>, k_deposit_tile5<true, false, true>},
                                                   {k_deposit_tile5<true, true>, k_deposit_tile5<true, true, true>}}};
+                  static const T5 t5b2[2][2] = {{k_deposit_tile5<false, false, true, true>, k_deposit_tile5<false, true, true, true>},
+                                                {k_deposit_tile5<true, false, true, true>, k_deposit_tile5<true, true, true, true>}};
+                  if (qc && bv.sbits == 2u) CU(cudaLaunchKernelEx(&cfg, t5b2[h->min_bq <= 0 ? 1 : 0][h->peer_ranks > 1 ? 1 : 0], bv, tv, dp, tp));
+                  else
                   CU(cudaLaunchKernelEx(&cfg, t5[h->min_bq <= 0 ? 1 : 0][h->peer_ranks > 1 ? 1 : 0][qc ? 1 : 0], bv, tv, dp, tp));
               } else if (h->min_bq <= 0) CU(cudaLaunchKernelEx(&cfg, k_deposit_tile4<true>, bv, tv, dp, tp));
               else CU(cudaLaunchKernelEx(&cfg, k_deposit_tile4<false>, bv, tv, dp, tp));
@@ -532,7 +549,7 @@ static int deposit_with_replay(lvc_handle* h, const BatchView& bv, uint64_t n_ci
                                   !((f & 1u) && !(f & 2u));
                 if (live) { lo = std::min<uint64_t>(lo, account->seq_off[i]); hi = std::max<uint64_t>(hi, account->seq_off[i + 1]); }
             }
-            if (hi > lo) { const uint64_t q = ((hi + 15) & ~15ull) - (lo & ~15ull); moved += (account->qual_bits == 2u ? q / 4 : q) + q / 2; }
+            if (hi > lo) { const uint64_t q = ((hi + 15) & ~15ull) - (lo & ~15ull); moved += (account->qual_bits == 2u ? q / 4 : q) + ((account->seq_form & 255u) == 2u ? q / 4 : q / 2); }
         }
         h->h2d_payload_bytes += moved;
     }
@@ -616,12 +633,23 @@ static int validate_batch(lvc_handle* h, const lvc_batch* b) {
         return fail(h, LVC_EINVAL, "lvc_batch has a null array");
     if (b->qual_bits != 0 && b->qual_bits != 8 && b->qual_bits != 2)
         return fail(h, LVC_EINVAL, "lvc_batch.qual_bits must be 0 / 8 (phred bytes) or 2 (codes into qual_dict), not %u", b->qual_bits);
+    const uint32_t sbits = b->seq_form & 255u, s_min_bq = (b->seq_form >> 8) & 255u;
+    if (sbits != 0 && sbits != 4 && sbits != 2)
+        return fail(h, LVC_EINVAL, "lvc_batch.seq_form: base width must be 0 / 4 (BAM nibbles) or 2 (codes), not %u", sbits);
+    if (sbits == 2) {
+        if (b->qual_bits != 2) return fail(h, LVC_EINVAL, "2-bit base codes need 2-bit quality codes (qual_bits = 2)");
+        // bases whose quality is below the threshold the codes were made for are not represented (lvc_pack_base_codes)
+        if ((uint32_t)std::max(h->min_bq, 0) < s_min_bq)
+            return fail(h, LVC_EINVAL, "the batch's 2-bit base codes were made for a base-quality threshold of %u; this handle uses %d",
+                        s_min_bq, h->min_bq);
+    }
     return LVC_OK;
 }
 
 // the batch's quality form as the kernels see it
 static void set_quality_form(BatchView& bv, const lvc_batch* b) {
     bv.qbits = b->qual_bits == 2u ? 2u : 0u;
+    bv.sbits = (b->seq_form & 255u) == 2u ? 2u : 0u;
     bv.qdict = (uint32_t)b->qual_dict[0] | ((uint32_t)b->qual_dict[1] << 8) | ((uint32_t)b->qual_dict[2] << 16) |
                ((uint32_t)b->qual_dict[3] << 24);
 }
@@ -639,10 +667,12 @@ int lvc_push_batch(lvc_handle* h, const lvc_batch* b) {
         {&h->b_pos, b->pos, n * 4, true},           {&h->b_flag, b->flag, n * 2, true},
         {&h->b_mapq, b->mapq, n, true},             {&h->b_keep, b->keep, n, true},
         {&h->b_coff, b->cigar_off, (n + 1) * 4, true}, {&h->b_cig, b->cigar, (size_t)b->n_cigar_ops * 4, true},
-        {&h->b_soff, b->seq_off, (n + 1) * 8, true},   {&h->b_seq, b->seq4, (size_t)(b->n_qual_bytes + 1) / 2, false},
+        {&h->b_soff, b->seq_off, (n + 1) * 8, true},
+        {&h->b_seq, b->seq4, (size_t)((b->seq_form & 255u) == 2u ? (b->n_qual_bytes + 3) / 4 : (b->n_qual_bytes + 1) / 2), false},
         {&h->b_qual, b->qual, (size_t)(b->qual_bits == 2u ? (b->n_qual_bytes + 3) / 4 : b->n_qual_bytes), false},
     };
     const bool qc = b->qual_bits == 2u;
+    const bool b2 = (b->seq_form & 255u) == 2u;              // 2-bit base codes: a quarter byte per base instead of a half
     // LVC_ZC_HEADERS=1: the per-read arrays other than `keep` are read in place too when they are page-locked -- a chunk
     // whose reads were all dropped leaves after its `keep` bytes (copied in bulk) and never asks for the rest
     const void* hdr_alias[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -687,7 +717,8 @@ int lvc_push_batch(lvc_handle* h, const lvc_batch* b) {
         for (; i < n && dense; ++i) dense = (b->keep[i] & 1u) != 0;
     }
     if (dense) {
-        const size_t qb = (size_t)(qc ? (b->n_qual_bytes + 3) / 4 : b->n_qual_bytes), sb = (size_t)(b->n_qual_bytes + 1) / 2;
+        const size_t qb = (size_t)(qc ? (b->n_qual_bytes + 3) / 4 : b->n_qual_bytes);
+        const size_t sb = (size_t)(b2 ? (b->n_qual_bytes + 3) / 4 : (b->n_qual_bytes + 1) / 2);
         if (qb) CU(cudaMemcpyAsync(h->b_qual.p, b->qual, qb, cudaMemcpyHostToDevice, h->stream));
         if (sb) CU(cudaMemcpyAsync(h->b_seq.p, b->seq4, sb, cudaMemcpyHostToDevice, h->stream));
         h->h2d_payload_bytes += qb + sb;
@@ -718,7 +749,8 @@ int lvc_push_batch(lvc_handle* h, const lvc_batch* b) {
                 if (qc) CU(cudaMemcpyAsync((uint8_t*)h->b_qual.p + q0 / 4, b->qual + q0 / 4, (q1 - q0 + 3) / 4, cudaMemcpyHostToDevice, h->stream));
                 else
                 CU(cudaMemcpyAsync((uint8_t*)h->b_qual.p + q0, b->qual + q0, q1 - q0, cudaMemcpyHostToDevice, h->stream));
-                const uint64_t s0 = q0 >> 1, s1 = std::min<uint64_t>((q1 + 1) >> 1, (b->n_qual_bytes + 1) >> 1);
+                const uint64_t s0 = b2 ? q0 >> 2 : q0 >> 1;
+                const uint64_t s1 = b2 ? std::min<uint64_t>((q1 + 3) >> 2, (b->n_qual_bytes + 3) >> 2) : std::min<uint64_t>((q1 + 1) >> 1, (b->n_qual_bytes + 1) >> 1);
                 CU(cudaMemcpyAsync((uint8_t*)h->b_seq.p + s0, b->seq4 + s0, s1 - s0, cudaMemcpyHostToDevice, h->stream));
                 h->h2d_payload_bytes += (qc ? (q1 - q0 + 3) / 4 : (q1 - q0)) + (s1 - s0);
             }

@@ -70,6 +70,7 @@ struct BatchView {
     const uint8_t* qual;
     uint32_t qbits = 0;           // 2: `qual` holds 2-bit codes (four bases per byte, low bits first), phred = byte `code` of qdict
     uint32_t qdict = 0;           // lvc_batch::qual_dict, code 0 in the low byte
+    uint32_t sbits = 0;           // 2: `seq4` holds 2-bit base codes (A,C,G,T = 0..3; four bases per byte, low bits first)
     uint32_t hdr_lazy = 0;        // the per-read arrays other than `keep` sit in host memory (read in place over PCIe): a
                                   // chunk asks for them only after its `keep` bytes say that some read is admitted
 };
@@ -81,6 +82,13 @@ __device__ __forceinline__ uint32_t batch_qual(const BatchView& b, uint64_t x) {
         return (b.qdict >> (8u * c)) & 255u;
     }
     return b.qual[x];
+}
+
+// BAM nibble code of the base with quality index x (= seq_off[read] + query index; seq_off is even), either batch form
+__device__ __forceinline__ uint32_t batch_nibble(const BatchView& b, uint64_t x) {
+    if (b.sbits == 2u) return 1u << (((uint32_t)b.seq4[x >> 2] >> (2u * ((uint32_t)x & 3u))) & 3u);
+    const uint32_t byte = b.seq4[x >> 1];
+    return (x & 1u) ? (byte & 15u) : (byte >> 4);
 }
 
 struct DepositParams {

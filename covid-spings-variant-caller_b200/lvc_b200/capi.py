@@ -36,7 +36,7 @@ class Batch(C.Structure):
     _fields_ = [("n_reads", C.c_uint32), ("qual_bits", C.c_uint32), ("n_cigar_ops", C.c_uint64),
                 ("n_qual_bytes", C.c_uint64), ("pos", C.c_void_p), ("flag", C.c_void_p), ("mapq", C.c_void_p),
                 ("keep", C.c_void_p), ("cigar_off", C.c_void_p), ("cigar", C.c_void_p), ("seq_off", C.c_void_p),
-                ("seq4", C.c_void_p), ("qual", C.c_void_p), ("qual_dict", C.c_uint8 * 4), ("reserved", C.c_uint32)]
+                ("seq4", C.c_void_p), ("qual", C.c_void_p), ("qual_dict", C.c_uint8 * 4), ("seq_form", C.c_uint32)]
 
 
 class Candidate(C.Structure):
@@ -76,6 +76,9 @@ SIGNATURES = [
     ("lvc_reads_compact", C.c_int, [C.c_void_p, C.c_int]),
     ("lvc_pack_quality_codes", C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_int, C.c_void_p, C.c_void_p]),
+    ("lvc_pack_base_codes", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    ("lvc_reads_batch_for", C.c_int, [C.c_void_p, C.c_int, C.POINTER(Batch)]),
     ("lvc_reads_info", C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int),
                                  C.POINTER(C.c_int)]),
     ("lvc_reads_free", None, [C.c_void_p]),
@@ -234,6 +237,22 @@ def pack_quality_codes(qual: np.ndarray, n_qual: int, keep: Optional[np.ndarray]
     return codes, bytes(d)
 
 
+def pack_base_codes(seq4: np.ndarray, qual: np.ndarray, n_qual: int, keep: np.ndarray, seq_off: np.ndarray,
+                    cigar_off: np.ndarray, cigar: np.ndarray, min_base_quality: int, n_threads: int = 0):
+    """lvc_pack_base_codes: 2-bit base codes (uint8 [(n_qual+3)//4 + 64 slack]) or None if a base that can reach the
+    tables (admitted read, quality >= min_base_quality) is not A, C, G or T."""
+    lib = load_library()
+    arrs = [np.ascontiguousarray(seq4, dtype=np.uint8), np.ascontiguousarray(qual, dtype=np.uint8),
+            np.ascontiguousarray(keep, dtype=np.uint8), np.ascontiguousarray(seq_off, dtype=np.uint64),
+            np.ascontiguousarray(cigar_off, dtype=np.uint32), np.ascontiguousarray(cigar, dtype=np.uint32)]
+    codes = np.zeros((n_qual + 3) // 4 + 64, dtype=np.uint8)
+    rc = lib.lvc_pack_base_codes(_ptr(arrs[0]), _ptr(arrs[1]), int(n_qual), int(len(arrs[2])), _ptr(arrs[2]), _ptr(arrs[3]),
+                                 _ptr(arrs[4]), _ptr(arrs[5]), int(min_base_quality), int(n_threads), _ptr(codes))
+    if rc < 0:
+        raise LvcError(rc, "lvc_pack_base_codes failed")
+    return codes if rc == 1 else None
+
+
 class NativeReads:
     """Alignments of one contig read and packed by the native ingest (lvc_read_alignments)."""
 
@@ -280,6 +299,14 @@ class NativeReads:
             self.lib.lvc_reads_batch(self.r, C.byref(self._batch))
             self._batch._keepalive = self
         return self._batch
+
+    def batch_for(self, min_base_quality: int) -> Batch:
+        """lvc_reads_batch_for: `batch` for a handle with this base-quality threshold -- a quality-code batch also carries
+        2-bit base codes when every base that can reach the tables is A, C, G or T (0.5 payload bytes per base)"""
+        b = Batch()
+        self.lib.lvc_reads_batch_for(self.r, int(min_base_quality), C.byref(b))
+        b._keepalive = self
+        return b
 
     def compact(self) -> bool:
         """lvc_reads_compact: leave out the reads the admission dropped (views taken before are invalid)"""
@@ -411,13 +438,16 @@ class Handle:
     # ---- deposit
     @staticmethod
     def make_batch(n_reads, n_cigar, n_qual, pos, flag, mapq, keep, cigar_off, cigar, seq_off, seq4, qual,
-                   qual_dict=None) -> Batch:
-        """`qual_dict` (4 phred values): `qual` holds 2-bit quality codes (lvc_batch::qual_bits == 2), else phred bytes"""
+                   qual_dict=None, base_codes_min_bq=None) -> Batch:
+        """`qual_dict` (4 phred values): `qual` holds 2-bit quality codes (lvc_batch::qual_bits == 2), else phred bytes.
+        `base_codes_min_bq` (with qual_dict): `seq4` holds 2-bit base codes made for that base-quality threshold"""
         b = Batch(int(n_reads), 2 if qual_dict is not None else 0, int(n_cigar), int(n_qual), _ptr(pos), _ptr(flag),
                   _ptr(mapq), _ptr(keep), _ptr(cigar_off), _ptr(cigar), _ptr(seq_off), _ptr(seq4), _ptr(qual))
         if qual_dict is not None:
             for k in range(4):
                 b.qual_dict[k] = int(qual_dict[k])
+        if base_codes_min_bq is not None:
+            b.seq_form = 2 | (max(0, min(int(base_codes_min_bq), 255)) << 8)
         return b
 
     def push_batch(self, batch: Batch):

@@ -46,6 +46,10 @@ class ReadBatch:
     # the phred bytes; `qual` stays for the host side (oracle, BAM writer, tests)
     qcode: Optional[np.ndarray] = None   # uint8 [seq_off[n]/4 (+pad)]
     qdict: Optional[bytes] = None        # 4 phred values
+    # optional 2-bit base codes (lvc_batch seq_form 2; only beside quality codes): when set, as_capi() ships them instead
+    # of the nibbles in `seq4`, which stay for the host side
+    scode: Optional[np.ndarray] = None   # uint8 [seq_off[n]/4 (+pad)]
+    scode_min_bq: int = 0                # the base-quality threshold they were made for
 
     @property
     def n_reads(self) -> int:
@@ -72,7 +76,11 @@ class ReadBatch:
         return int(20 * self.n_reads + 4 * self.n_cigar + ((lq + 1) // 2).sum() + lq.sum() + 52 * ref_len)
 
     def as_capi(self) -> capi.Batch:
-        if self.qcode is not None:
+        if self.qcode is not None and self.scode is not None:
+            b = capi.Handle.make_batch(self.n_reads, self.n_cigar, self.n_qual, self.pos, self.flag, self.mapq,
+                                       self.keep, self.cigar_off, self.cigar, self.seq_off, self.scode, self.qcode,
+                                       qual_dict=self.qdict, base_codes_min_bq=self.scode_min_bq)
+        elif self.qcode is not None:
             b = capi.Handle.make_batch(self.n_reads, self.n_cigar, self.n_qual, self.pos, self.flag, self.mapq,
                                        self.keep, self.cigar_off, self.cigar, self.seq_off, self.seq4, self.qcode,
                                        qual_dict=self.qdict)
@@ -92,6 +100,23 @@ class ReadBatch:
             return self
         out = ReadBatch(self.pos, self.flag, self.mapq, self.keep, self.cigar_off, self.cigar, self.seq_off, self.seq4,
                         self.qual, got[0], got[1])
+        for extra in ("overlap_pairs", "overlap_bases", "_keepalive", "_pins"):
+            if hasattr(self, extra):
+                setattr(out, extra, getattr(self, extra))
+        return out
+
+    def with_base_codes(self, min_base_quality: int, n_threads: int = 0) -> "ReadBatch":
+        """the same quality-code batch carrying 2-bit base codes as well (lvc_pack_base_codes) if every base that can reach
+        the tables of a handle with this base-quality threshold is A, C, G or T; otherwise (or without quality codes) the
+        batch itself.  Arrays are shared."""
+        if self.qcode is None or self.scode is not None or self.n_reads == 0 or self.n_qual == 0:
+            return self
+        codes = capi.pack_base_codes(self.seq4, self.qual, self.n_qual, self.keep, self.seq_off, self.cigar_off, self.cigar,
+                                     min_base_quality, n_threads)
+        if codes is None:
+            return self
+        out = ReadBatch(self.pos, self.flag, self.mapq, self.keep, self.cigar_off, self.cigar, self.seq_off, self.seq4,
+                        self.qual, self.qcode, self.qdict, codes, int(min_base_quality))
         for extra in ("overlap_pairs", "overlap_bases", "_keepalive", "_pins"):
             if hasattr(self, extra):
                 setattr(out, extra, getattr(self, extra))
@@ -298,6 +323,12 @@ def pin_batch(b: ReadBatch) -> ReadBatch:
     """Copy a batch into page-locked host memory so lvc_push_batch's H2D copies run at full PCIe speed.  A batch that
     carries quality codes gets those pinned (they are what is shipped); its phred bytes stay where they are."""
     fields = ["pos", "flag", "mapq", "keep", "cigar_off", "cigar", "seq_off", "seq4"]
+    if b.qcode is not None and b.scode is not None:
+        # quality codes and base codes are what is shipped: the nibbles and the phred bytes stay where they are
+        pins = [_Pinned(getattr(b, f)) for f in fields[:7]] + [_Pinned(b.qcode), _Pinned(b.scode)]
+        out = ReadBatch(*[p.array for p in pins[:7]], b.seq4, b.qual, pins[7].array, b.qdict, pins[8].array, b.scode_min_bq)
+        out._pins = pins
+        return out
     pins = [_Pinned(getattr(b, f)) for f in fields]
     if b.qcode is not None:
         pins.append(_Pinned(b.qcode))

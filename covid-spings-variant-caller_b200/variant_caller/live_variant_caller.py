@@ -119,7 +119,8 @@ class LiveVariantCaller:
             try:
                 reads.compact()                 # reads the admission dropped never reach the device
                 if reads.n_reads:
-                    self._handle.push_batch(reads.batch)
+                    # quality codes where the file qualifies, 2-bit base codes on top where its bases allow it
+                    self._handle.push_batch(reads.batch_for(int(self.minBaseQuality)))
             finally:
                 reads.close()
 

@@ -77,7 +77,8 @@ typedef struct lvc_batch {
     const uint8_t* seq4;       /* [n_qual_bytes/2] */
     const uint8_t* qual;       /* [n_qual_bytes], or [n_qual_bytes/4] codes when qual_bits == 2 */
     uint8_t qual_dict[4];      /* qual_bits == 2: phred value of code 0..3 (unused entries 0) */
-    uint32_t reserved;
+    uint32_t seq_form;         /* bits 0..7: width of a base in `seq4`: 0 or 4 = BAM nibbles, 2 = codes (below);
+                                  bits 8..15: the base-quality threshold 2-bit codes were made for */
 } lvc_batch;
 
 /* Byte qualities -> 2-bit codes (no GPU needed).  Returns the number of distinct values found (1..4) after writing
@@ -89,6 +90,18 @@ typedef struct lvc_batch {
 int lvc_pack_quality_codes(const uint8_t* qual, uint64_t n_qual_bytes, uint32_t n_reads, const uint8_t* keep,
                            const uint64_t* seq_off, const uint32_t* cigar_off, const uint32_t* cigar, int n_threads,
                            uint8_t dict_out[4], uint8_t* codes_out);
+
+/* 4-bit BAM base codes -> 2-bit codes (A, C, G, T = 0..3; the base with quality index x in bits 2*(x & 3) of
+ * codes_out[x >> 2], like the quality codes) [EXT] (no GPU needed).  Only a batch with quality codes (qual_bits = 2) may
+ * carry them: lvc_batch.seq4 = codes_out, lvc_batch.seq_form = 2 | min_base_quality << 8; its payload is then 0.5 bytes
+ * per base.  Returns 1 if every base that can reach the tables is A, C, G or T -- a base of a read the admission dropped,
+ * a base whose quality is below min_base_quality (pileup(min_base_quality=...) never shows it,
+ * live_variant_caller.py:56-60: Illumina writes its N calls with quality 2) and the pad nibble of an odd-length read may be
+ * anything, and get code 0 --, 0 if not (the batch keeps its nibbles); LVC_EINVAL on null arguments.  `qual`: the phred
+ * bytes.  lvc_push_batch refuses such a batch on a handle whose threshold is LOWER than the one the codes were made for. */
+int lvc_pack_base_codes(const uint8_t* seq4, const uint8_t* qual, uint64_t n_qual_bytes, uint32_t n_reads, const uint8_t* keep,
+                        const uint64_t* seq_off, const uint32_t* cigar_off, const uint32_t* cigar, int min_base_quality,
+                        int n_threads, uint8_t* codes_out);
 
 /* One (position, allele) that passed the genotype-stage filters; the host finalises log10/round/
  * formatting with the host libm so the text matches the reference. */
@@ -174,6 +187,10 @@ int lvc_reads_overlap_stats(const lvc_reads* r, uint64_t* n_pairs, uint64_t* n_b
 int lvc_reads_batch(const lvc_reads* r, lvc_batch* batch_out);   /* pointers stay valid until lvc_reads_free; the
                                                                     quality-code form when the file qualifies */
 int lvc_reads_batch_bytes(const lvc_reads* r, lvc_batch* batch_out); /* always one phred byte per base */
+/* lvc_reads_batch for a handle whose base-quality threshold is min_base_quality: a quality-code batch also gets 2-bit
+ * base codes (lvc_pack_base_codes) when its bases allow it -- 0.5 instead of 0.75 payload bytes per base over PCIe.
+ * LVC_BASE_CODES=0 in the environment keeps the nibbles. */
+int lvc_reads_batch_for(const lvc_reads* r, int min_base_quality, lvc_batch* batch_out);
 /* Leaves out the reads the admission dropped (keep bit0 clear: read-level filter, max_depth rule): no kernel reads them,
  * the tables that result are the same, and first-seen ordinals number the admitted reads in the same order.  The arrays
  * are re-packed (batches obtained before the call are invalid).  Returns 1 if reads were removed, 0 if the batch stays

@@ -211,3 +211,108 @@ def packing_qual(reads, mq):
     from lvc_b200 import packing
     b = packing.pack_reads(_tuples(reads), mq)
     return b.qual[:b.n_qual]
+
+
+def _with_ns(reads, q_fail, every=7):
+    """an N with a failing quality in every `every`-th read (what Illumina writes for a no-call)"""
+    out = []
+    for k, r in enumerate(reads):
+        if k % every == 0 and len(r.seq) > 3:
+            j = (k * 13) % len(r.seq)
+            r.seq = r.seq[:j] + "N" + r.seq[j + 1:]
+            r.qual = list(r.qual)
+            r.qual[j] = q_fail
+        out.append(r)
+    return out
+
+
+@pytest.mark.parametrize("impl", [0, 1, 5])
+@pytest.mark.parametrize("tname", ["strict", "loose", "zero"])
+@pytest.mark.parametrize("scen", ["deep_amplicon", "indel_dense", "two_values"])
+def test_base_code_batches_vs_oracle_and_nibbles(lib, tmp_path, scen, tname, impl):
+    """2-bit base codes on top of the quality codes (lvc_batch seq_form 2): no-calls with a failing quality are not
+    represented -- the pileup never shows them --, everything else gives the tables of the oracle and of the nibble form"""
+    cfg = dict(
+        deep_amplicon=dict(seed=112, ref_len=900, n_reads=3000, len_lo=149, len_hi=150, q_lo=0, q_hi=0, indel_rate=0.01, weird=False,
+                           amplicon=(0, 250, 251, 600, 750), qbins=QBINS, planted=((10, 0.5), (300, 0.2), (620, 1.0))),
+        indel_dense=dict(seed=113, ref_len=700, n_reads=500, len_lo=80, len_hi=250, q_lo=0, q_hi=0, indel_rate=0.12, weird=False, qbins=QBINS),
+        two_values=dict(seed=114, ref_len=300, n_reads=300, len_lo=30, len_hi=101, q_lo=0, q_hi=0, indel_rate=0.02, weird=False, qbins=(37, 37, 11, 37)),
+    )[scen]
+    ref, reads = synth_small.make_scenario(**cfg)
+    th = THS[tname]
+    if th["minBQ"] > 11:
+        reads = _with_ns(reads, min(cfg["qbins"]))
+    fa = _fasta(tmp_path, "chrS", ref)
+    raw, coded = _coded(reads, th["minMQ"])
+    b2 = coded.with_base_codes(th["minBQ"])
+    assert b2.scode is not None and (b2.as_capi().seq_form & 255) == 2, "the scenario must qualify for base codes"
+    oc = po.OracleCaller(ref, th["minBQ"], th["minMQ"], th["minDP"], th["minAD"], th["ratio"])
+    oc.process_reads(reads)
+    lvc = _lvc(fa, th, impl=impl)
+    lvc.process_batch(b2)
+    _check_against_golden_memory(lvc, oc.memory, f"{scen}/{tname} base codes vs oracle")
+    ref_run = _lvc(fa, th, impl=impl)
+    ref_run.process_batch(coded)
+    assert_variants_equal(lvc.prepare_variants(), ref_run.prepare_variants(), f"{scen}/{tname} base codes vs nibbles")
+    h, hr = lvc._handle, ref_run._handle
+    ka, kb = set(h.plane_keys().tolist()), set(hr.plane_keys().tolist())
+    for k in sorted(ka | kb):
+        pa = h.copy_plane(k) if k in ka else None
+        pb = hr.copy_plane(k) if k in kb else None
+        if pa is None or pb is None:
+            assert not (pa if pb is None else pb).any(), f"plane {k} exists on one side only and is not empty"
+        else:
+            assert np.array_equal(pa, pb), f"plane {k}"
+    assert np.array_equal(h.copy_dels(), hr.copy_dels()) and np.array_equal(h.copy_covdiff(), hr.copy_covdiff())
+    a, b = h.copy_first(0), hr.copy_first(0)
+    assert (a is None) == (b is None) and (a is None or np.array_equal(a, b)), "first-seen ordinals"
+    lvc.close(); ref_run.close()
+
+
+def test_base_codes_need_the_threshold_they_were_made_for(lib, tmp_path):
+    """codes made for minBQ 30 leave out the no-calls below 30: a handle with a lower threshold must refuse them; a
+    batch with a no-call that passes keeps its nibbles"""
+    from lvc_b200 import capi
+    ref, reads = synth_small.make_scenario(seed=120, ref_len=300, n_reads=200, len_lo=50, len_hi=100, q_lo=0, q_hi=0,
+                                           indel_rate=0.0, weird=False, qbins=QBINS)
+    reads = _with_ns(reads, 12)
+    fa = _fasta(tmp_path, "chrS", ref)
+    raw, coded = _coded(reads, 0)
+    b2 = coded.with_base_codes(30)
+    assert b2.scode is not None
+    assert coded.with_base_codes(12).scode is None              # an N at quality 12 passes a threshold of 12
+    lvc = _lvc(fa, THS["loose"])                                # minBQ 13 < 30
+    with pytest.raises(capi.LvcError):
+        lvc.process_batch(b2)
+    lvc.close()
+    lvc = _lvc(fa, dict(THS["strict"], minBQ=35))               # a higher threshold is fine
+    lvc.process_batch(b2)
+    oc = po.OracleCaller(ref, 35, 20, 10, 5, 0.10)
+    oc.process_reads(reads)
+    _check_against_golden_memory(lvc, oc.memory, "base codes at a higher threshold")
+    lvc.close()
+
+
+def test_process_bam_ships_base_codes(lib, tmp_path):
+    """process_bam on a BAM with instrument-binned qualities and no-calls at quality 2: the native reader hands out
+    quality codes + base codes (lvc_reads_batch_for); records and memory are the oracle's"""
+    from lvc_b200 import samio, capi
+    th = THS["strict"]
+    ref, reads = synth_small.make_scenario(seed=121, ref_len=800, n_reads=2500, len_lo=100, len_hi=151, q_lo=0, q_hi=0,
+                                           indel_rate=0.02, weird=False, qbins=QBINS)
+    reads = _with_ns(reads, 2)
+    bam = str(tmp_path / "b2.bam")
+    samio.write_bam(bam, [("chrS", len(ref))], [(r.flag, r.pos, r.mapq, r.cigar, r.seq, r.qual, f"r{k}") for k, r in enumerate(reads)])
+    nat = capi.NativeReads(bam, None, th["minMQ"])
+    nat.compact()
+    assert (nat.batch_for(30).seq_form & 255) == 2 and nat.batch_for(30).qual_bits == 2
+    assert (nat.batch_for(0).seq_form & 255) == 0               # the no-calls pass a threshold of 0: nibbles
+    nat.close()
+    fa = _fasta(tmp_path, "chrS", ref)
+    lvc = _lvc(fa, th)
+    lvc.process_bam(bam)
+    oc = po.OracleCaller(ref, th["minBQ"], th["minMQ"], th["minDP"], th["minAD"], th["ratio"])
+    oc.process_reads(reads)
+    _check_against_golden_memory(lvc, oc.memory, "process_bam with base codes")
+    assert_variants_equal(lvc.prepare_variants(), oc.prepare_variants(), "process_bam with base codes")
+    lvc.close()

@@ -20,6 +20,7 @@ void keys16(uint32_t s0, uint32_t s1, uint32_t w, uint32_t pcode, uint32_t* out)
 uint32_t cold_flags(uint32_t w, uint32_t cold) { return lvc::qc_cold_flags(w, cold); }
 uint32_t eq_flags(uint32_t w, uint32_t c) { return lvc::qc_eq_flags(w, c); }
 uint32_t spread8(uint32_t v) { return lvc::qc_spread8(v); }
+void onehot16(uint32_t w, uint32_t* out) { lvc::b2_onehot16(w, out[0], out[1]); }
 }
 """
 
@@ -36,6 +37,7 @@ def qc(tmp_path_factory):
         getattr(lib, f).restype = C.c_uint32
         getattr(lib, f).argtypes = [C.c_uint32, C.c_uint32] if f != "spread8" else [C.c_uint32]
     lib.keys16.argtypes = [C.c_uint32] * 4 + [C.POINTER(C.c_uint32)]
+    lib.onehot16.argtypes = [C.c_uint32, C.POINTER(C.c_uint32)]
     return lib
 
 
@@ -148,3 +150,73 @@ def test_native_ingest_compact_and_codes(tmp_path):
     wc = want.with_quality_codes()
     assert bytes(got.qdict) == wc.qdict and np.array_equal(got.qcode[:(got.n_qual + 3) // 4], wc.qcode[:(got.n_qual + 3) // 4])
     nat.close()
+
+
+def test_base_code_transform_matches_base_by_base(qc):
+    """b2_onehot16: 16 two-bit base codes -> the one-hot BAM nibbles (A, C, G, T = 1, 2, 4, 8) the tiled kernel stages"""
+    rng = np.random.default_rng(11)
+    words = [0, 0xFFFFFFFF, 0x55555555, 0xAAAAAAAA, 0x1B1B1B1B] + [int(x) for x in rng.integers(0, 1 << 32, 4000, dtype=np.uint64)]
+    for w in words:
+        out = (C.c_uint32 * 2)()
+        qc.onehot16(w, out)
+        got = [(out[k // 8] >> (4 * (k % 8))) & 15 for k in range(16)]
+        assert got == [1 << ((w >> (2 * k)) & 3) for k in range(16)], hex(w)
+
+
+def _base_codes_restated(b, min_bq):
+    """what lvc_pack_base_codes must produce, base by base; None if a base that can reach the tables is not A/C/G/T"""
+    n_qual = b.n_qual
+    codes = np.zeros((n_qual + 3) // 4, dtype=np.uint8)
+    lq = packing.query_lengths(b.cigar_off, b.cigar)
+    code_of = {1: 0, 2: 1, 4: 2, 8: 3}
+    for i in range(b.n_reads):
+        x0, x1 = int(b.seq_off[i]), int(b.seq_off[i + 1])
+        live = bool(b.keep[i] & 1)
+        for x in range(x0, x1):
+            byte = int(b.seq4[x >> 1])
+            nib = (byte & 15) if (x & 1) else (byte >> 4)
+            if nib not in code_of:
+                if live and x < x0 + int(lq[i]) and int(b.qual[x]) >= min_bq:
+                    return None
+                c = 0
+            else:
+                c = code_of[nib]
+            codes[x >> 2] |= c << (2 * (x & 3))
+    return codes
+
+
+@pytest.mark.parametrize("min_bq", [0, 13, 30])
+def test_base_code_packer_matches_restatement(lib, min_bq):
+    """lvc_pack_base_codes (every thread count) against the base-by-base rule, on reads with odd lengths, ambiguity codes
+    below and above the threshold, dropped reads"""
+    rng = np.random.default_rng(100 + min_bq)
+    rows = []
+    pos = 0
+    for i in range(3000):
+        l = int(rng.integers(1, 60))
+        seq = "".join(rng.choice(list("ACGT"), size=l))
+        qual = [int(q) for q in rng.choice([2, 12, 23, 37], size=l)]
+        if rng.random() < 0.2:                                  # an N with the lowest quality: allowed iff it cannot pass
+            k = int(rng.integers(0, l))
+            seq = seq[:k] + "N" + seq[k + 1:]
+            qual[k] = 2
+        flag = 1024 if rng.random() < 0.1 else 0               # a duplicate: dropped by the admission, may hold anything
+        if flag and rng.random() < 0.5:
+            seq = "R" * l
+        rows.append((flag, pos, 60, [(0, l)], seq, qual))
+        pos += int(rng.integers(0, 3))
+    b = packing.pack_reads(rows, 20)
+    want = _base_codes_restated(b, min_bq)
+    assert (want is None) == (min_bq <= 2)                      # an admitted N at quality 2 passes a threshold of 0 ... 2
+    for nt in (1, 2, 5):
+        got = capi.pack_base_codes(b.seq4, b.qual, b.n_qual, b.keep, b.seq_off, b.cigar_off, b.cigar, min_bq, nt)
+        if want is None:
+            assert got is None
+        else:
+            assert got is not None and np.array_equal(got[:len(want)], want), nt
+    # an admitted ambiguity code with a passing quality: the batch keeps its nibbles
+    rows.append((0, pos, 60, [(0, 4)], "ACRT", [37, 37, 37, 37]))
+    b2 = packing.pack_reads(rows, 20)
+    assert capi.pack_base_codes(b2.seq4, b2.qual, b2.n_qual, b2.keep, b2.seq_off, b2.cigar_off, b2.cigar, 30, 3) is None
+    wb = packing.pack_reads(rows[:-1], 20).with_quality_codes().with_base_codes(30)
+    assert (wb.scode is not None) == (min_bq >= 0) and wb.as_capi().seq_form == (2 | (30 << 8))
