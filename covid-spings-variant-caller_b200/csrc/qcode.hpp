@@ -158,8 +158,15 @@ inline int pack_base_codes(const uint8_t* seq4, const uint8_t* qual, uint64_t nq
         auto code = [](int nib) { return nib == 2 ? 1 : nib == 4 ? 2 : nib == 8 ? 3 : 0; };
         pair[v] = (uint8_t)((is_acgt(v >> 4) && is_acgt(v & 15) ? 0 : 0x80) | code(v >> 4) | (code(v & 15) << 2));
     }
-    // one read: its bases x in [seq_off[i], seq_off[i + 1]) (even bounds), two per step.  An output byte holds the bases
-    // 4k .. 4k + 3: its low half is written with `=`, its high half OR-ed in afterwards (by the same thread, see the cuts)
+    // four bases (two bytes) per lookup: low byte = their codes, bit 8 = one of them is not A/C/G/T
+    static const std::vector<uint16_t> quad = [&] {
+        std::vector<uint16_t> q(65536);
+        for (int v = 0; v < 65536; ++v)
+            q[(size_t)v] = (uint16_t)((pair[v & 255] & 15u) | ((pair[v >> 8] & 15u) << 4) | (((pair[v & 255] | pair[v >> 8]) & 0x80u) << 1));
+        return q;
+    }();
+    // one read: its bases x in [seq_off[i], seq_off[i + 1]) (even bounds).  An output byte holds the bases 4k .. 4k + 3:
+    // its low half is written with `=`, its high half OR-ed in afterwards (by the same thread, see the cuts)
     auto do_read = [&](uint64_t i) -> bool {
         const uint64_t x0 = seq_off[i], x1 = seq_off[i + 1];
         uint64_t lq = 0;
@@ -169,7 +176,7 @@ inline int pack_base_codes(const uint8_t* seq4, const uint8_t* qual, uint64_t nq
         }
         const bool live = (keep[i] & 1u) != 0;
         const uint64_t xe = std::min<uint64_t>(x0 + lq, x1);       // the pad nibble of an odd-length read is not a base
-        for (uint64_t x = x0; x < x1; x += 2) {
+        auto two = [&](uint64_t x) -> bool {                       // the bases x, x + 1 (one byte of nibbles)
             const uint8_t by = seq4[x >> 1], p = pair[by];
             if ((p & 0x80) && live) {
                 if ((!is_acgt(by >> 4) && x < xe && (int)qual[x] >= min_bq) ||
@@ -177,7 +184,18 @@ inline int pack_base_codes(const uint8_t* seq4, const uint8_t* qual, uint64_t nq
             }
             const uint8_t v = (uint8_t)((p & 15u) << (2 * (x & 3)));
             if (x & 2) codes_out[x >> 2] |= v; else codes_out[x >> 2] = v;
+            return true;
+        };
+        uint64_t x = x0;
+        if ((x & 2) && x < x1) { if (!two(x)) return false; x += 2; }
+        for (; x + 4 <= x1; x += 4) {
+            uint16_t w;
+            memcpy(&w, seq4 + (x >> 1), 2);                        // little endian: bases x, x + 1 in the low byte
+            const uint16_t q = quad[w];
+            if ((q & 0x100u) && live) { if (!two(x) || !two(x + 2)) return false; }
+            else codes_out[x >> 2] = (uint8_t)q;
         }
+        if (x < x1 && !two(x)) return false;
         return true;
     };
     // threads take runs of reads that start where seq_off is a multiple of four: no output byte is shared between them
