@@ -61,6 +61,15 @@ typedef struct lvc_handle lvc_handle;
  *   lvc_read_alignments produces this form by itself when a file qualifies (lvc_reads_batch; lvc_reads_batch_bytes
  *   always gives the byte form); lvc_pack_quality_codes converts a byte array.  Code batches run on the generation-5
  *   tiled kernel and the any-record kernel (impl 0, 1 or 5; other selections are refused with LVC_EINVAL).
+ *
+ *   Base codes (seq_form = 2 | threshold << 8) [EXT]: a quality-code batch may carry its bases as 2-bit codes too
+ *   (A, C, G, T = 0..3, the base with quality index x in bits 2*(x & 3) of seq4[x >> 2]; `seq4` then holds
+ *   n_qual_bytes / 4 bytes).  The pileup the reference iterates never shows a base whose quality is below
+ *   min_base_quality (live_variant_caller.py:56-60), so such a base -- every no-call an Illumina instrument writes:
+ *   N at quality 2 --, any base of a read the admission dropped and pad nibbles need no representation; a batch in
+ *   which every OTHER base is A, C, G or T qualifies (lvc_pack_base_codes; lvc_reads_batch_for makes the codes for a
+ *   given threshold).  Tables, records and checkpoints are identical; the payload over PCIe is 0.5 bytes per base.
+ *   A handle whose threshold is lower than the one in seq_form refuses the batch (LVC_EINVAL).
  */
 typedef struct lvc_batch {
     uint32_t n_reads;
