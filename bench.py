@@ -886,8 +886,9 @@ def main():
                                           "value": world * bases * args.e2e_steps / (e2e_masked_ms * 1e-3),
                                           "note": "the same step with the dropped reads still in the batch (keep bit clear)"},
                     "admit_ms": admit_ms,
-                    "h2d_note": "small per-read arrays copied in full + payload read in place over PCIe: the 16-byte "
-                                "groups of each chunk's staged extent, counted by the library"},
+                    "h2d_note": "per-read arrays copied in full; payload of an admitted-only batch copied in bulk (one copy per "
+                                "array), payload of a keep-masked batch read in place over PCIe (the 16-byte groups of each "
+                                "chunk's staged extent): counted by the library"},
             "e2e_api": e2e_api,
             "device_batch": f"{dev_batch.n_reads} reads on the device ({args.device_batch}: " + (
                 "the reads the host admission dropped are left out at pack time, as process_bam does" if args.device_batch == "admitted"
