@@ -183,8 +183,12 @@ k_deposit_tile5(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
     // byte extent of the reads that pass the read-level filter (a superset of what will be deposited):
     // known before the CIGARs arrive, so the bulk copy overlaps classification
     const uint32_t so_rel = hd.so - (uint32_t)so0, so1_rel = hd.so1 - (uint32_t)so0;
+    // "every base of the read is A, C, G or T" (keep bit 1).  A base-code batch holds nothing else by construction: what
+    // was another code had a quality below the threshold and is code 0 now, which the quality test still drops -- so a read
+    // with a no-call takes the tiled path there instead of the one-warp-per-read path
+    const bool acgt = B2 || (hd.keep & 2u);
     {
-        const bool pass = read_passes_filter(hd.flag, hd.mapq, hd.keep, dp.min_mq) && (hd.keep & 2u) &&
+        const bool pass = read_passes_filter(hd.flag, hd.mapq, hd.keep, dp.min_mq) && acgt &&
                           (so1_rel - so_rel) <= kMaxReadBytes && so1_rel > so_rel;
         uint32_t lo = pass ? so_rel : 0xFFFFFFFFu, hi = pass ? so1_rel : 0u;
         lo = __reduce_min_sync(0xFFFFFFFFu, lo);
@@ -240,14 +244,14 @@ k_deposit_tile5(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
         const bool rpass = read_passes_filter(hd.flag, hd.mapq, hd.keep, dp.min_mq);
         // warp-uniform shortcut: every read of the warp that passes the filter is one match op (150M): no CIGAR walk
         const uint32_t l0 = hd.cg0 >> 4;
-        const bool one_m = hd.nc == 1 && op_is_match(hd.cg0 & 15u) && (hd.keep & 2u) && (hd.so1 - hd.so) <= kMaxReadBytes &&
+        const bool one_m = hd.nc == 1 && op_is_match(hd.cg0 & 15u) && acgt && (hd.so1 - hd.so) <= kMaxReadBytes &&
                            l0 >= 1u && l0 <= 65535u;
         if (__all_sync(0xFFFFFFFFu, !rpass || one_m)) {
             if (rpass) {
                 if (hd.pos < 0 || (int64_t)hd.pos + l0 > tv.G) atomicAdd(&tv.status[ST_RANGE_ERR], 1u);
                 else { nr = 1; run_pos[0] = hd.pos; run_len[0] = l0; run_q[0] = 0; rspan = l0; }
             }
-        } else if (__all_sync(0xFFFFFFFFu, !rpass || (hd.nc >= 1u && hd.nc <= 3u && (hd.keep & 2u) &&
+        } else if (__all_sync(0xFFFFFFFFu, !rpass || (hd.nc >= 1u && hd.nc <= 3u && acgt &&
                                                         (hd.so1 - hd.so) <= kMaxReadBytes))) {
             // second warp-uniform shortcut: at most 3 CIGAR ops per read (one indel or soft clips), all of them
             // already in registers: straight-line code, same results as the general walk below
@@ -303,7 +307,7 @@ k_deposit_tile5(LVC_GC BatchView b, LVC_GC TableView tv, LVC_GC DepositParams dp
             }
         } else if (rpass) {
             bool tileable = hd.nc <= (uint32_t)kMaxCigarTile && hd.nc > 0 && (hd.so1 - hd.so) <= kMaxReadBytes &&
-                            (hd.keep & 2u);
+                            acgt;
             uint32_t lq = 0;
             bool any_ref = false;
             if (tileable) {
