@@ -136,23 +136,56 @@ static std::string fail(const char* fmt, ...) {
 // several MB are anonymous mappings aligned to 2 MB with MADV_HUGEPAGE: the inflate threads first-touch the array, and with
 // 4 KB pages those 125,000 page faults per config-2 BAM cost more host time than the decoder itself (measured: 0.53 s of
 // thread time for inflate + walk, of which 0.19 s were faults).  Where transparent huge pages are off the advice is a no-op.
+// One such mapping is parked between calls (live batches arrive every few seconds and have similar sizes): the next file
+// neither faults its pages in again nor pays for unmapping half a gigabyte at the end of the call.  At most kRawParkMax
+// bytes stay parked; LVC_INGEST_PARK=0 disables it.
+struct RawPark {
+    std::mutex mu;
+    void* map = nullptr; size_t map_len = 0;
+};
+static RawPark g_raw_park;
+constexpr size_t kRawParkMax = 2ull << 30;
+
 struct RawBuf {
     uint8_t* p = nullptr; size_t n = 0;
     void* map = nullptr; size_t map_len = 0;
+    static constexpr size_t kHuge = 2u << 20;
     ~RawBuf() { release(); }
+    static uint8_t* aligned(void* q) { return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(q) + kHuge - 1) & ~(uintptr_t)(kHuge - 1)); }
     void release() {
-        if (map) munmap(map, map_len); else free(p);
+        if (map) {
+            const char* env = getenv("LVC_INGEST_PARK");
+            bool parked = false;
+            if (map_len <= kRawParkMax && !(env && atoi(env) == 0)) {
+                std::lock_guard<std::mutex> g(g_raw_park.mu);
+                if (!g_raw_park.map || g_raw_park.map_len < map_len) {      // keep the larger one
+                    if (g_raw_park.map) munmap(g_raw_park.map, g_raw_park.map_len);
+                    g_raw_park.map = map; g_raw_park.map_len = map_len;
+                    parked = true;
+                }
+            }
+            if (!parked) munmap(map, map_len);
+        } else free(p);
         p = nullptr; n = 0; map = nullptr; map_len = 0;
     }
     bool resize(size_t m) {
         release();
-        constexpr size_t kHuge = 2u << 20;
         if (m >= 4 * kHuge) {
             const size_t len = ((m + kHuge - 1) & ~(kHuge - 1)) + kHuge;
+            {
+                // a parked mapping that is large enough, and not more than four times too large
+                std::lock_guard<std::mutex> g(g_raw_park.mu);
+                if (g_raw_park.map && g_raw_park.map_len >= len && g_raw_park.map_len / 4 <= len) {
+                    map = g_raw_park.map; map_len = g_raw_park.map_len;
+                    g_raw_park.map = nullptr; g_raw_park.map_len = 0;
+                    p = aligned(map); n = m;
+                    return true;
+                }
+            }
             void* q = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
             if (q != MAP_FAILED) {
                 map = q; map_len = len;
-                p = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(q) + kHuge - 1) & ~(uintptr_t)(kHuge - 1));
+                p = aligned(q);
 #ifdef MADV_HUGEPAGE
                 madvise(p, len - kHuge, MADV_HUGEPAGE);
 #endif

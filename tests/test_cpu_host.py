@@ -369,3 +369,34 @@ def test_native_inflate_every_deflate_form(lib, tmp_path, monkeypatch):
     with pytest.raises(rejected):
         open(str(tmp_path / "cut.bam"), "wb").write(good[:len(good) // 2])
         native(str(tmp_path / "cut.bam"))
+
+
+def test_native_ingest_reuses_its_parked_inflate_buffer(lib, tmp_path, monkeypatch):
+    """files of more than 8 MB inflate into a huge-page backed mapping that is parked between calls: a second, different
+    file read through the reused mapping (and a file read with LVC_INGEST_PARK=0) gives the arrays of a fresh read"""
+    from lvc_b200 import samio, synth
+    files = []
+    for seed, pairs in ((21, 36_000), (22, 30_000)):
+        ref, batch = synth.amplicon_sample(seed=seed, n_pairs=pairs)[:2]
+        path = str(tmp_path / f"p{seed}.bam")
+        samio.write_bam_batch(path, ("chrS", len(ref)), batch, level=1)
+        files.append((path, batch))
+
+    def read(path):
+        nat = samio.read_alignments_native(path, None, 20, n_threads=4)
+        nb = nat.as_readbatch()
+        out = (nat.n_reads, nb.pos.copy(), nb.keep.copy(), nb.cigar[:nb.n_cigar].copy(), nb.qual[:nb.n_qual].copy(),
+               nb.seq4[:nb.n_qual // 2].copy())
+        nat.close()
+        return out
+
+    monkeypatch.setenv("LVC_INGEST_PARK", "0")
+    fresh = [read(p) for p, _ in files]
+    monkeypatch.delenv("LVC_INGEST_PARK")
+    for rnd in range(2):                                   # big file, smaller file, big file ...: the mapping is reused
+        for k, (p, batch) in enumerate(files):
+            got = read(p)
+            assert got[0] == fresh[k][0] == batch.n_reads
+            for a, b in zip(got[1:], fresh[k][1:]):
+                assert np.array_equal(a, b), (rnd, k)
+            assert np.array_equal(got[4], batch.qual[:batch.n_qual]) and np.array_equal(got[1], batch.pos)
