@@ -844,26 +844,66 @@ static std::string read_sam(lvc_reads* r, const Bytes& file, const char* contig,
     size_t total = 0;
     for (auto& pc : pieces) { if (!pc.err.empty()) return pc.err; total += pc.tmp.size(); }
     timer.mark("sam parse");
-    std::vector<Tmp> tmp;
-    tmp.reserve(total);
-    for (auto& pc : pieces) { tmp.insert(tmp.end(), pc.tmp.begin(), pc.tmp.end()); std::vector<Tmp>().swap(pc.tmp); }
-    // samtools sort: position, forward before reverse strand, input order
-    std::stable_sort(tmp.begin(), tmp.end(), [](const Tmp& a, const Tmp& b) {
-        if (a.rec.pos != b.rec.pos) return a.rec.pos < b.rec.pos;
-        return ((a.rec.flag >> 4) & 1) < ((b.rec.flag >> 4) & 1);
-    });
+    // samtools sort: position, forward before reverse strand, input order.  The records stay where the parser put them;
+    // what is sorted is one 64-bit key per record (position | strand | input index), and a file that is in order already --
+    // the usual case -- is not sorted at all.
+    std::vector<const Tmp*> order(total);
+    {
+        size_t k = 0;
+        for (auto& pc : pieces) for (auto& t : pc.tmp) order[k++] = &t;
+    }
+    bool sorted = true;
+    for (size_t i = 1; i < total && sorted; ++i) {
+        const Rec &x = order[i - 1]->rec, &y = order[i]->rec;
+        sorted = x.pos < y.pos || (x.pos == y.pos && ((x.flag >> 4) & 1) <= ((y.flag >> 4) & 1));
+    }
+    if (!sorted) {
+        if (total >= (1ull << 31)) return fail("too many records in one SAM file");
+        std::vector<uint64_t> key(total);
+        for (size_t i = 0; i < total; ++i) {
+            const Rec& x = order[i]->rec;
+            key[i] = ((uint64_t)(uint32_t)((int64_t)x.pos + 2) << 32) | ((uint64_t)((x.flag >> 4) & 1) << 31) | (uint64_t)i;   // pos >= -1
+        }
+        std::sort(key.begin(), key.end());
+        std::vector<const Tmp*> by_key(total);
+        for (size_t i = 0; i < total; ++i) by_key[i] = order[(size_t)(key[i] & 0x7FFFFFFFu)];
+        order.swap(by_key);
+    }
     timer.mark("sort");
-    std::vector<Rec> recs;
-    recs.reserve(tmp.size());
-    for (auto& t : tmp) {
-        const uint8_t* base = pieces[t.piece].store.data();
-        t.rec.cig = base + t.cig_o; t.rec.seq = base + t.seq_o; t.rec.qual = base + t.qual_o;
-        std::string v = validate(t.rec, "SAM");
-        if (!v.empty()) return v;
-        uint64_t rl = 0;
-        for (uint32_t k = 0; k < t.rec.n_cig; ++k) { uint32_t c; memcpy(&c, t.rec.cig + 4 * k, 4); const uint32_t op = c & 15u; if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) rl += c >> 4; }
-        if (rl == 0) { t.rec.n_cig = 0; t.rec.l_seq = 0; }
-        recs.push_back(t.rec);
+    // pointers, validation and the reference length of every record, on all threads; the error of the first bad record wins
+    std::vector<Rec> recs(total);
+    {
+        std::atomic<size_t> next{0};
+        std::mutex emu;
+        size_t err_at = total;
+        std::string err_msg;
+        auto work = [&]() {
+            for (;;) {
+                const size_t i0 = next.fetch_add(2048);
+                if (i0 >= total) return;
+                for (size_t i = i0; i < std::min(total, i0 + 2048); ++i) {
+                    const Tmp& t = *order[i];
+                    Rec x = t.rec;
+                    const uint8_t* base = pieces[t.piece].store.data();
+                    x.cig = base + t.cig_o; x.seq = base + t.seq_o; x.qual = base + t.qual_o;
+                    std::string v = validate(x, "SAM");
+                    if (!v.empty()) {
+                        std::lock_guard<std::mutex> g(emu);
+                        if (i < err_at) { err_at = i; err_msg = v; }
+                    }
+                    uint64_t rl = 0;
+                    for (uint32_t k = 0; k < x.n_cig; ++k) { uint32_t c; memcpy(&c, x.cig + 4 * k, 4); const uint32_t op = c & 15u; if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) rl += c >> 4; }
+                    if (rl == 0) { x.n_cig = 0; x.l_seq = 0; }
+                    recs[i] = x;
+                }
+            }
+        };
+        const int nt = total < 4096 ? 1 : std::max(1, std::min(n_threads, 64));
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; ++t) th.emplace_back(work);
+        work();
+        for (auto& t : th) t.join();
+        if (err_at < total) return err_msg;
     }
     timer.mark("validate");
     return pack(r, recs.data(), recs.size(), min_mapq, max_depth, n_threads, overlap_model, timer);
